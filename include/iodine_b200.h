@@ -1,0 +1,168 @@
+/*
+ * iodine_b200.h -- C ABI of the B200-native IODINE refinement-loop engine.
+ *
+ * The reference (zhixuan-lin/IODINE) has no FFI of its own: the seam is the Python class
+ * surface of lib/modeling/iodine.py.  Each entry point below names
+ * the reference function it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; iodine_last_error()
+ *     returns a thread-local, NUL-terminated description of the last failure.
+ *   - unless a name ends in _host, every data pointer is a caller-owned DEVICE pointer
+ *     (fp32, contiguous, the reference's own NCHW / [B,K,L] layouts).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
+ *     enqueued on it and nothing synchronises unless stated.
+ *   - a plan is bound to the device that is current at iodine_plan_create() time, is not
+ *     thread-safe and is not re-entrant (mirrors the per-instance state of the reference
+ *     module, iodine.py:37-52).
+ *   - no hidden allocations after iodine_plan_create(): the activation workspace is
+ *     queried with iodine_plan_workspace_bytes() and supplied by the caller.
+ */
+#ifndef IODINE_B200_H_
+#define IODINE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define IODINE_API __attribute__((visibility("default")))
+#else
+#define IODINE_API
+#endif
+
+#define IODINE_ABI_VERSION 1
+#define IODINE_MAX_LAYERS 8
+
+/* arithmetic of the decoder convolutions (everything else is always fp32) */
+enum IodinePrecision {
+  IODINE_FP32 = 0,  /* FFMA, fp32 activations: the exact path                           */
+  IODINE_BF16 = 1,  /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate in TMEM)      */
+  IODINE_TF32 = 2   /* reserved: tcgen05 kind::tf32                                     */
+};
+
+/* Mirrors the cfg.ARCH fields the reference model reads (iodine.py:10-32,
+ * lib/config/defaults.py:35-100) plus the batch geometry. */
+typedef struct IodineShape {
+  int32_t B;           /* images per call handled by this plan (per rank)               */
+  int32_t K;           /* ARCH.SLOTS                                                     */
+  int32_t L;           /* ARCH.DIM_LATENT                                                */
+  int32_t H, W;        /* ARCH.IMG_SIZE (square in the reference; kept separate)        */
+  int32_t T;           /* ARCH.ITERS                                                     */
+  int32_t img_c;       /* ARCH.IMG_CHANNELS, must be 3                                   */
+  int32_t dec_layers;  /* ARCH.DEC.CONV_LAYERS                                           */
+  int32_t dec_chan;    /* ARCH.DEC.CONV_CHAN                                             */
+  int32_t dec_k;       /* ARCH.DEC.KERNEL_SIZE                                           */
+  int32_t ref_layers;  /* ARCH.REF.CONV_LAYERS                                           */
+  int32_t ref_chan;    /* ARCH.REF.CONV_CHAN                                             */
+  int32_t ref_k;       /* ARCH.REF.KERNEL_SIZE                                           */
+  int32_t ref_stride;  /* ARCH.REF.STRIDE                                                */
+  int32_t mlp_units;   /* ARCH.REF.MLP_UNITS                                             */
+  int32_t layernorm;   /* ARCH.LAYERNORM                                                 */
+  float   sigma;       /* ARCH.SIGMA                                                     */
+  int32_t precision;   /* enum IodinePrecision                                           */
+} IodineShape;
+
+/* One pointer per state_dict key of the reference model, PyTorch layouts
+ * (conv OIHW, linear [out,in]), fp32, DEVICE memory.  iodine_plan_set_weights() repacks
+ * them once into kernel layouts held inside the plan. */
+typedef struct IodineWeights {
+  const float* dec_w[IODINE_MAX_LAYERS];  /* decoder.mlc.layers.{i}.weight               */
+  const float* dec_b[IODINE_MAX_LAYERS];  /* decoder.mlc.layers.{i}.bias                 */
+  const float* dec_out_w;                 /* decoder.conv.weight  [4,C,k,k]              */
+  const float* dec_out_b;                 /* decoder.conv.bias    [4]                    */
+  const float* ref_w[IODINE_MAX_LAYERS];  /* refine.mlc.layers.{i}.weight                */
+  const float* ref_b[IODINE_MAX_LAYERS];  /* refine.mlc.layers.{i}.bias                  */
+  const float* mlp_w;                     /* refine.mlp.layers.0.weight [M,Cr]           */
+  const float* mlp_b;                     /* refine.mlp.layers.0.bias                    */
+  const float* lstm_w_ih;                 /* refine.lstm.weight_ih [4M, M+4L]            */
+  const float* lstm_w_hh;                 /* refine.lstm.weight_hh [4M, M]               */
+  const float* lstm_b_ih;                 /* refine.lstm.bias_ih                         */
+  const float* lstm_b_hh;                 /* refine.lstm.bias_hh                         */
+  const float* mean_w;                    /* refine.mean_update.weight [L,M]             */
+  const float* mean_b;                    /* refine.mean_update.bias                     */
+  const float* logvar_w;                  /* refine.logvar_update.weight                 */
+  const float* logvar_b;                  /* refine.logvar_update.bias                   */
+  const float* init_mean;                 /* posterior.init_mean [L]                     */
+  const float* init_logvar;               /* posterior.init_logvar [L]                   */
+} IodineWeights;
+
+typedef struct IodinePlan IodinePlan;
+
+IODINE_API int         iodine_abi_version(void);
+IODINE_API const char* iodine_last_error(void);
+
+/* IODINE.__init__ (iodine.py:8-33): validates the architecture, sizes every buffer. */
+IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_out);
+IODINE_API int iodine_plan_destroy(IodinePlan* plan);
+
+/* bytes of activation workspace the caller must supply (device memory, 1024-B aligned) */
+IODINE_API int iodine_plan_workspace_bytes(const IodinePlan* plan, size_t* bytes_out);
+IODINE_API int iodine_plan_set_workspace(IodinePlan* plan, void* workspace, size_t bytes);
+
+/* nn.Module.load_state_dict for the keys listed in IodineWeights (checkpoint.py:68). */
+IODINE_API int iodine_plan_set_weights(IodinePlan* plan, const IodineWeights* w, void* stream);
+
+/* Gaussian.init_unit (iodine.py:607-618) + `self.lstm_hidden = None` (iodine.py:82):
+ * post_mean/post_logvar[B,K,L] <- init_mean/init_logvar tiled; lstm_h/lstm_c[B*K,M] <- 0 */
+IODINE_API int iodine_init_state(IodinePlan* plan, float* post_mean, float* post_logvar,
+                      float* lstm_h, float* lstm_c, void* stream);
+
+/* One iteration of the loop body of IODINE.encode (iodine.py:83-100): elbo() 161-241,
+ * the five gradients of (B*elbo).backward() 90 in closed form, get_input_encoding()
+ * 243-343, refine() 466-503 and Gaussian.update() 636-651.
+ *   x[B,3,H,W]; eps_t[B,K,L]; post_mean/post_logvar[B,K,L] in-out;
+ *   lstm_h/lstm_c[B*K,M] in-out (true h / true c of nn.LSTMCell);
+ *   elbo_terms_out[2] = { sum_b log-likelihood, sum_b KL } of THIS step (nullable);
+ *   aux_out: nullable; if given receives the reference's normalised refinement input
+ *            [B,K,17,H,W] followed by latent [B,K,4L] (tests only). */
+IODINE_API int iodine_refine_step(IodinePlan* plan, const float* x, const float* eps_t,
+                       float* post_mean, float* post_logvar, float* lstm_h, float* lstm_c,
+                       float* elbo_terms_out, float* aux_out, void* stream);
+
+/* IODINE.elbo (iodine.py:161-241) for given posterior and noise, no gradients:
+ * elbo_terms_out[2] = { sum_b log-likelihood, sum_b KL }. */
+IODINE_API int iodine_elbo(IodinePlan* plan, const float* x, const float* eps_t,
+                const float* post_mean, const float* post_logvar,
+                float* elbo_terms_out, void* stream);
+
+/* IODINE.encode (iodine.py:73-105): eps[T+1,B,K,L]; z_out[B,K,L];
+ * elbo_terms_out[T,2] nullable; post_out[2,B,K,L] nullable (final mean, logvar). */
+IODINE_API int iodine_encode(IodinePlan* plan, const float* x, const float* eps, float* z_out,
+                  float* elbo_terms_out, float* post_out, void* stream);
+
+/* IODINE.decode (iodine.py:59-71): z[B,K,L] -> pred[B,3,H,W], mask[B,K,1,H,W],
+ * mean[B,K,3,H,W] (any output may be NULL). */
+IODINE_API int iodine_decode(IodinePlan* plan, const float* z, float* pred_out, float* mask_out,
+                  float* mean_out, void* stream);
+
+/* IODINE.reconstruct (iodine.py:107-112) = encode + decode. */
+IODINE_API int iodine_reconstruct(IodinePlan* plan, const float* x, const float* eps,
+                       float* pred_out, float* mask_out, float* mean_out, float* z_out,
+                       float* elbo_terms_out, void* stream);
+
+/* Same, HOST buffers (what lib/eval/ari_eval.py:22 + lib/engine/eval.py:27 do around the
+ * call: image.to(device) ... .cpu()).  Copies x and eps host->device, runs reconstruct,
+ * copies the outputs device->host and synchronises the stream.  Host pointers should be
+ * pinned for full PCIe speed.  Staging buffers live inside the caller's workspace. */
+IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, const float* eps_host,
+                            float* pred_host, float* mask_host, float* mean_host,
+                            float* z_host, float* elbo_terms_host, void* stream);
+
+/* Test hook: copy a named internal buffer of the last step to dst (device memory).
+ * names: "out4" [BK,H,W,4], "seed4" [BK,H,W,4], "dz" [BK,L], "act<i>" [BK,H,W,C] (fp32
+ * view of decoder layer i's post-activation), "pool" [BK,Cr], "stats" [BK,4,2] (f64),
+ * "z" [BK,L].  *bytes_out receives the byte count; dst may be NULL to query the size. */
+IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, size_t dst_bytes,
+                      size_t* bytes_out, void* stream);
+
+/* number of kernel launches issued by this plan since creation (bench's gpu_launches) */
+IODINE_API int iodine_plan_launch_count(const IodinePlan* plan, uint64_t* count_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IODINE_B200_H_ */

@@ -1,0 +1,172 @@
+// common.cuh -- shared declarations for the iodine_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/iodine_b200.h"
+
+namespace iod {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const char* fmt, ...);
+#define IOD_CHECK_CUDA(expr)                                                      \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      iod::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                \
+                     cudaGetErrorString(_e));                                     \
+      return 1;                                                                   \
+    }                                                                             \
+  } while (0)
+#define IOD_REQUIRE(cond, ...)                                                    \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      iod::set_error(__VA_ARGS__);                                                \
+      return 1;                                                                   \
+    }                                                                             \
+  } while (0)
+#define IOD_LAUNCH_CHECK(plan)                                                    \
+  do {                                                                            \
+    (plan)->launches++;                                                           \
+    IOD_CHECK_CUDA(cudaGetLastError());                                           \
+  } while (0)
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ float elu_f(float v) { return v > 0.f ? v : expm1f(v); }
+// ELU'(pre) recovered from the post-activation a = ELU(pre): a>0 -> 1, else exp(pre)=a+1
+__device__ __forceinline__ float elu_grad_from_act(float a) { return a > 0.f ? 1.f : a + 1.f; }
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + expf(-v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// border class of coordinate y for a k-tap zero-padded conv (p = k/2): 0..p-1 = distance
+// from the low border, p = interior, p+1..2p = high border (2p = last row/col).
+__host__ __device__ __forceinline__ int border_class(int y, int n, int p) {
+  if (y < p) return y;
+  if (y >= n - p) return 2 * p - (n - 1 - y);
+  return p;
+}
+
+// ------------------------------------------------------------------ the plan
+struct ConvPack {       // fp32 direct-conv weights repacked [chunk][tap][ci_in_chunk][co]
+  float* w = nullptr;   // forward
+  float* wt = nullptr;  // data-gradient (transposed + flipped)
+  float* b = nullptr;   // bias [co]
+};
+
+struct Plan {
+  IodineShape s;
+  int device = 0;
+  int num_sms = 148;
+  int BK = 0, HW = 0, M = 0, C = 0, Cr = 0;
+  int n_class = 0;            // dec_k * dec_k border classes of decoder layer 1
+  int ref_h[IODINE_MAX_LAYERS + 1];
+  int ref_w[IODINE_MAX_LAYERS + 1];
+  uint64_t launches = 0;
+  bool weights_set = false;
+
+  // ---- weights (plan-owned device memory, allocated at create)
+  float* wsum = nullptr;      // [n_class][C][L]   layer-1 tap sums per border class
+  float* ptab = nullptr;      // [H][W][C]         layer-1 coord-conv + bias table
+  ConvPack dec[IODINE_MAX_LAYERS];   // layers 1..n-1 (index = layer), C->C
+  float* out_w = nullptr;     // [tap][ci][4]      decoder.conv forward
+  float* out_wt = nullptr;    // [tap][4][co]      decoder.conv data-gradient (flipped)
+  float* out_b = nullptr;     // [4]
+  float* ref_w0 = nullptr;    // [tap][17][Cr]     refine layer 0
+  float* ref_wp[IODINE_MAX_LAYERS];  // [tap][ci][Cr] refine layers >= 1
+  float* ref_b[IODINE_MAX_LAYERS];
+  float *mlp_w = nullptr, *mlp_b = nullptr;
+  float *w_ih = nullptr, *w_hh = nullptr, *b_ih = nullptr, *b_hh = nullptr;
+  float *head_w = nullptr, *head_b = nullptr;   // [2L, M] (mean rows then logvar rows), [2L]
+  float *init_mean = nullptr, *init_logvar = nullptr;
+  // bf16 tensor-core weights (conv_tc.cu), [layer][tap][co][ci] K-major, fwd and dgrad
+  __nv_bfloat16* tc_w[IODINE_MAX_LAYERS];
+  __nv_bfloat16* tc_wt[IODINE_MAX_LAYERS];
+
+  // ---- workspace carve-up (caller memory)
+  void* ws = nullptr;
+  size_t ws_bytes = 0, ws_need = 0;
+  void* act[IODINE_MAX_LAYERS];   // [BK,H,W,C] fp32 (or bf16 in IODINE_BF16) post-activations
+  void* gbuf[2];                  // dgrad ping-pong, same type as act
+  float* out4 = nullptr;          // [BK,H,W,4]
+  float* seed4 = nullptr;         // [BK,H,W,4]
+  float* auxs = nullptr;          // [BK,H,W,12] per-slot raw aux channels
+  float* lik = nullptr;           // [B,H,W] raw pixel likelihood
+  float* enc20 = nullptr;         // [BK,H,W,20] normalised refinement input (17 + 3 pad)
+  float* rbuf[2];                 // refine conv ping-pong
+  float* z = nullptr;             // [BK,L]
+  float* u = nullptr;             // [BK,n_class,C]
+  float* G = nullptr;             // [BK,n_class,C] class-wise pixel sums of dJ/d(pre-act 1)
+  float* dz = nullptr;            // [BK,L]
+  double* stats = nullptr;        // [BK,4,2] (sum, sumsq) for grad_means/grad_mask/lik/loo
+  double* accum = nullptr;        // [2] (sum ll, sum kl) of the step
+  float* pool = nullptr;          // [BK,Cr]
+  float* xin = nullptr;           // [BK, M+4L]
+  float* gates = nullptr;         // [BK, 4M]
+  float* st_mean = nullptr;       // [BK,L] scratch state for encode()/reconstruct()
+  float* st_logvar = nullptr;
+  float* st_h = nullptr;          // [BK,M]
+  float* st_c = nullptr;
+  float* st_z = nullptr;          // [BK,L]
+  float* st_terms = nullptr;      // [T,2]
+  // staging for *_host entry points
+  float* hx = nullptr;            // [B,3,H,W]
+  float* heps = nullptr;          // [T+1,B,K,L]
+  float* hpred = nullptr;         // [B,3,H,W]
+  float* hmask = nullptr;         // [B,K,1,H,W]
+  float* hmean = nullptr;         // [B,K,3,H,W]
+};
+
+inline size_t act_elem_bytes(const Plan* p) { return p->s.precision == IODINE_BF16 ? 2 : 4; }
+
+// ------------------------------------------------------------------ launchers (conv_f32.cu)
+// stride-1 C->C conv, NHWC fp32.  mode 0: out = ELU(conv + bias); mode 1: out = conv * ELU'(act)
+// mode 2: like 1 but instead of storing, accumulate class-wise pixel sums into G[n][class][co]
+int launch_conv_cc(Plan* p, const float* in, const float* wpack, const float* bias,
+                   const float* act_prev, float* out, float* G, int mode, cudaStream_t st);
+int launch_conv_out4(Plan* p, const float* in, float* out4, cudaStream_t st);
+int launch_dgrad_in4(Plan* p, const float* seed4, const float* act_prev, float* gout,
+                     cudaStream_t st);
+int launch_refine_convs(Plan* p, const float* x, cudaStream_t st);
+
+// ------------------------------------------------------------------ launchers (mixture.cu)
+int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st);
+int launch_recombine(Plan* p, float* pred, float* mask, float* mean, cudaStream_t st);
+int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st);
+
+// ------------------------------------------------------------------ launchers (head.cu)
+int launch_sample_l1(Plan* p, const float* mu, const float* logvar, const float* eps,
+                     const float* z_in, float* act0_f32, cudaStream_t st);
+int launch_post_grads(Plan* p, const float* mu, const float* logvar, const float* eps,
+                      float* latent_out, cudaStream_t st);
+int launch_head(Plan* p, float* mu, float* logvar, float* h, float* c, cudaStream_t st);
+int launch_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st);
+
+// ------------------------------------------------------------------ conv_tc.cu (tcgen05 path)
+int tc_supported(const Plan* p);      // 1 if the bf16 tensor-core path can run this shape
+int tc_alloc(Plan* p);
+void tc_free(Plan* p);
+int tc_on_workspace(Plan* p);         // (re)build TMA descriptors over the workspace
+int tc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st);
+// layer l (1..n-1) forward: out = ELU(conv(in) + b); dgrad: out = convT(in) * ELU'(act_prev),
+// or, when G != nullptr, the class-wise pixel sums of that product (nothing stored).
+int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* act_prev,
+                   void* out, float* G, cudaStream_t st);
+int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st);
+int tc_launch_dgrad_in4(Plan* p, const float* seed4, const void* act_prev, void* gout, cudaStream_t st);
+int tc_export_f32(Plan* p, const void* src_bf16, float* dst, size_t n, cudaStream_t st);
+
+}  // namespace iod

@@ -1,0 +1,335 @@
+// mixture.cu -- the fused pixel-mixture kernel ("K4" of SURVEY.md) and its consumers.
+//
+// One pass over the decoder's 4-channel output computes, per pixel and for all K slots in
+// registers: the mask softmax (reference lib/modeling/iodine.py:185), the per-channel
+// Gaussian log-likelihood (661-666), the per-channel mixture logsumexp (213-216), the
+// closed-form gradients that (B*elbo).backward() (iodine.py:90) leaves in mean.grad /
+// mask.grad, their chain through sigmoid / softmax down to the decoder's pre-activation
+// outputs ("seed4"), and every raw auxiliary channel of get_input_encoding() (243-343):
+// mask_posterior (289-292), pixel likelihood (309-312) and leave-one-out likelihood
+// (321-328), plus the sums the parameter-free layer-norm (376-395) needs.  No [B,K,C,H,W]
+// intermediate of the reference (K_log_likelihood, log(mask), r, ...) touches HBM.
+#include "common.cuh"
+
+namespace iod {
+
+// auxs layout per slot-pixel (12 floats): 0-2 mean rgb | 3 mask | 4 logit | 5 mask_post |
+// 6-8 dJ/dmean rgb | 9 dJ/dmask | 10 leave-one-out | 11 unused
+template <int KMAX>
+__global__ void __launch_bounds__(128)
+mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
+               float* __restrict__ seed4, float* __restrict__ auxs, float* __restrict__ lik,
+               double* __restrict__ stats, double* __restrict__ accum,
+               int K, int HW, float inv_2s2, float inv_s2, float ll_const, int want_grads) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = pix < HW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = 4;
+
+  float lg[KMAX], mr[KMAX], mg[KMAX], mb[KMAX];   // logit -> mask ; pre-sigmoid -> mean
+  float xr = 0.f, xg = 0.f, xb = 0.f;
+  if (live) {
+    xr = x[((size_t)b * 3 + 0) * HW + pix];
+    xg = x[((size_t)b * 3 + 1) * HW + pix];
+    xb = x[((size_t)b * 3 + 2) * HW + pix];
+  }
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    lg[k] = -INFINITY; mr[k] = mg[k] = mb[k] = 0.f;
+    if (k < K && live) {
+      const float4 v = reinterpret_cast<const float4*>(out4)[((size_t)(b * K + k)) * HW + pix];
+      mr[k] = sigmoid_f(v.x); mg[k] = sigmoid_f(v.y); mb[k] = sigmoid_f(v.z);
+      lg[k] = v.w;
+      lmax = fmaxf(lmax, v.w);
+    }
+  }
+  // ---- mask = softmax_K(logits)                                      (iodine.py:185)
+  float logit_raw[KMAX];
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    logit_raw[k] = lg[k];
+    if (k < K && live) { lg[k] = expf(lg[k] - lmax); den += lg[k]; }
+  }
+  const float inv_den = live ? 1.f / den : 0.f;
+  // ---- per-channel a_kc = log(mask+1e-12) + ll_kc ; s_c = logsumexp_k  (210-216)
+  float amax_r = -INFINITY, amax_g = -INFINITY, amax_b = -INFINITY;
+  float lm[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    lm[k] = 0.f;
+    if (k < K && live) {
+      lg[k] *= inv_den;                              // lg now holds the mask
+      lm[k] = logf(lg[k] + 1e-12f);
+      const float dr = xr - mr[k], dg = xg - mg[k], db = xb - mb[k];
+      amax_r = fmaxf(amax_r, lm[k] - dr * dr * inv_2s2 + ll_const);
+      amax_g = fmaxf(amax_g, lm[k] - dg * dg * inv_2s2 + ll_const);
+      amax_b = fmaxf(amax_b, lm[k] - db * db * inv_2s2 + ll_const);
+    }
+  }
+  float sr = 0.f, sg = 0.f, sb = 0.f;
+  float kl_tot = 0.f, mkl_tot = 0.f;                 // sum_k Lk_k ; sum_k mask_k Lk_k
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K && live) {
+      const float dr = xr - mr[k], dg = xg - mg[k], db = xb - mb[k];
+      const float llr = -dr * dr * inv_2s2 + ll_const, llg = -dg * dg * inv_2s2 + ll_const,
+                  llb = -db * db * inv_2s2 + ll_const;
+      sr += expf(lm[k] + llr - amax_r);
+      sg += expf(lm[k] + llg - amax_g);
+      sb += expf(lm[k] + llb - amax_b);
+      const float Lk = expf(llr + llg + llb);        // un-stabilised, as the reference (290)
+      kl_tot += Lk;
+      mkl_tot += lg[k] * Lk;
+    }
+  }
+  float s_r = 0.f, s_g = 0.f, s_b = 0.f;
+  if (live) { s_r = amax_r + logf(sr); s_g = amax_g + logf(sg); s_b = amax_b + logf(sb); }
+  const float ll_pix = s_r + s_g + s_b;              // summed over channels (220)
+
+  // ---- block reduction of the log-likelihood
+  __shared__ double red[NW];
+  {
+    float v = warp_sum(live ? ll_pix : 0.f);
+    if (lane == 0) red[warp] = (double)v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < NW; ++w) t += red[w];
+      atomicAdd(&accum[0], t);
+    }
+  }
+  if (!want_grads) return;
+
+  // ---- gradients + aux channels
+  const float likv = live ? expf(ll_pix) : 0.f;      // exp(sum_c s_c)           (309-310)
+  if (live) lik[(size_t)b * HW + pix] = likv;
+  float gm[KMAX];                                     // dJ/dmask_k
+  float mgsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    gm[k] = 0.f;
+    if (k < K && live) {
+      const float dr = xr - mr[k], dg = xg - mg[k], db = xb - mb[k];
+      // exp(ll_kc - s_c) = r_kc / (mask_k + 1e-12)
+      const float er = expf(-dr * dr * inv_2s2 + ll_const - s_r);
+      const float eg = expf(-dg * dg * inv_2s2 + ll_const - s_g);
+      const float eb = expf(-db * db * inv_2s2 + ll_const - s_b);
+      gm[k] = er + eg + eb;
+      mgsum += lg[k] * gm[k];
+    }
+  }
+  __shared__ float sred[NW][8];
+  for (int k = 0; k < K; ++k) {
+    float a_mean = 0.f, a_mean2 = 0.f, a_gm = 0.f, a_gm2 = 0.f, a_loo = 0.f, a_loo2 = 0.f;
+    // (runtime k indexes compile-time-unrolled registers through a select chain)
+    float mk = 0.f, m_r = 0.f, m_g = 0.f, m_b = 0.f, gmk = 0.f, lgr = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KMAX; ++kk)
+      if (kk == k) { mk = lg[kk]; m_r = mr[kk]; m_g = mg[kk]; m_b = mb[kk]; gmk = gm[kk]; lgr = logit_raw[kk]; }
+    if (live) {
+      const float dr = xr - m_r, dg = xg - m_g, db = xb - m_b;
+      const float llr = -dr * dr * inv_2s2 + ll_const, llg = -dg * dg * inv_2s2 + ll_const,
+                  llb = -db * db * inv_2s2 + ll_const;
+      const float me = mk + 1e-12f;
+      const float er = expf(llr - s_r), eg = expf(llg - s_g), eb = expf(llb - s_b);
+      // dJ/dmean_kc = r_kc (x_c - mean_kc)/sigma^2 with r_kc = (mask+1e-12) * exp(ll - s)
+      const float gr = me * er * dr * inv_s2, gg = me * eg * dg * inv_s2, gb = me * eb * db * inv_s2;
+      const float Lk = expf(llr + llg + llb);
+      const float mpost = Lk / kl_tot;                                   // (292) 0/0 -> NaN as ref
+      const float loo = (mkl_tot - mk * Lk) / (1.f - mk + 1e-5f);        // (326-328)
+      const size_t sp = ((size_t)(b * K + k)) * HW + pix;
+      float4* ax = reinterpret_cast<float4*>(auxs) + sp * 3;
+      ax[0] = make_float4(m_r, m_g, m_b, mk);
+      ax[1] = make_float4(lgr, mpost, gr, gg);
+      ax[2] = make_float4(gb, gmk, loo, 0.f);
+      // chain to the decoder's raw outputs: sigmoid' and softmax'
+      reinterpret_cast<float4*>(seed4)[sp] =
+          make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g), gb * m_b * (1.f - m_b),
+                      mk * (gmk - mgsum));
+      a_mean = gr + gg + gb; a_mean2 = gr * gr + gg * gg + gb * gb;
+      a_gm = gmk; a_gm2 = gmk * gmk;
+      a_loo = loo; a_loo2 = loo * loo;
+    }
+    a_mean = warp_sum(a_mean); a_mean2 = warp_sum(a_mean2);
+    a_gm = warp_sum(a_gm); a_gm2 = warp_sum(a_gm2);
+    a_loo = warp_sum(a_loo); a_loo2 = warp_sum(a_loo2);
+    __syncthreads();
+    if (lane == 0) {
+      sred[warp][0] = a_mean; sred[warp][1] = a_mean2; sred[warp][2] = a_gm;
+      sred[warp][3] = a_gm2; sred[warp][4] = a_loo; sred[warp][5] = a_loo2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      double t = 0.0;
+      for (int w = 0; w < NW; ++w) t += (double)sred[w][threadIdx.x];
+      // stats[n][group][2]: group 0 grad_means, 1 grad_mask, 2 likelihood, 3 leave-one-out
+      const int grp = threadIdx.x >> 1, which = threadIdx.x & 1;
+      const int g = (grp == 2) ? 3 : grp;
+      atomicAdd(&stats[((size_t)(b * K + k) * 4 + g) * 2 + which], t);
+    }
+  }
+  // likelihood statistics are per image; every slot of the image gets the same numbers
+  {
+    float a = warp_sum(likv), a2 = warp_sum(likv * likv);
+    __syncthreads();
+    if (lane == 0) { sred[warp][0] = a; sred[warp][1] = a2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+      for (int w = 0; w < NW; ++w) t += (double)sred[w][threadIdx.x];
+      for (int k = 0; k < K; ++k)
+        atomicAdd(&stats[((size_t)(b * K + k) * 4 + 2) * 2 + threadIdx.x], t);
+    }
+  }
+}
+
+int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st) {
+  const IodineShape& s = p->s;
+  const float sg = s.sigma;
+  const float inv_2s2 = 1.f / (2.f * sg * sg), inv_s2 = 1.f / (sg * sg);
+  const float ll_const = -logf(sg) - 0.5f * logf(2.f * 3.14159265358979323846f);
+  IOD_CHECK_CUDA(cudaMemsetAsync(p->accum, 0, 2 * sizeof(double), st));
+  if (want_grads)
+    IOD_CHECK_CUDA(cudaMemsetAsync(p->stats, 0, (size_t)p->BK * 8 * sizeof(double), st));
+  dim3 grid((p->HW + 127) / 128, s.B);
+  if (s.K <= 8)
+    mixture_kernel<8><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
+                                            p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads);
+  else
+    mixture_kernel<16><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
+                                             p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------
+// assemble: the refinement network's 17-channel input (get_input_encoding, iodine.py:277-340)
+// in NHWC with 3 zero pad channels, layer-norm (376-395, biased std over C,H,W per slot)
+// applied from the sums the mixture kernel accumulated.  Channel order is the reference's
+// code order: image 0-2 | means 3-5 | mask 6 | logits 7 | mask_post 8 | grad_means 9-11 |
+// grad_mask 12 | likelihood 13 | leave-one-out 14 | x-coord 15 | y-coord 16.
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+assemble_kernel(const float* __restrict__ auxs, const float* __restrict__ lik,
+                const float* __restrict__ x, const double* __restrict__ stats,
+                float* __restrict__ enc20, int K, int H, int W, int layernorm) {
+  const int n = blockIdx.y, b = n / K;
+  const int HW = H * W;
+  __shared__ float s_mu[4], s_is[4];
+  if (threadIdx.x < 4) {
+    float mu = 0.f, is = 1.f;
+    if (layernorm) {
+      const double cnt = (threadIdx.x == 0) ? 3.0 * HW : (double)HW;
+      const double sum = stats[((size_t)n * 4 + threadIdx.x) * 2 + 0];
+      const double sq = stats[((size_t)n * 4 + threadIdx.x) * 2 + 1];
+      const double m = sum / cnt;
+      double var = sq / cnt - m * m;
+      if (var < 0.0) var = 0.0;
+      mu = (float)m;
+      is = 1.f / ((float)sqrt(var) + 1e-5f);
+    }
+    s_mu[threadIdx.x] = mu; s_is[threadIdx.x] = is;
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const int y = pix / W, xx = pix % W;
+  const float4* ax = reinterpret_cast<const float4*>(auxs) + ((size_t)n * HW + pix) * 3;
+  const float4 a0 = ax[0], a1 = ax[1], a2 = ax[2];
+  const float xr = x[((size_t)b * 3 + 0) * HW + pix], xg = x[((size_t)b * 3 + 1) * HW + pix],
+              xb = x[((size_t)b * 3 + 2) * HW + pix];
+  const float lk = lik[(size_t)b * HW + pix];
+  const float cxv = (W > 1) ? -1.f + 2.f * (float)xx / (float)(W - 1) : -1.f;
+  const float cyv = (H > 1) ? -1.f + 2.f * (float)y / (float)(H - 1) : -1.f;
+  float4* o = reinterpret_cast<float4*>(enc20) + ((size_t)n * HW + pix) * 5;
+  o[0] = make_float4(xr, xg, xb, a0.x);
+  o[1] = make_float4(a0.y, a0.z, a0.w, a1.x);
+  o[2] = make_float4(a1.y, (a1.z - s_mu[0]) * s_is[0], (a1.w - s_mu[0]) * s_is[0],
+                     (a2.x - s_mu[0]) * s_is[0]);
+  o[3] = make_float4((a2.y - s_mu[1]) * s_is[1], (lk - s_mu[2]) * s_is[2],
+                     (a2.z - s_mu[3]) * s_is[3], cxv);
+  o[4] = make_float4(cyv, 0.f, 0.f, 0.f);
+}
+
+int launch_assemble(Plan* p, const float* x, cudaStream_t st) {
+  dim3 grid((p->HW + 255) / 256, p->BK);
+  assemble_kernel<<<grid, 256, 0, st>>>(p->auxs, p->lik, x, p->stats, p->enc20, p->s.K, p->s.H,
+                                        p->s.W, p->s.layernorm);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// tests only: reference layout [B,K,17,H,W] followed by latent [B,K,4L]
+__global__ void export_aux_kernel(const float* __restrict__ enc20, const float* __restrict__ xin,
+                                  float* __restrict__ aux_out, int BK, int HW, int M, int L4) {
+  const size_t total = (size_t)BK * 17 * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int pix = i % HW;
+    const int c = (i / HW) % 17;
+    const int n = i / ((size_t)HW * 17);
+    aux_out[i] = enc20[((size_t)n * HW + pix) * 20 + c];
+  }
+  const size_t tl = (size_t)BK * L4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tl;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int n = i / L4, j = i % L4;
+    aux_out[total + i] = xin[(size_t)n * (M + L4) + M + j];
+  }
+}
+
+int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st) {
+  (void)x;
+  export_aux_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->enc20, p->xin, aux_out, p->BK, p->HW, p->M,
+                                                    4 * p->s.L);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------
+// recombine: IODINE.decode's tail (iodine.py:67-71): mask = softmax_K, pred = sum_k mask*mean;
+// outputs in the reference's NCHW layouts.
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+recombine_kernel(const float* __restrict__ out4, float* __restrict__ pred, float* __restrict__ mask,
+                 float* __restrict__ mean, int K, int HW) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  float lmax = -INFINITY;
+  for (int k = 0; k < K; ++k)
+    lmax = fmaxf(lmax, out4[(((size_t)(b * K + k)) * HW + pix) * 4 + 3]);
+  float den = 0.f;
+  for (int k = 0; k < K; ++k) den += expf(out4[(((size_t)(b * K + k)) * HW + pix) * 4 + 3] - lmax);
+  const float inv = 1.f / den;
+  float pr = 0.f, pg = 0.f, pb = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float4 v = reinterpret_cast<const float4*>(out4)[((size_t)(b * K + k)) * HW + pix];
+    const float m = expf(v.w - lmax) * inv;
+    const float r = sigmoid_f(v.x), g = sigmoid_f(v.y), bl = sigmoid_f(v.z);
+    pr += m * r; pg += m * g; pb += m * bl;
+    if (mask) mask[((size_t)(b * K + k)) * HW + pix] = m;
+    if (mean) {
+      mean[(((size_t)(b * K + k)) * 3 + 0) * HW + pix] = r;
+      mean[(((size_t)(b * K + k)) * 3 + 1) * HW + pix] = g;
+      mean[(((size_t)(b * K + k)) * 3 + 2) * HW + pix] = bl;
+    }
+  }
+  if (pred) {
+    pred[((size_t)b * 3 + 0) * HW + pix] = pr;
+    pred[((size_t)b * 3 + 1) * HW + pix] = pg;
+    pred[((size_t)b * 3 + 2) * HW + pix] = pb;
+  }
+}
+
+int launch_recombine(Plan* p, float* pred, float* mask, float* mean, cudaStream_t st) {
+  dim3 grid((p->HW + 255) / 256, p->s.B);
+  recombine_kernel<<<grid, 256, 0, st>>>(p->out4, pred, mask, mean, p->s.K, p->HW);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+}  // namespace iod

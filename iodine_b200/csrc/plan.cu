@@ -1,0 +1,417 @@
+// plan.cu -- the C ABI (include/iodine_b200.h): plan lifetime, workspace carve-up and the
+// per-step kernel sequence that replaces IODINE.encode/decode/reconstruct/elbo
+// (reference lib/modeling/iodine.py:59-241).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace iod {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_assemble(Plan* p, const float* x, cudaStream_t st);
+int launch_kl(Plan* p, const float* mu, const float* logvar, cudaStream_t st);
+int launch_init_state(Plan* p, float* mu, float* lv, float* h, float* c, cudaStream_t st);
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Walk the workspace layout; with base == nullptr only the size is computed.
+static size_t carve(Plan* p, char* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> void* {
+    void* r = base ? base + off : nullptr;
+    off = align_up(off + bytes, 1024);
+    return r;
+  };
+  const IodineShape& s = p->s;
+  const size_t BK = p->BK, HW = p->HW, C = p->C, L = s.L, M = p->M, Cr = p->Cr;
+  const size_t eb = act_elem_bytes(p);
+  for (int l = 0; l < s.dec_layers; ++l) p->act[l] = take(BK * HW * C * eb);
+  for (int i = 0; i < 2; ++i) p->gbuf[i] = take(s.dec_layers > 1 ? BK * HW * C * eb : 1024);
+  p->out4 = (float*)take(BK * HW * 4 * sizeof(float));
+  p->seed4 = (float*)take(BK * HW * 4 * sizeof(float));
+  p->auxs = (float*)take(BK * HW * 12 * sizeof(float));
+  p->enc20 = (float*)take(BK * HW * 20 * sizeof(float));
+  p->lik = (float*)take((size_t)s.B * HW * sizeof(float));
+  size_t r0 = (size_t)p->ref_h[1] * p->ref_w[1] * Cr;
+  size_t r1 = s.ref_layers > 1 ? (size_t)p->ref_h[2] * p->ref_w[2] * Cr : 256;
+  p->rbuf[0] = (float*)take(BK * r0 * sizeof(float));
+  p->rbuf[1] = (float*)take(BK * r1 * sizeof(float));
+  p->z = (float*)take(BK * L * sizeof(float));
+  p->u = (float*)take(BK * p->n_class * C * sizeof(float));
+  p->G = (float*)take(BK * p->n_class * C * sizeof(float));
+  p->dz = (float*)take(BK * L * sizeof(float));
+  p->stats = (double*)take(BK * 8 * sizeof(double));
+  p->accum = (double*)take(2 * sizeof(double));
+  p->pool = (float*)take(BK * Cr * sizeof(float));
+  p->xin = (float*)take(BK * (M + 4 * L) * sizeof(float));
+  p->gates = (float*)take(BK * 4 * M * sizeof(float));
+  p->st_mean = (float*)take(BK * L * sizeof(float));
+  p->st_logvar = (float*)take(BK * L * sizeof(float));
+  p->st_h = (float*)take(BK * M * sizeof(float));
+  p->st_c = (float*)take(BK * M * sizeof(float));
+  p->st_z = (float*)take(BK * L * sizeof(float));
+  p->st_terms = (float*)take((size_t)(s.T + 1) * 2 * sizeof(float));
+  p->hx = (float*)take((size_t)s.B * 3 * HW * sizeof(float));
+  p->heps = (float*)take((size_t)(s.T + 1) * BK * L * sizeof(float));
+  p->hpred = (float*)take((size_t)s.B * 3 * HW * sizeof(float));
+  p->hmask = (float*)take(BK * HW * sizeof(float));
+  p->hmean = (float*)take(BK * 3 * HW * sizeof(float));
+  return off;
+}
+
+static int alloc_f(float** dst, size_t n) {
+  IOD_CHECK_CUDA(cudaMalloc((void**)dst, (n ? n : 1) * sizeof(float)));
+  return 0;
+}
+
+__global__ void terms_kernel(const double* __restrict__ accum, float* __restrict__ out) {
+  if (threadIdx.x < 2) out[threadIdx.x] = (float)accum[threadIdx.x];
+}
+__global__ void sample_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                              const float* __restrict__ eps, float* __restrict__ z, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    z[i] = mu[i] + expf(0.5f * lv[i]) * eps[i];
+}
+
+// ---------------------------------------------------------------- decoder forward / dgrad
+static int decoder_forward(Plan* p, const float* mu, const float* lv, const float* eps,
+                           const float* z_in, cudaStream_t st) {
+  const IodineShape& s = p->s;
+  if (launch_sample_l1(p, mu, lv, eps, z_in, (float*)p->act[0], st)) return 1;
+  for (int l = 1; l < s.dec_layers; ++l) {
+    if (s.precision == IODINE_BF16) {
+      if (tc_launch_conv(p, l, false, p->act[l - 1], nullptr, p->act[l], nullptr, st)) return 1;
+    } else {
+      if (launch_conv_cc(p, (const float*)p->act[l - 1], p->dec[l].w, p->dec[l].b, nullptr,
+                         (float*)p->act[l], nullptr, 0, st))
+        return 1;
+    }
+  }
+  if (s.precision == IODINE_BF16) return tc_launch_out4(p, p->act[s.dec_layers - 1], p->out4, st);
+  return launch_conv_out4(p, (const float*)p->act[s.dec_layers - 1], p->out4, st);
+}
+
+static int decoder_dgrad(Plan* p, cudaStream_t st) {
+  const IodineShape& s = p->s;
+  const int n = s.dec_layers;
+  IOD_CHECK_CUDA(cudaMemsetAsync(p->G, 0, (size_t)p->BK * p->n_class * p->C * sizeof(float), st));
+  if (s.precision == IODINE_BF16) {
+    if (tc_launch_dgrad_in4(p, p->seed4, p->act[n - 1], p->gbuf[0], st)) return 1;
+  } else {
+    if (launch_dgrad_in4(p, p->seed4, (const float*)p->act[n - 1], (float*)p->gbuf[0], st)) return 1;
+  }
+  int cur = 0;
+  for (int l = n - 1; l >= 1; --l) {
+    const bool last = (l == 1);
+    if (s.precision == IODINE_BF16) {
+      if (tc_launch_conv(p, l, true, p->gbuf[cur], p->act[l - 1], last ? nullptr : p->gbuf[cur ^ 1],
+                         last ? p->G : nullptr, st))
+        return 1;
+    } else {
+      if (launch_conv_cc(p, (const float*)p->gbuf[cur], p->dec[l].wt, nullptr,
+                         (const float*)p->act[l - 1], last ? nullptr : (float*)p->gbuf[cur ^ 1],
+                         last ? p->G : nullptr, last ? 2 : 1, st))
+        return 1;
+    }
+    cur ^= 1;
+  }
+  return 0;
+}
+
+static int refine_step(Plan* p, const float* x, const float* eps_t, float* mu, float* lv, float* h,
+                       float* c, float* terms_out, float* aux_out, cudaStream_t st) {
+  if (decoder_forward(p, mu, lv, eps_t, nullptr, st)) return 1;
+  if (launch_mixture(p, x, true, st)) return 1;
+  if (decoder_dgrad(p, st)) return 1;
+  if (launch_post_grads(p, mu, lv, eps_t, nullptr, st)) return 1;
+  if (launch_assemble(p, x, st)) return 1;
+  if (launch_refine_convs(p, p->enc20, st)) return 1;
+  if (aux_out && launch_export_aux(p, x, aux_out, st)) return 1;
+  if (launch_head(p, mu, lv, h, c, st)) return 1;
+  if (terms_out) {
+    terms_kernel<<<1, 32, 0, st>>>(p->accum, terms_out);
+    IOD_LAUNCH_CHECK(p);
+  }
+  return 0;
+}
+
+static int check_ready(Plan* p) {
+  IOD_REQUIRE(p != nullptr, "null plan");
+  IOD_REQUIRE(p->ws != nullptr, "workspace not set (iodine_plan_set_workspace)");
+  IOD_REQUIRE(p->weights_set, "weights not set (iodine_plan_set_weights)");
+  return 0;
+}
+
+static int do_encode(Plan* p, const float* x, const float* eps, float* z_out, float* terms,
+                     float* post_out, cudaStream_t st) {
+  const IodineShape& s = p->s;
+  const size_t nl = (size_t)p->BK * s.L;
+  if (launch_init_state(p, p->st_mean, p->st_logvar, p->st_h, p->st_c, st)) return 1;
+  for (int t = 0; t < s.T; ++t) {
+    if (refine_step(p, x, eps + t * nl, p->st_mean, p->st_logvar, p->st_h, p->st_c,
+                    terms ? terms + 2 * t : nullptr, nullptr, st))
+      return 1;
+  }
+  sample_kernel<<<64, 256, 0, st>>>(p->st_mean, p->st_logvar, eps + (size_t)s.T * nl, z_out, (int)nl);
+  IOD_LAUNCH_CHECK(p);
+  if (post_out) {
+    IOD_CHECK_CUDA(cudaMemcpyAsync(post_out, p->st_mean, nl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    IOD_CHECK_CUDA(cudaMemcpyAsync(post_out + nl, p->st_logvar, nl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+static int do_decode(Plan* p, const float* z, float* pred, float* mask, float* mean, cudaStream_t st) {
+  if (decoder_forward(p, nullptr, nullptr, nullptr, z, st)) return 1;
+  return launch_recombine(p, pred, mask, mean, st);
+}
+
+}  // namespace iod
+
+using namespace iod;
+
+// =========================================================================== C ABI
+extern "C" {
+
+IODINE_API int iodine_abi_version(void) { return IODINE_ABI_VERSION; }
+IODINE_API const char* iodine_last_error(void) { return g_err; }
+
+IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_out) {
+  IOD_REQUIRE(shape && plan_out, "iodine_plan_create: null argument");
+  const IodineShape& s = *shape;
+  IOD_REQUIRE(s.B > 0 && s.K > 0 && s.K <= 16, "unsupported B=%d K=%d (1 <= K <= 16)", s.B, s.K);
+  IOD_REQUIRE(s.img_c == 3, "IMG_CHANNELS must be 3 (got %d)", s.img_c);
+  IOD_REQUIRE(s.L >= 2 && s.L <= 256, "unsupported DIM_LATENT=%d", s.L);
+  IOD_REQUIRE(s.dec_layers >= 1 && s.dec_layers <= IODINE_MAX_LAYERS, "unsupported DEC.CONV_LAYERS=%d", s.dec_layers);
+  IOD_REQUIRE(s.ref_layers >= 1 && s.ref_layers <= IODINE_MAX_LAYERS, "unsupported REF.CONV_LAYERS=%d", s.ref_layers);
+  IOD_REQUIRE(s.dec_chan == 16 || s.dec_chan == 32 || s.dec_chan == 64, "unsupported DEC.CONV_CHAN=%d", s.dec_chan);
+  IOD_REQUIRE(s.ref_chan == 16 || s.ref_chan == 32 || s.ref_chan == 64, "unsupported REF.CONV_CHAN=%d", s.ref_chan);
+  IOD_REQUIRE(s.dec_k == 3 || s.dec_k == 5, "unsupported DEC.KERNEL_SIZE=%d", s.dec_k);
+  IOD_REQUIRE(s.ref_k == 3 || s.ref_k == 5, "unsupported REF.KERNEL_SIZE=%d", s.ref_k);
+  IOD_REQUIRE(s.ref_stride == 1 || s.ref_stride == 2, "unsupported REF.STRIDE=%d", s.ref_stride);
+  IOD_REQUIRE(s.H >= 2 * s.dec_k && s.W >= 2 * s.dec_k, "image %dx%d too small for kernel %d", s.H, s.W, s.dec_k);
+  IOD_REQUIRE(s.mlp_units >= 1 && s.T >= 0 && s.sigma > 0.f, "bad MLP_UNITS/ITERS/SIGMA");
+  IOD_REQUIRE(s.precision == IODINE_FP32 || s.precision == IODINE_BF16, "unsupported precision %d", s.precision);
+
+  Plan* p = new Plan();
+  p->s = s;
+  IOD_CHECK_CUDA(cudaGetDevice(&p->device));
+  IOD_CHECK_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+  p->BK = s.B * s.K; p->HW = s.H * s.W; p->M = s.mlp_units; p->C = s.dec_chan; p->Cr = s.ref_chan;
+  p->n_class = s.dec_k * s.dec_k;
+  p->ref_h[0] = s.H; p->ref_w[0] = s.W;
+  for (int l = 0; l < s.ref_layers; ++l) {
+    const int pad = s.ref_k / 2;
+    p->ref_h[l + 1] = (p->ref_h[l] + 2 * pad - s.ref_k) / s.ref_stride + 1;
+    p->ref_w[l + 1] = (p->ref_w[l] + 2 * pad - s.ref_k) / s.ref_stride + 1;
+    IOD_REQUIRE(p->ref_h[l + 1] >= 1 && p->ref_w[l + 1] >= 1, "refine layer %d output is empty", l);
+  }
+  if (s.precision == IODINE_BF16) {
+    if (!tc_supported(p)) { delete p; return 1; }
+  }
+  const size_t C = p->C, L = s.L, M = p->M, Cr = p->Cr, kk = (size_t)s.dec_k * s.dec_k,
+               rkk = (size_t)s.ref_k * s.ref_k;
+  if (alloc_f(&p->wsum, kk * C * L) || alloc_f(&p->ptab, (size_t)p->HW * C)) return 1;
+  for (int l = 1; l < s.dec_layers; ++l)
+    if (alloc_f(&p->dec[l].w, kk * C * C) || alloc_f(&p->dec[l].wt, kk * C * C) || alloc_f(&p->dec[l].b, C)) return 1;
+  if (alloc_f(&p->out_w, kk * C * 4) || alloc_f(&p->out_wt, kk * C * 4) || alloc_f(&p->out_b, 4)) return 1;
+  if (alloc_f(&p->ref_w0, rkk * 20 * Cr)) return 1;
+  for (int l = 0; l < s.ref_layers; ++l) {
+    p->ref_wp[l] = nullptr;
+    if (l > 0 && alloc_f(&p->ref_wp[l], rkk * Cr * Cr)) return 1;
+    if (alloc_f(&p->ref_b[l], Cr)) return 1;
+  }
+  if (alloc_f(&p->mlp_w, M * Cr) || alloc_f(&p->mlp_b, M) || alloc_f(&p->w_ih, 4 * M * (M + 4 * L)) ||
+      alloc_f(&p->w_hh, 4 * M * M) || alloc_f(&p->b_ih, 4 * M) || alloc_f(&p->b_hh, 4 * M) ||
+      alloc_f(&p->head_w, 2 * L * M) || alloc_f(&p->head_b, 2 * L) || alloc_f(&p->init_mean, L) ||
+      alloc_f(&p->init_logvar, L))
+    return 1;
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { p->tc_w[l] = nullptr; p->tc_wt[l] = nullptr; }
+  if (s.precision == IODINE_BF16 && tc_alloc(p)) return 1;
+  p->ws_need = carve(p, nullptr);
+  *plan_out = reinterpret_cast<IodinePlan*>(p);
+  return 0;
+}
+
+IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (!p) return 0;
+  cudaFree(p->wsum); cudaFree(p->ptab);
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) {
+    cudaFree(p->dec[l].w); cudaFree(p->dec[l].wt); cudaFree(p->dec[l].b);
+    if (l < p->s.ref_layers) { cudaFree(p->ref_wp[l]); cudaFree(p->ref_b[l]); }
+    cudaFree(p->tc_w[l]); cudaFree(p->tc_wt[l]);
+  }
+  cudaFree(p->out_w); cudaFree(p->out_wt); cudaFree(p->out_b); cudaFree(p->ref_w0);
+  cudaFree(p->mlp_w); cudaFree(p->mlp_b); cudaFree(p->w_ih); cudaFree(p->w_hh); cudaFree(p->b_ih);
+  cudaFree(p->b_hh); cudaFree(p->head_w); cudaFree(p->head_b); cudaFree(p->init_mean);
+  cudaFree(p->init_logvar);
+  tc_free(p);
+  delete p;
+  return 0;
+}
+
+IODINE_API int iodine_plan_workspace_bytes(const IodinePlan* plan, size_t* bytes_out) {
+  IOD_REQUIRE(plan && bytes_out, "null argument");
+  *bytes_out = reinterpret_cast<const Plan*>(plan)->ws_need;
+  return 0;
+}
+
+IODINE_API int iodine_plan_set_workspace(IodinePlan* plan, void* workspace, size_t bytes) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  IOD_REQUIRE(p && workspace, "null argument");
+  IOD_REQUIRE(bytes >= p->ws_need, "workspace too small: %zu < %zu", bytes, p->ws_need);
+  IOD_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+  p->ws = workspace; p->ws_bytes = bytes;
+  carve(p, (char*)workspace);
+  if (p->s.precision == IODINE_BF16 && tc_on_workspace(p)) return 1;
+  return 0;
+}
+
+IODINE_API int iodine_plan_set_weights(IodinePlan* plan, const IodineWeights* w, void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  IOD_REQUIRE(p && w, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (launch_setup_weights(p, w, st)) return 1;
+  if (p->s.precision == IODINE_BF16 && tc_setup_weights(p, w, st)) return 1;
+  p->weights_set = true;
+  return 0;
+}
+
+IODINE_API int iodine_init_state(IodinePlan* plan, float* post_mean, float* post_logvar, float* lstm_h,
+                      float* lstm_c, void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  return launch_init_state(p, post_mean, post_logvar, lstm_h, lstm_c, (cudaStream_t)stream);
+}
+
+IODINE_API int iodine_refine_step(IodinePlan* plan, const float* x, const float* eps_t, float* post_mean,
+                       float* post_logvar, float* lstm_h, float* lstm_c, float* elbo_terms_out,
+                       float* aux_out, void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  IOD_REQUIRE(x && eps_t && post_mean && post_logvar && lstm_h && lstm_c, "null tensor argument");
+  return refine_step(p, x, eps_t, post_mean, post_logvar, lstm_h, lstm_c, elbo_terms_out, aux_out,
+                     (cudaStream_t)stream);
+}
+
+IODINE_API int iodine_elbo(IodinePlan* plan, const float* x, const float* eps_t, const float* post_mean,
+                const float* post_logvar, float* elbo_terms_out, void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  IOD_REQUIRE(x && eps_t && post_mean && post_logvar && elbo_terms_out, "null tensor argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (decoder_forward(p, post_mean, post_logvar, eps_t, nullptr, st)) return 1;
+  if (launch_mixture(p, x, false, st)) return 1;
+  if (launch_kl(p, post_mean, post_logvar, st)) return 1;
+  terms_kernel<<<1, 32, 0, st>>>(p->accum, elbo_terms_out);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+IODINE_API int iodine_encode(IodinePlan* plan, const float* x, const float* eps, float* z_out,
+                  float* elbo_terms_out, float* post_out, void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  IOD_REQUIRE(x && eps && z_out, "null tensor argument");
+  return do_encode(p, x, eps, z_out, elbo_terms_out, post_out, (cudaStream_t)stream);
+}
+
+IODINE_API int iodine_decode(IodinePlan* plan, const float* z, float* pred_out, float* mask_out, float* mean_out,
+                  void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  IOD_REQUIRE(z, "null tensor argument");
+  return do_decode(p, z, pred_out, mask_out, mean_out, (cudaStream_t)stream);
+}
+
+IODINE_API int iodine_reconstruct(IodinePlan* plan, const float* x, const float* eps, float* pred_out,
+                       float* mask_out, float* mean_out, float* z_out, float* elbo_terms_out,
+                       void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  IOD_REQUIRE(x && eps, "null tensor argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (do_encode(p, x, eps, p->st_z, elbo_terms_out, nullptr, st)) return 1;
+  if (z_out)
+    IOD_CHECK_CUDA(cudaMemcpyAsync(z_out, p->st_z, (size_t)p->BK * p->s.L * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, st));
+  return do_decode(p, p->st_z, pred_out, mask_out, mean_out, st);
+}
+
+IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, const float* eps_host,
+                            float* pred_host, float* mask_host, float* mean_host, float* z_host,
+                            float* elbo_terms_host, void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  IOD_REQUIRE(x_host && eps_host, "null tensor argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const IodineShape& s = p->s;
+  const size_t HW = p->HW, BK = p->BK;
+  IOD_CHECK_CUDA(cudaMemcpyAsync(p->hx, x_host, (size_t)s.B * 3 * HW * sizeof(float), cudaMemcpyHostToDevice, st));
+  IOD_CHECK_CUDA(cudaMemcpyAsync(p->heps, eps_host, (size_t)(s.T + 1) * BK * s.L * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (do_encode(p, p->hx, p->heps, p->st_z, p->st_terms, nullptr, st)) return 1;
+  if (do_decode(p, p->st_z, pred_host ? p->hpred : nullptr, mask_host ? p->hmask : nullptr,
+                mean_host ? p->hmean : nullptr, st))
+    return 1;
+  if (pred_host) IOD_CHECK_CUDA(cudaMemcpyAsync(pred_host, p->hpred, (size_t)s.B * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (mask_host) IOD_CHECK_CUDA(cudaMemcpyAsync(mask_host, p->hmask, BK * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (mean_host) IOD_CHECK_CUDA(cudaMemcpyAsync(mean_host, p->hmean, BK * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (z_host) IOD_CHECK_CUDA(cudaMemcpyAsync(z_host, p->st_z, BK * s.L * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (elbo_terms_host) IOD_CHECK_CUDA(cudaMemcpyAsync(elbo_terms_host, p->st_terms, (size_t)s.T * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  IOD_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, size_t dst_bytes, size_t* bytes_out,
+                      void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  IOD_REQUIRE(p && name && p->ws, "null argument / workspace not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t BK = p->BK, HW = p->HW;
+  const void* src = nullptr;
+  size_t bytes = 0;
+  bool act_view = false;
+  int act_idx = 0;
+  if (!strcmp(name, "out4")) { src = p->out4; bytes = BK * HW * 4 * sizeof(float); }
+  else if (!strcmp(name, "seed4")) { src = p->seed4; bytes = BK * HW * 4 * sizeof(float); }
+  else if (!strcmp(name, "dz")) { src = p->dz; bytes = BK * p->s.L * sizeof(float); }
+  else if (!strcmp(name, "z")) { src = p->z; bytes = BK * p->s.L * sizeof(float); }
+  else if (!strcmp(name, "G")) { src = p->G; bytes = BK * p->n_class * p->C * sizeof(float); }
+  else if (!strcmp(name, "pool")) { src = p->pool; bytes = BK * p->Cr * sizeof(float); }
+  else if (!strcmp(name, "stats")) { src = p->stats; bytes = BK * 8 * sizeof(double); }
+  else if (!strcmp(name, "auxs")) { src = p->auxs; bytes = BK * HW * 12 * sizeof(float); }
+  else if (!strncmp(name, "act", 3) || !strncmp(name, "gbuf", 4)) {
+    const bool is_g = name[0] == 'g';
+    act_idx = atoi(name + (is_g ? 4 : 3));
+    IOD_REQUIRE(act_idx >= 0 && act_idx < (is_g ? 2 : p->s.dec_layers), "bad buffer index in %s", name);
+    src = is_g ? p->gbuf[act_idx] : p->act[act_idx];
+    bytes = BK * HW * p->C * sizeof(float);
+    act_view = true;
+  } else {
+    set_error("iodine_debug_read: unknown buffer '%s'", name);
+    return 1;
+  }
+  if (bytes_out) *bytes_out = bytes;
+  if (!dst) return 0;
+  IOD_REQUIRE(dst_bytes >= bytes, "destination too small for %s: %zu < %zu", name, dst_bytes, bytes);
+  if (act_view && p->s.precision == IODINE_BF16) return tc_export_f32(p, src, (float*)dst, BK * HW * p->C, st);
+  IOD_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+IODINE_API int iodine_plan_launch_count(const IodinePlan* plan, uint64_t* count_out) {
+  IOD_REQUIRE(plan && count_out, "null argument");
+  *count_out = reinterpret_cast<const Plan*>(plan)->launches;
+  return 0;
+}
+
+}  // extern "C"

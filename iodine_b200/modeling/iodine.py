@@ -1,0 +1,272 @@
+"""IODINE -- host-side mirror of the reference model class (lib/modeling/iodine.py:7-408).
+
+Same constructor (``IODINE(ARCH)``), same methods (``encode / decode / reconstruct / elbo``,
+attribute ``sigma``) and the same state_dict keys and parameter shapes, so reference
+checkpoints load unchanged (lib/utils/checkpoint.py:68).  The sub-modules below are
+PARAMETER CONTAINERS only: all arithmetic of the refinement loop runs in the hand-written
+CUDA library behind ``iodine_b200.engine.RefinementEngine`` (C ABI, include/iodine_b200.h).
+There is no PyTorch/CPU fallback -- on a non-CUDA device the methods raise.
+"""
+import torch
+from torch import nn
+
+from .. import _cabi
+from ..engine import RefinementEngine
+from ..utils.vis_logger import logger
+
+
+class _MultiLayerConv(nn.Module):
+    """Parameter container for reference MultiLayerConv (iodine.py:570-594)."""
+
+    def __init__(self, dim_in, dim_out, n_layers, kernel_size, stride=1):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(n_layers):
+            self.layers.append(nn.Conv2d(dim_in, dim_out, kernel_size=kernel_size,
+                                         padding=kernel_size // 2, stride=stride))
+            dim_in = dim_out
+
+
+class _MLP(nn.Module):
+    """Parameter container for reference MLP (iodine.py:543-567)."""
+
+    def __init__(self, dim_in, dim_out, n_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(n_layers):
+            self.layers.append(nn.Linear(dim_in, dim_out))
+            dim_in = dim_out
+
+
+class _RefinementNetwork(nn.Module):
+    """Parameter container for reference RefinementNetwork (iodine.py:446-464); creation
+    order matches so that a seeded default init reproduces the reference's weights."""
+
+    def __init__(self, dim_in, dim_conv, dim_hidden, dim_out, n_layers, kernel_size, stride):
+        super().__init__()
+        self.mlc = _MultiLayerConv(dim_in, dim_conv, n_layers, kernel_size, stride=stride)
+        self.mlp = _MLP(dim_conv, dim_hidden, n_layers=1)
+        self.lstm = nn.LSTMCell(dim_hidden + 4 * dim_out, dim_hidden)
+        self.mean_update = nn.Linear(dim_hidden, dim_out)
+        self.logvar_update = nn.Linear(dim_hidden, dim_out)
+
+
+class _Decoder(nn.Module):
+    """Parameter container for reference Decoder (iodine.py:412-423)."""
+
+    def __init__(self, dim_in, dim_hidden, n_layers, kernel_size, img_size):
+        super().__init__()
+        self.mlc = _MultiLayerConv(dim_in + 2, dim_hidden, n_layers, kernel_size)
+        self.conv = nn.Conv2d(dim_hidden, 4, kernel_size=kernel_size, stride=1,
+                              padding=kernel_size // 2)
+        self.img_size = img_size
+
+
+class _Gaussian(nn.Module):
+    """Posterior state holder (reference Gaussian, iodine.py:596-604)."""
+
+    def __init__(self, dim_latent):
+        super().__init__()
+        self.mean = None
+        self.logvar = None
+        self.init_mean = nn.Parameter(data=torch.zeros(dim_latent))
+        self.init_logvar = nn.Parameter(data=torch.zeros(dim_latent))
+
+
+ALL_ENCODINGS = ('posterior', 'grad_post', 'image', 'means', 'mask', 'mask_logits',
+                 'mask_posterior', 'grad_means', 'grad_mask', 'likelihood',
+                 'leave_one_out_likelihood', 'coordinate')
+
+
+class IODINE(nn.Module):
+    def __init__(self, ARCH, precision='fp32'):
+        nn.Module.__init__(self)
+        self.arch = ARCH
+        self.dim_latent = ARCH.DIM_LATENT
+        self.n_iters = ARCH.ITERS
+        self.K = ARCH.SLOTS
+        self.encodings = list(ARCH.ENCODING)
+        self.img_channels = ARCH.IMG_CHANNELS
+        self.img_size = ARCH.IMG_SIZE
+        self.sigma = ARCH.SIGMA
+        self.use_layernorm = ARCH.LAYERNORM
+        self.use_stop_gradient = ARCH.STOP_GRADIENT
+        if precision not in _cabi.PRECISIONS:
+            raise ValueError('precision must be one of %s' % sorted(_cabi.PRECISIONS))
+        self.precision = precision
+        missing = [e for e in ALL_ENCODINGS if e not in self.encodings]
+        if missing:
+            # every shipped config of the reference enables all twelve (configs/*.yaml)
+            raise NotImplementedError('the native engine implements the full encoding set; '
+                                      'missing from ARCH.ENCODING: %s' % missing)
+        if self.img_channels != 3:
+            raise NotImplementedError('ARCH.IMG_CHANNELS must be 3')
+
+        input_size, lambda_size = self.get_input_size()
+        self.refine = _RefinementNetwork(
+            input_size, ARCH.REF.CONV_CHAN, ARCH.REF.MLP_UNITS, ARCH.DIM_LATENT,
+            ARCH.REF.CONV_LAYERS, kernel_size=ARCH.REF.KERNEL_SIZE, stride=ARCH.REF.STRIDE)
+        self.decoder = _Decoder(dim_in=ARCH.DIM_LATENT, dim_hidden=ARCH.DEC.CONV_CHAN,
+                                n_layers=ARCH.DEC.CONV_LAYERS, kernel_size=ARCH.DEC.KERNEL_SIZE,
+                                img_size=self.img_size)
+        self.posterior = _Gaussian(self.dim_latent)
+
+        # per-call state, as on the reference instance (iodine.py:37-52)
+        self.lstm_hidden = None
+        self.z = None
+        self.mean = None
+        self.mask = None
+        self.elbo_terms = None      # [T,2]: (sum_b log-lik, sum_b KL) per refinement step
+        self._engines = {}
+        self._weights_sig = {}
+        self.max_images_per_call = None   # None = automatic (fit the workspace in free HBM)
+
+    # ------------------------------------------------------------------ bookkeeping
+    def get_input_size(self):
+        """reference iodine.py:345-374 with every encoding enabled: (17, 4L)."""
+        return 3 * self.img_channels + 8, 4 * self.dim_latent
+
+    def _device(self):
+        return self.posterior.init_mean.device
+
+    def _sig(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _engine(self, B):
+        dev = self._device()
+        key = (int(B), str(dev), self.precision)
+        eng = self._engines.get(key)
+        if eng is None:
+            if len(self._engines) >= 2:          # keep at most two plans (full + tail chunk)
+                old = next(iter(self._engines))
+                self._engines.pop(old).close()
+                self._weights_sig.pop(old, None)
+            eng = RefinementEngine(self.arch, B, dev, self.precision)
+            self._engines[key] = eng
+        sig = self._sig()
+        if self._weights_sig.get(key) != sig:
+            eng.set_weights(self.state_dict())
+            self._weights_sig[key] = sig
+        return eng
+
+    def _chunk(self, B):
+        if self.max_images_per_call:
+            return min(B, int(self.max_images_per_call))
+        dev = self._device()
+        free, _ = torch.cuda.mem_get_info(dev)
+        a = self.arch
+        eb = 2 if self.precision == 'bf16' else 4
+        per_img = self.K * a.IMG_SIZE * a.IMG_SIZE * (
+            (a.DEC.CONV_LAYERS + 2) * a.DEC.CONV_CHAN * eb + (8 + 12 + 20 + 4) * 4
+            + a.REF.CONV_CHAN * 4 // 2)
+        cached = sum(e.workspace_bytes for e in self._engines.values())
+        return max(1, min(B, int(0.8 * (free + cached) // max(per_img, 1))))
+
+    def _noise(self, B, eps):
+        T, K, L = self.n_iters, self.K, self.dim_latent
+        if eps is None:
+            # reference: torch.randn_like on the model's device, T+1 draws (iodine.py:632)
+            return torch.randn(T + 1, B, K, L, device=self._device(), dtype=torch.float32)
+        assert tuple(eps.shape) == (T + 1, B, K, L), 'eps must be [T+1,B,K,L]'
+        return eps
+
+    def _require_cuda(self, x):
+        if self._device().type != 'cuda':
+            raise _cabi.IodineError(
+                'iodine_b200.IODINE runs on CUDA only (model is on %s). The reference CPU path '
+                'is not re-implemented here; there is no fallback.' % self._device())
+        return x.to(self._device())
+
+    # ------------------------------------------------------------------ public API
+    def decode(self, z):
+        """reference iodine.py:59-71: z[B,K,L] -> pred[B,3,H,W], mask[B,K,1,H,W], mean[B,K,3,H,W]"""
+        z = self._require_cuda(z)
+        B = z.shape[0]
+        outs = [self._engine(b1 - b0).decode(z[b0:b1]) for b0, b1 in self._spans(B)]
+        return tuple(torch.cat(t, dim=0) if len(t) > 1 else t[0] for t in zip(*outs))
+
+    def _spans(self, B):
+        c = self._chunk(B)
+        return [(b0, min(B, b0 + c)) for b0 in range(0, B, c)]
+
+    @torch.no_grad()
+    def encode(self, x, eps=None):
+        """reference iodine.py:73-105: x[B,3,H,W] -> z[B,K,L].  ``eps`` ([T+1,B,K,L]) injects
+        the noise the reference draws with torch.randn_like; default = fresh device noise."""
+        x = self._require_cuda(x)
+        B = x.shape[0]
+        eps = self._noise(B, eps)
+        zs, terms, posts = [], 0, []
+        for b0, b1 in self._spans(B):
+            z, t, post = self._engine(b1 - b0).encode(x[b0:b1], eps[:, b0:b1])
+            zs.append(z)
+            posts.append(post)
+            terms = terms + t
+        self.elbo_terms = terms
+        post = torch.cat(posts, dim=1)
+        self.posterior.mean, self.posterior.logvar = post[0], post[1]
+        self.z = torch.cat(zs, dim=0)
+        self._log_scalars(B)
+        return self.z
+
+    @torch.no_grad()
+    def reconstruct(self, x, eps=None):
+        """reference iodine.py:107-112: encode + decode."""
+        x = self._require_cuda(x)
+        B = x.shape[0]
+        eps = self._noise(B, eps)
+        outs, terms = [], 0
+        for b0, b1 in self._spans(B):
+            pred, mask, mean, z, t = self._engine(b1 - b0).reconstruct(x[b0:b1], eps[:, b0:b1])
+            outs.append((pred, mask, mean, z))
+            terms = terms + t
+        pred, mask, mean, z = (torch.cat(t, dim=0) if len(t) > 1 else t[0] for t in zip(*outs))
+        self.elbo_terms, self.z, self.mean, self.mask = terms, z, mean, mask
+        self._log_scalars(B)
+        self._log_images(x, pred, mask, mean)
+        return pred, mask, mean
+
+    @torch.no_grad()
+    def elbo(self, x, eps=None):
+        """reference iodine.py:161-241: single-pass ELBO (mean over batch) for the current
+        posterior (``self.posterior.mean/logvar``; the learnt initial posterior if unset)."""
+        x = self._require_cuda(x)
+        B, K, L = x.shape[0], self.K, self.dim_latent
+        mu, lv = self.posterior.mean, self.posterior.logvar
+        if mu is None or mu.shape[0] != B:
+            mu = self.posterior.init_mean.detach()[None, None].repeat(B, K, 1)
+            lv = self.posterior.init_logvar.detach()[None, None].repeat(B, K, 1)
+        if eps is None:
+            eps = torch.randn(B, K, L, device=self._device())
+        terms = 0
+        for b0, b1 in self._spans(B):
+            terms = terms + self._engine(b1 - b0).elbo_terms(x[b0:b1], eps[b0:b1], mu[b0:b1], lv[b0:b1])
+        logger.update(kl=terms[1] / B, likelihood=terms[0] / B)
+        return (terms[0] - terms[1]) / B
+
+    def elbo_per_step(self, B=None):
+        """ELBO of every refinement step of the last encode()/reconstruct() call, as the
+        reference would have returned from elbo() inside the loop (mean over batch)."""
+        t = self.elbo_terms
+        B = B or self.z.shape[0]
+        return (t[:, 0] - t[:, 1]) / B
+
+    def forward(self, x):
+        """Training objective (reference iodine.py:115-158).  Back-propagation through the
+        refinement loop is not part of the native inference path."""
+        raise NotImplementedError(
+            'IODINE.forward (training loss with BPTT through the refinement loop) is not '
+            'implemented by the native engine yet; encode/decode/reconstruct/elbo are.')
+
+    # ------------------------------------------------------------------ side channel (A9)
+    def _log_scalars(self, B):
+        if self.elbo_terms is not None and self.elbo_terms.numel():
+            logger.update(kl=self.elbo_terms[-1, 1] / B, likelihood=self.elbo_terms[-1, 0] / B)
+
+    def _log_images(self, x, pred, mask, mean):
+        logger.update(image=x[0], pred=pred[0])
+        logger.update(**{'mask_{}'.format(i): mask[0, i, 0] for i in range(self.K)})
+        logger.update(**{'pred_{}'.format(i): mean[0, i] for i in range(self.K)})
+
+    def state_for_debug(self, B):
+        return self._engine(B)
