@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- refinement-steps/sec (B*K*T / time) of IODINE's iterative-refinement loop.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+Workload (BASELINE.json configs[1]): CLEVR6 arch, 128x128, K=7, T=5, B=32 images PER GPU
+(weak scaling: every rank owns B whole images = B*K slot-images; the only cross-rank traffic
+is one all-reduce of the [T,2] ELBO partial sums per call).  Synthetic data:
+x ~ U[0,1), default-init weights under torch.manual_seed(0), eps ~ N(0,1).
+
+One "step" = one IODINE.encode() (T refinement iterations + final sample) over the batch.
+  value : device-resident inputs, CUDA events on the launching stream, max over ranks.
+  e2e   : the reference-facing call with HOST buffers -- iodine_reconstruct_host():
+          pinned x/eps H2D, encode + decode, pred/mask/mean/z/ELBO D2H, all inside the timer
+          (what lib/eval/ari_eval.py:22 + lib/engine/eval.py:27 do around model.reconstruct).
+  roofline : the dominant kernel = decoder C->C 3x3 convolutions (forward + data-gradient),
+          bracketed live by CUDA events inside the library (iodine_plan_profile).
+  cpu_baseline : the oracle port (oracle/restatement.py, torch CPU ops, all host threads) on a
+          bounded sample of the same workload (B reduced, stated).
+--impl reference : the reference's CPU implementation of the path.  /root/reference is not
+  present on the GPU box, so this is the oracle port (kind "port"), timed on reconstruct().
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import torch  # noqa: E402
+
+METRIC = 'refinement-steps/sec (BxKxT) CLEVR6 128x128 K=7 T=5'
+UNIT = 'refinement-steps/s'
+
+
+def clevr6_arch():
+    from oracle.arch import arch_by_name   # plain data (SimpleNamespace), no oracle compute
+    return arch_by_name('clevr6')
+
+
+def flops_per_unit(arch):
+    """F_dec = 2*HW*k^2*[(L+2)C + (n-1)C^2 + 4C]; F_unit = 2*F_dec + F_ref."""
+    HW = arch.IMG_SIZE ** 2
+    k2 = arch.DEC.KERNEL_SIZE ** 2
+    C, n, L = arch.DEC.CONV_CHAN, arch.DEC.CONV_LAYERS, arch.DIM_LATENT
+    f_dec = 2 * HW * k2 * ((L + 2) * C + (n - 1) * C * C + 4 * C)
+    f_cc_layer = 2 * HW * k2 * C * C           # one C->C layer on one slot-image
+    return f_dec, f_cc_layer
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1400.8), d.get('hbm_gbs', 6555.8), 'measured (MEASURED_PEAKS.json, sustained bf16)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# =========================================================================== CPU arms
+def oracle_port_steps_per_s(arch, B, calls, warmup, fn='encode', threads=None):
+    """Time the oracle port on the host cores: B*K*T / median wall of `calls` calls."""
+    from helpers import seeded_model
+    from oracle import restatement as S
+    if threads:
+        torch.set_num_threads(threads)
+    model = seeded_model(arch)
+    sd = S.state_dict_to(model.state_dict(), torch.float32)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 3, arch.IMG_SIZE, arch.IMG_SIZE, generator=g)
+    eps = torch.randn(arch.ITERS + 1, B, arch.SLOTS, arch.DIM_LATENT,
+                      generator=torch.Generator().manual_seed(123))
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + calls):
+            t0 = time.perf_counter()
+            S.encode_trace(sd, arch, x, eps)      # encode + decode == reconstruct()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return B * arch.SLOTS * arch.ITERS / med, med
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    arch = clevr6_arch()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # bounded sample per step so that the whole run ends within a few minutes
+    Bs = args.cpu_batch if steps + warm <= 16 else 1
+    v, med = oracle_port_steps_per_s(arch, Bs, steps, warm, threads=cores)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warm, 'ms_per_step': med * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'CLEVR6 128x128 K=7 T=5, reconstruct() on host cores, B=%d sample '
+                               '(steps/s is flat in B on CPU)' % Bs,
+                   'note': '/root/reference is absent on the GPU box: oracle port of the reference '
+                           'algorithm (torch CPU ops, closed-form grads, no unused weight-grads)'},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': 'reconstruct() of B=%d images (=%d units) per step' % (Bs, Bs * 35)},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =========================================================================== native arm
+def run_native(args):
+    import torch.distributed as dist
+    from iodine_b200.modeling.iodine import IODINE
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    arch = clevr6_arch()
+    B, K, T, L, S = args.batch, arch.SLOTS, arch.ITERS, arch.DIM_LATENT, arch.IMG_SIZE
+    torch.manual_seed(0)
+    model = IODINE(arch, precision=args.precision).to(dev)
+    model.max_images_per_call = B
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.rand(B, 3, S, S, generator=g).pin_memory()
+    eps_host = torch.randn(T + 1, B, K, L, generator=torch.Generator().manual_seed(123 + rank)).pin_memory()
+    x, eps = x_host.to(dev), eps_host.to(dev)
+    eng = model.state_for_debug(B)
+    pin = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
+    host_out = dict(pred=pin(B, 3, S, S), mask=pin(B, K, 1, S, S), mean=pin(B, K, 3, S, S),
+                    z=pin(B, K, L), terms=pin(T, 2))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        z, terms, _ = eng.encode(x, eps)
+        if world > 1:                      # the path's only exchange: ELBO partial sums
+            dist.all_reduce(terms)
+        return terms
+
+    def step_host():
+        out = eng.reconstruct_host(x_host, eps_host, host_out)   # synchronises
+        if world > 1:
+            t = out['terms'].to(dev)
+            dist.all_reduce(t)
+        return out
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- device-resident: warmup, then exactly `steps` timed steps
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = eng.launch_count()
+    eng.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launch_count() - n0
+    conv_ms, conv_n = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host-buffer C-ABI call
+    host_steps = 1 if args.profile_mode else args.steps
+    for _ in range(0 if args.profile_mode else max(1, min(args.warmup, 3))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(host_steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+
+    units_per_step = world * B * K * T
+    value = units_per_step * args.steps / (dev_ms * 1e-3)
+    e2e_value = units_per_step * host_steps / e2e_s
+    h2d = x_host.numel() * 4 + eps_host.numel() * 4
+    d2h = sum(v.numel() * 4 for v in host_out.values())
+
+    if rank == 0:
+        f_dec, f_cc = flops_per_unit(arch)
+        peak_tf, peak_gbs, peak_src = measured_peaks()
+        per_launch_flop = B * K * f_cc                     # one C->C layer over the rank's slots
+        achieved_tf = per_launch_flop * conv_n / (conv_ms * 1e-3) / 1e12 if conv_n else None
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32' if args.precision == 'fp32' else 'bf16 operands / f32 accumulate',
+            'data': 'synthetic',
+            'config': {'workload': 'CLEVR6 128x128 K=7 T=5 B=%d per GPU (configs[1]); step = one '
+                                   'IODINE.encode() over the batch' % B,
+                       'units_per_step': units_per_step, 'precision': args.precision,
+                       'l2': 'activations (%.2f GB/layer) exceed the 126 MB L2; no flush needed'
+                             % (B * K * S * S * arch.DEC.CONV_CHAN * (4 if args.precision == 'fp32' else 2) / 1e9),
+                       'parallelism': 'slot-shard x%d (whole images per rank)' % world},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h,
+                    'call': 'iodine_reconstruct_host (encode + decode, pinned host buffers)'},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {
+                'bound': 'tensor', 'kernel': 'decoder C->C 3x3 conv fwd+dgrad (%s)' % (
+                    'conv_cc_kernel FFMA' if args.precision == 'fp32' else 'conv_tc tcgen05'),
+                'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': (achieved_tf / peak_tf) if achieved_tf else None,
+                'traffic': None, 'peak_source': peak_src,
+                'launches_timed': int(conv_n), 'avg_launch_ms': conv_ms / conv_n if conv_n else None,
+                'flop_per_launch': per_launch_flop,
+                'share_of_step': conv_ms / dev_ms if dev_ms else None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, med = oracle_port_steps_per_s(arch, args.cpu_batch, 2, 1, threads=cores)
+            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': 'reconstruct() of B=%d images (%d units), median of 2, %.1f s each'
+                                              % (args.cpu_batch, args.cpu_batch * K * T, med)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='images per GPU')
+    ap.add_argument('--precision', default=os.environ.get('IODINE_PRECISION', 'fp32'))
+    ap.add_argument('--cpu-batch', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-mode', action='store_true',
+                    help='for runs under ncu: no warm-up clamp, no e2e loop, no CPU baseline')
+    args = ap.parse_args()
+    if args.impl == 'native' and not args.profile_mode:
+        args.warmup = max(args.warmup, 3)
+    if args.profile_mode:
+        args.no_cpu_baseline = True
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+               '--nproc-per-node', str(args.gpus), '--master-addr', '127.0.0.1',
+               '--master-port', os.environ.get('MASTER_PORT', '29517'), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_native(args)
+
+
+if __name__ == '__main__':
+    main()

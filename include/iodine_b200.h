@@ -159,6 +159,13 @@ IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, co
 IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, size_t dst_bytes,
                       size_t* bytes_out, void* stream);
 
+/* Measurement hook (bench.py's roofline): while enabled, every decoder C->C convolution
+ * launch (forward and data-gradient -- the dominant kernel) is bracketed by CUDA events on
+ * the launching stream.  iodine_plan_profile_read() synchronises those events, returns
+ * the summed device time in milliseconds and the number of bracketed launches, and resets. */
+IODINE_API int iodine_plan_profile(IodinePlan* plan, int enable);
+IODINE_API int iodine_plan_profile_read(IodinePlan* plan, double* ms_total_out, uint64_t* launches_out);
+
 /* number of kernel launches issued by this plan since creation (bench's gpu_launches) */
 IODINE_API int iodine_plan_launch_count(const IodinePlan* plan, uint64_t* count_out);
 

@@ -77,6 +77,9 @@ struct Plan {
   int ref_w[IODINE_MAX_LAYERS + 1];
   uint64_t launches = 0;
   bool weights_set = false;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
+  size_t prof_used = 0;
 
   // ---- weights (plan-owned device memory, allocated at create)
   float* wsum = nullptr;      // [n_class][C][L]   layer-1 tap sums per border class

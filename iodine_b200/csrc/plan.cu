@@ -81,12 +81,24 @@ __global__ void sample_kernel(const float* __restrict__ mu, const float* __restr
     z[i] = mu[i] + expf(0.5f * lv[i]) * eps[i];
 }
 
+// ---------------------------------------------------------------- profiling brackets
+static void prof_mark(Plan* p, cudaStream_t st) {
+  if (!p->profiling) return;
+  if (p->prof_used == p->prof_events.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    p->prof_events.push_back(e);
+  }
+  cudaEventRecord(p->prof_events[p->prof_used++], st);
+}
+
 // ---------------------------------------------------------------- decoder forward / dgrad
 static int decoder_forward(Plan* p, const float* mu, const float* lv, const float* eps,
                            const float* z_in, cudaStream_t st) {
   const IodineShape& s = p->s;
   if (launch_sample_l1(p, mu, lv, eps, z_in, (float*)p->act[0], st)) return 1;
   for (int l = 1; l < s.dec_layers; ++l) {
+    prof_mark(p, st);
     if (s.precision == IODINE_BF16) {
       if (tc_launch_conv(p, l, false, p->act[l - 1], nullptr, p->act[l], nullptr, st)) return 1;
     } else {
@@ -94,6 +106,7 @@ static int decoder_forward(Plan* p, const float* mu, const float* lv, const floa
                          (float*)p->act[l], nullptr, 0, st))
         return 1;
     }
+    prof_mark(p, st);
   }
   if (s.precision == IODINE_BF16) return tc_launch_out4(p, p->act[s.dec_layers - 1], p->out4, st);
   return launch_conv_out4(p, (const float*)p->act[s.dec_layers - 1], p->out4, st);
@@ -111,6 +124,7 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
   int cur = 0;
   for (int l = n - 1; l >= 1; --l) {
     const bool last = (l == 1);
+    prof_mark(p, st);
     if (s.precision == IODINE_BF16) {
       if (tc_launch_conv(p, l, true, p->gbuf[cur], p->act[l - 1], last ? nullptr : p->gbuf[cur ^ 1],
                          last ? p->G : nullptr, st))
@@ -121,6 +135,7 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
                          last ? p->G : nullptr, last ? 2 : 1, st))
         return 1;
     }
+    prof_mark(p, st);
     cur ^= 1;
   }
   return 0;
@@ -255,6 +270,7 @@ IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
   cudaFree(p->b_hh); cudaFree(p->head_w); cudaFree(p->head_b); cudaFree(p->init_mean);
   cudaFree(p->init_logvar);
   tc_free(p);
+  for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   delete p;
   return 0;
 }
@@ -405,6 +421,30 @@ IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, 
   IOD_REQUIRE(dst_bytes >= bytes, "destination too small for %s: %zu < %zu", name, dst_bytes, bytes);
   if (act_view && p->s.precision == IODINE_BF16) return tc_export_f32(p, src, (float*)dst, BK * HW * p->C, st);
   IOD_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+IODINE_API int iodine_plan_profile(IodinePlan* plan, int enable) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  IOD_REQUIRE(p, "null plan");
+  p->profiling = enable != 0;
+  p->prof_used = 0;
+  return 0;
+}
+
+IODINE_API int iodine_plan_profile_read(IodinePlan* plan, double* ms_total_out, uint64_t* launches_out) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  IOD_REQUIRE(p && ms_total_out && launches_out, "null argument");
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
+    IOD_CHECK_CUDA(cudaEventSynchronize(p->prof_events[i + 1]));
+    float ms = 0.f;
+    IOD_CHECK_CUDA(cudaEventElapsedTime(&ms, p->prof_events[i], p->prof_events[i + 1]));
+    tot += ms;
+  }
+  *ms_total_out = tot;
+  *launches_out = p->prof_used / 2;
+  p->prof_used = 0;
   return 0;
 }
 

@@ -212,3 +212,12 @@ class RefinementEngine:
         n = C.c_uint64()
         _cabi.check(self.lib.iodine_plan_launch_count(self._plan, C.byref(n)))
         return n.value
+
+    def profile(self, enable):
+        _cabi.check(self.lib.iodine_plan_profile(self._plan, 1 if enable else 0))
+
+    def profile_read(self):
+        """(summed device ms of the bracketed decoder-conv launches, number of launches)"""
+        ms, n = C.c_double(), C.c_uint64()
+        _cabi.check(self.lib.iodine_plan_profile_read(self._plan, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
