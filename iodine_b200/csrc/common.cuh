@@ -95,9 +95,7 @@ struct Plan {
   float *w_ih = nullptr, *w_hh = nullptr, *b_ih = nullptr, *b_hh = nullptr;
   float *head_w = nullptr, *head_b = nullptr;   // [2L, M] (mean rows then logvar rows), [2L]
   float *init_mean = nullptr, *init_logvar = nullptr;
-  // bf16 tensor-core weights (conv_tc.cu), [layer][tap][co][ci] K-major, fwd and dgrad
-  __nv_bfloat16* tc_w[IODINE_MAX_LAYERS];
-  __nv_bfloat16* tc_wt[IODINE_MAX_LAYERS];
+  void* tc = nullptr;         // tensor-core path state (conv_tc.cu: TcState), IODINE_BF16 only
 
   // ---- workspace carve-up (caller memory)
   void* ws = nullptr;
@@ -105,7 +103,8 @@ struct Plan {
   void* act[IODINE_MAX_LAYERS];   // [BK,H,W,C] fp32 (or bf16 in IODINE_BF16) post-activations
   void* gbuf[2];                  // dgrad ping-pong, same type as act
   float* out4 = nullptr;          // [BK,H,W,4]
-  float* seed4 = nullptr;         // [BK,H,W,4]
+  float* seed4 = nullptr;         // [BK,H,W,4] fp32; IODINE_BF16: the same bytes hold [BK,H,W,8] bf16
+                                  // (4 gradient channels + 4 zeros = one 8-channel plane)
   float* auxs = nullptr;          // [BK,H,W,12] per-slot raw aux channels
   float* lik = nullptr;           // [B,H,W] raw pixel likelihood
   float* enc20 = nullptr;         // [BK,H,W,20] normalised refinement input (17 + 3 pad)
@@ -171,5 +170,10 @@ int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* a
 int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st);
 int tc_launch_dgrad_in4(Plan* p, const float* seed4, const void* act_prev, void* gout, cudaStream_t st);
 int tc_export_f32(Plan* p, const void* src_bf16, float* dst, size_t n, cudaStream_t st);
+int tc_export_seed(Plan* p, const void* seed8, float* dst, cudaStream_t st);
+// collapsed first decoder layer into the chunk-planar bf16 layout, and the class-wise pixel
+// sums of the last data-gradient (its inverse)
+int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st);
+int tc_launch_class_sum(Plan* p, const void* g, cudaStream_t st);
 
 }  // namespace iod

@@ -1,13 +1,868 @@
-// conv_tc.cu -- tcgen05 (bf16) decoder convolutions.  Placeholder until the kernels land.
+// conv_tc.cu -- tcgen05 (5th-gen tensor core) decoder convolutions for sm_100a.
+//
+// Replaces, in the IODINE_BF16 precision mode, the same reference code as conv_f32.cu:
+// MultiLayerConv.forward layers >= 1 (reference lib/modeling/iodine.py:586-594), Decoder.conv
+// (iodine.py:422,435) and the data-gradient half of the autograd convolution_backward that
+// (B*elbo).backward() (iodine.py:90) runs through the decoder.
+//
+// Formulation: im2col-free implicit GEMM on a FLATTENED, zero-padded image.
+//   * activations live in HBM "chunk-planar": [slot-image][C/8][H][W][8] bf16, i.e. one plane
+//     per group of 8 channels, 16 bytes per pixel per plane;
+//   * a TMA producer streams halo rows (image row y, columns -pad .. W+pad-1, zero filled by
+//     the TMA unit outside the image) of every plane into a shared-memory RING of rows with
+//     pitch Ps (a multiple of 8 pixels).  In ring space pixel (row j, col c) sits at flat
+//     position j*Ps + c, so the 3x3 (5x5) tap (dy,dx) of ANY run of 128 consecutive output
+//     positions is the run of 128 consecutive ring positions shifted by dy*Ps + dx;
+//   * that run is exactly a K-major, no-swizzle UMMA operand: 8 consecutive positions x 16 B
+//     form one core matrix (128 contiguous bytes), SBO = 128 B between groups of 8 positions,
+//     LBO = the plane stride between the two 8-channel halves of one K=16 step.  No-swizzle
+//     descriptors only need a 16-byte aligned start address, which is what makes the shifted
+//     views legal without any im2col copy;
+//   * one elected thread issues tcgen05.mma (M=128 positions, N=Cout, K=16) for every
+//     (tap, 16-channel step) into a TMEM accumulator; 4 accumulator stages let the epilogue
+//     warps (tcgen05.ld -> bias/ELU or ELU' -> bf16 -> coalesced 16-byte stores, straight from
+//     registers into the chunk-planar output) overlap the next tile's MMAs;
+//   * ring slots wrap: the first `m` slots are mirrored behind the ring end so that a 128-run
+//     that straddles the wrap point is still contiguous.
+// The 4-channel ends of the decoder use the same kernel: decoder.conv (C -> 4) runs with
+// N = 16 (the smallest N of an M=128 UMMA; 12 zero columns), its data-gradient (4 -> C) packs TWO taps into one K=16 step by
+// pointing LBO at the flat distance between the taps (one 8-channel plane, 4 real channels).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace iod {
-int tc_supported(const Plan* p) { (void)p; set_error("IODINE_BF16: tensor-core path not built"); return 0; }
-int tc_alloc(Plan*) { return 0; }
-void tc_free(Plan*) {}
-int tc_on_workspace(Plan*) { return 0; }
-int tc_setup_weights(Plan*, const IodineWeights*, cudaStream_t) { return 0; }
-int tc_launch_conv(Plan*, int, bool, const void*, const void*, void*, float*, cudaStream_t) { set_error("tc path not built"); return 1; }
-int tc_launch_out4(Plan*, const void*, float*, cudaStream_t) { set_error("tc path not built"); return 1; }
-int tc_launch_dgrad_in4(Plan*, const float*, const void*, void*, cudaStream_t) { set_error("tc path not built"); return 1; }
-int tc_export_f32(Plan*, const void*, float*, size_t, cudaStream_t) { set_error("tc path not built"); return 1; }
+
+// ------------------------------------------------------------------------------------------------
+// parameters of one launch
+// ------------------------------------------------------------------------------------------------
+struct TcEntry {      // one tcgen05.mma per tile
+  int32_t shift;      // flat ring shift of the A run (dy*Ps + dx)
+  int32_t plane;      // first input plane of the K=16 step
+  int32_t lbo16;      // LBO in 16-byte units (plane stride, or tap distance for 8-channel inputs)
+  int32_t boff16;     // start of the step's B image inside the weight block, 16-byte units
+};
+constexpr int TC_MAX_ENTRIES = 56;
+constexpr int TC_MAX_RING = 32;
+constexpr int TC_THREADS = 192;       // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
+constexpr int TC_ACC_STAGES = 4;
+
+enum TcEpi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_OUT4 = 2 };
+
+struct alignas(64) TcParams {
+  CUtensorMap tmap;               // source activations, 5-D {8, W, H, planes, BK}
+  TcEntry ent[TC_MAX_ENTRIES];
+  int32_t n_ent;
+  int32_t nch_in;                 // input planes
+  int32_t nch_out;                // output planes (N/8) for the bf16 epilogues
+  int32_t H, W;
+  int32_t pad;
+  int32_t Ps;                     // ring row pitch, positions
+  int32_t R, m;                   // ring rows, mirrored rows
+  int32_t segs;                   // W/128 when tiles are row aligned, 0 = flat tiling
+  int32_t TH;                     // image rows per work item
+  int32_t strips;                 // ceil(H / TH)
+  int32_t items;                  // BK * strips
+  uint32_t idesc;
+  uint32_t w_bytes;               // weight image bytes (multiple of 16)
+  uint32_t box_bytes;             // bytes of one (row, plane) TMA box
+  uint32_t plane_stride16;        // ring plane stride, 16-byte units
+  const void* wimg;               // packed bf16 weights (global), layout = smem image
+  const float* bias;              // [N] (EPI_FWD, EPI_OUT4)
+  const uint4* actp;              // chunk-planar previous activation (EPI_DGRAD)
+  void* out;                      // chunk-planar bf16 (uint4 per position-plane) or fp32 out4
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A deadlock must become a launch failure, never a hung GPU: bounded wait, then trap.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("conv_tc: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, (int)blockIdx.x,
+             (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, layout type 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)(addr16 & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) |
+         ((uint64_t)(sbo16 & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+#define IOD_TMEM_LD16(r, addr)                                                                  \
+  asm volatile(                                                                                 \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                 \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                          \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),      \
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), \
+        "=r"(r[14]), "=r"(r[15])                                                                \
+      : "r"(addr))
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+// ELU with the hardware exponential: |error| <= ~2e-7 absolute, far below bf16 rounding.
+__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+struct TcSmem {                    // tail of the dynamic shared memory block
+  uint64_t full[TC_MAX_RING];
+  uint64_t empty[TC_MAX_RING];
+  uint64_t tfull[TC_ACC_STAGES];
+  uint64_t tempty[TC_ACC_STAGES];
+  uint64_t wbar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ int tc_tile_start(const TcParams& p, int t) {
+  return p.segs ? (t / p.segs) * p.Ps + (t % p.segs) * 128 : t * 128;
+}
+__device__ __forceinline__ int tc_num_tiles(const TcParams& p, int th) {
+  return p.segs ? th * p.segs : ((th - 1) * p.Ps + p.W - 1) / 128 + 1;
+}
+
+template <int N, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int TMEM_COLS = (TC_ACC_STAGES * N < 32) ? 32 : TC_ACC_STAGES * N;
+  const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
+  uint8_t* s_w = smem;
+  uint8_t* s_a = smem + w_region;
+  const uint32_t plane_bytes = p.plane_stride16 * 16u;
+  TcSmem* sb = reinterpret_cast<TcSmem*>(s_a + (size_t)p.nch_in * plane_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pad = p.pad, Ps = p.Ps, R = p.R;
+  const int Q = R * Ps;
+
+  // ---- one-time setup: zero the ring (no stale NaN patterns under discarded positions),
+  //      barriers, TMEM
+  {
+    uint4* a4 = reinterpret_cast<uint4*>(s_a);
+    const int n16 = p.nch_in * (int)p.plane_stride16;
+    for (int i = threadIdx.x; i < n16; i += TC_THREADS) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < R; ++i) {
+      mbar_init(smem_u32(&sb->full[i]), 1);
+      mbar_init(smem_u32(&sb->empty[i]), 1);
+    }
+    for (int i = 0; i < TC_ACC_STAGES; ++i) {
+      mbar_init(smem_u32(&sb->tfull[i]), 1);
+      mbar_init(smem_u32(&sb->tempty[i]), 4);      // one arrive per epilogue warp
+    }
+    mbar_init(smem_u32(&sb->wbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sb->tmem_base)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sb->tmem_base;
+
+  if (warp == 0) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      {  // weights: one shot, resident for the whole kernel
+        const uint32_t wbar = smem_u32(&sb->wbar);
+        mbar_expect_tx(wbar, p.w_bytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg);
+        for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
+          const uint32_t n = (p.w_bytes - off < 16384u) ? (p.w_bytes - off) : 16384u;
+          bulk_load_1d(smem_u32(s_w + off), src + off, n, wbar);
+        }
+      }
+      const uint32_t a_base = smem_u32(s_a);
+      const uint32_t row_bytes = (uint32_t)Ps * 16u;
+      int g = 0;                                   // global halo-row counter of this CTA
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.strips, y0 = (item % p.strips) * p.TH;
+        const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
+        const int nrows = th + 2 * pad;
+        for (int j = 0; j < nrows; ++j, ++g) {
+          const int slot = g % R;
+          const uint32_t ph = (uint32_t)(g / R) & 1u;
+          mbar_wait(smem_u32(&sb->empty[slot]), ph ^ 1u, 1);
+          const uint32_t fb = smem_u32(&sb->full[slot]);
+          const bool mir = slot < p.m;
+          mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (mir ? 2u : 1u));
+          const int y = y0 - pad + j;
+          for (int c = 0; c < p.nch_in; ++c) {
+            const uint32_t dst = a_base + (uint32_t)c * plane_bytes + (uint32_t)slot * row_bytes;
+            tma_load_5d(dst, &p.tmap, fb, 0, -pad, y, c, n);
+            if (mir) tma_load_5d(dst + (uint32_t)R * row_bytes, &p.tmap, fb, 0, -pad, y, c, n);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      mbar_wait(smem_u32(&sb->wbar), 0, 2);
+      const uint32_t a_base16 = smem_u32(s_a) >> 4;
+      const uint32_t w_base16 = smem_u32(s_w) >> 4;
+      int g0 = 0, rows_ready = 0, rows_freed = 0, tau = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int y0 = (item % p.strips) * p.TH;
+        const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
+        const int nrows = th + 2 * pad;
+        const int ntiles = tc_num_tiles(p, th);
+        for (int t = 0; t < ntiles; ++t, ++tau) {
+          const int s = tc_tile_start(p, t);
+          int need = (s + 127 + 2 * pad * Ps + 2 * pad) / Ps;
+          if (need > nrows - 1) need = nrows - 1;
+          while (rows_ready <= g0 + need) {
+            mbar_wait(smem_u32(&sb->full[rows_ready % R]), (uint32_t)(rows_ready / R) & 1u, 3);
+            ++rows_ready;
+          }
+          const int stage = tau % TC_ACC_STAGES;
+          mbar_wait(smem_u32(&sb->tempty[stage]), ((uint32_t)(tau / TC_ACC_STAGES) & 1u) ^ 1u, 4);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(stage * N);
+          const int base_pos = ((g0 % R) * Ps + s) % Q;
+          for (int e = 0; e < p.n_ent; ++e) {
+            const TcEntry en = p.ent[e];
+            int pos = base_pos + en.shift;
+            if (pos >= Q) pos -= Q;
+            const uint64_t ad = make_desc(a_base16 + (uint32_t)en.plane * p.plane_stride16 + (uint32_t)pos,
+                                          (uint32_t)en.lbo16, 8u);
+            const uint64_t bd = make_desc(w_base16 + (uint32_t)en.boff16, (uint32_t)N, 8u);
+            tc_mma_bf16(d_tmem, ad, bd, p.idesc, e > 0 ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&sb->tfull[stage]));
+          // rows that no later tile of this CTA reads go back to the producer
+          const int free_upto = (t + 1 < ntiles) ? g0 + tc_tile_start(p, t + 1) / Ps : g0 + nrows;
+          while (rows_freed < free_upto) {
+            tc_commit(smem_u32(&sb->empty[rows_freed % R]));
+            ++rows_freed;
+          }
+        }
+        g0 += nrows;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int H = p.H, W = p.W;
+    constexpr int NB = (EPI == EPI_FWD) ? N : 4;
+    float bias_r[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) bias_r[i] = (EPI == EPI_DGRAD) ? 0.f : __ldg(p.bias + i);
+    int tau = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int n = item / p.strips, y0 = (item % p.strips) * p.TH;
+      const int th = (H - y0 < p.TH) ? (H - y0) : p.TH;
+      const int ntiles = tc_num_tiles(p, th);
+      for (int t = 0; t < ntiles; ++t, ++tau) {
+        const int stage = tau % TC_ACC_STAGES;
+        const int flat = tc_tile_start(p, t) + quad * 32 + lane;
+        const int r = flat / Ps, c = flat - r * Ps;
+        const bool valid = (c < W) && (r < th);
+        const int y = y0 + r;
+        const size_t pix = valid ? ((size_t)y * W + c) : 0;
+        const size_t plane_sz = (size_t)H * W;
+
+        // previous activation for ELU' (issued before the accumulator wait to overlap latency)
+        uint4 av[(EPI == EPI_DGRAD) ? N / 8 : 1];
+        if constexpr (EPI == EPI_DGRAD) {
+#pragma unroll
+          for (int k = 0; k < N / 8; ++k)
+            av[k] = valid ? __ldg(p.actp + ((size_t)n * (N / 8) + k) * plane_sz + pix) : make_uint4(0u, 0u, 0u, 0u);
+        }
+
+        mbar_wait(smem_u32(&sb->tfull[stage]), (uint32_t)(tau / TC_ACC_STAGES) & 1u, 5);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(stage * N) + ((uint32_t)(quad * 32) << 16);
+        uint32_t acc[N];
+#pragma unroll
+        for (int q = 0; q < N / 16; ++q) IOD_TMEM_LD16((acc + q * 16), taddr + q * 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[stage]));   // accumulator stage is free again
+
+        if (!valid) continue;
+        if constexpr (EPI == EPI_OUT4) {
+          float4 o;
+          o.x = __uint_as_float(acc[0]) + bias_r[0];
+          o.y = __uint_as_float(acc[1]) + bias_r[1];
+          o.z = __uint_as_float(acc[2]) + bias_r[2];
+          o.w = __uint_as_float(acc[3]) + bias_r[3];
+          reinterpret_cast<float4*>(p.out)[(size_t)n * plane_sz + pix] = o;
+        } else {
+          uint4* outp = reinterpret_cast<uint4*>(p.out);
+#pragma unroll
+          for (int k = 0; k < N / 8; ++k) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[k * 8 + e]);
+            if constexpr (EPI == EPI_FWD) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = elu_fast(v[e] + bias_r[k * 8 + e]);
+            } else {
+              const uint32_t aw[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 a = unpack_bf16(aw[e]);
+                v[2 * e] *= elu_grad_from_act(a.x);
+                v[2 * e + 1] *= elu_grad_from_act(a.y);
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16(v[0], v[1]);
+            o.y = pack_bf16(v[2], v[3]);
+            o.z = pack_bf16(v[4], v[5]);
+            o.w = pack_bf16(v[6], v[7]);
+            outp[((size_t)n * (N / 8) + k) * plane_sz + pix] = o;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TcGeom {             // shared-memory geometry of one kernel flavour
+  int Ps, R, m, segs, TH;
+  uint32_t w_bytes, plane_stride16, box_bytes;
+  size_t smem;
+};
+
+struct TcState {
+  CUtensorMap map_act[IODINE_MAX_LAYERS];
+  CUtensorMap map_g[2];
+  CUtensorMap map_seed;
+  __nv_bfloat16* w_fwd[IODINE_MAX_LAYERS];    // layers 1..n-1
+  __nv_bfloat16* w_bwd[IODINE_MAX_LAYERS];
+  __nv_bfloat16* w_out = nullptr;             // decoder.conv forward, N = 16 (4 real rows)
+  __nv_bfloat16* w_in4 = nullptr;             // decoder.conv data-gradient, tap pairs
+  float* ptab_c = nullptr;                    // chunk-planar fp32 copy of ptab
+  int n_ent_cc = 0, n_ent_in4 = 0;
+  TcGeom g_cc, g_out, g_in4;
+  bool attr_done = false;
+};
+
+static TcState* tc_state(Plan* p) { return reinterpret_cast<TcState*>(p->tc); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, void* base, int W, int H, int planes, int BK, int pad) {
+  EncodeTiledFn fn = get_encode_fn();
+  IOD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes, (cuuint64_t)BK};
+  cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)planes * H * W * 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)(W + 2 * pad), 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IOD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+static int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// geometry for (input planes, N, entries, max extra reach of an entry's second K half)
+static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo_pos, TcGeom* g) {
+  const IodineShape& s = p->s;
+  const int pad = s.dec_k / 2;
+  if (s.W + 2 * pad > 256) return false;                      // TMA box limit
+  g->Ps = round_up(s.W + 2 * pad, 8);
+  g->segs = (s.W % 128 == 0) ? s.W / 128 : 0;
+  g->w_bytes = (uint32_t)n_ent * 2u * (uint32_t)N * 16u;
+  g->box_bytes = (uint32_t)(s.W + 2 * pad) * 16u;
+  g->m = (127 + max_lbo_pos + g->Ps - 1) / g->Ps;
+  const size_t row_bytes = (size_t)nch_in * g->Ps * 16;
+  const size_t budget = (size_t)227 * 1024 - round_up((int)g->w_bytes, 1024) - 1024 - sizeof(TcSmem);
+  int rows = (int)(budget / row_bytes);
+  int R = rows - g->m;
+  if (R > TC_MAX_RING) R = TC_MAX_RING;
+  const int span = g->segs ? 2 * pad + 1 : (127 + 2 * pad * g->Ps + 2 * pad) / g->Ps + 2;
+  if (R < span + 1 || R <= g->m) return false;
+  g->R = R;
+  g->plane_stride16 = (uint32_t)(R + g->m) * g->Ps;
+  if (g->plane_stride16 >= 16384u) return false;              // LBO field is 14 bits
+  // rows per work item: balance the grid (items >> SMs) against halo re-reads
+  int TH = 8;
+  if (s.H < 8) TH = s.H;
+  g->TH = TH;
+  g->smem = (size_t)round_up((int)g->w_bytes, 1024) + (size_t)nch_in * g->plane_stride16 * 16 + sizeof(TcSmem) + 64;
+  return g->smem <= (size_t)227 * 1024;
+}
+
+int tc_supported(const Plan* p) {
+  const IodineShape& s = p->s;
+  const int C = s.dec_chan, kk = s.dec_k * s.dec_k;
+  TcGeom g;
+  if (C % 16 != 0) { set_error("IODINE_BF16: DEC.CONV_CHAN=%d must be a multiple of 16", C); return 0; }
+  const int n_cc = kk * (C / 16);
+  if (n_cc > TC_MAX_ENTRIES || !tc_geometry(p, C / 8, C, n_cc, 0, &g)) {
+    set_error("IODINE_BF16: decoder shape (C=%d, k=%d, W=%d) does not fit the tensor-core kernel's shared memory",
+              C, s.dec_k, s.W);
+    return 0;
+  }
+  return 1;
+}
+
+int tc_alloc(Plan* p) {
+  TcState* st = new TcState();
+  p->tc = st;
+  const IodineShape& s = p->s;
+  const int C = p->C, kk = s.dec_k * s.dec_k, pad = s.dec_k / 2;
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { st->w_fwd[l] = nullptr; st->w_bwd[l] = nullptr; }
+  st->n_ent_cc = kk * (C / 16);
+  st->n_ent_in4 = (kk + 1) / 2;
+  const int Ps = round_up(s.W + 2 * pad, 8);
+  IOD_REQUIRE(tc_geometry(p, C / 8, C, st->n_ent_cc, 0, &st->g_cc), "tc geometry (C->C) failed");
+  IOD_REQUIRE(tc_geometry(p, C / 8, 16, st->n_ent_cc, 0, &st->g_out), "tc geometry (C->4) failed");
+  IOD_REQUIRE(tc_geometry(p, 1, C, st->n_ent_in4, Ps, &st->g_in4), "tc geometry (4->C) failed");
+  for (int l = 1; l < s.dec_layers; ++l) {
+    IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd[l], st->g_cc.w_bytes));
+    IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_bwd[l], st->g_cc.w_bytes));
+  }
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_out, st->g_out.w_bytes));
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_in4, st->g_in4.w_bytes));
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->ptab_c, (size_t)p->HW * C * sizeof(float)));
+  return 0;
+}
+
+void tc_free(Plan* p) {
+  TcState* st = tc_state(p);
+  if (!st) return;
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { cudaFree(st->w_fwd[l]); cudaFree(st->w_bwd[l]); }
+  cudaFree(st->w_out); cudaFree(st->w_in4); cudaFree(st->ptab_c);
+  delete st;
+  p->tc = nullptr;
+}
+
+int tc_on_workspace(Plan* p) {
+  TcState* st = tc_state(p);
+  const IodineShape& s = p->s;
+  const int pad = s.dec_k / 2, planes = p->C / 8;
+  for (int l = 0; l < s.dec_layers; ++l)
+    if (make_map(&st->map_act[l], p->act[l], s.W, s.H, planes, p->BK, pad)) return 1;
+  if (s.dec_layers > 1)
+    for (int i = 0; i < 2; ++i)
+      if (make_map(&st->map_g[i], p->gbuf[i], s.W, s.H, planes, p->BK, pad)) return 1;
+  if (make_map(&st->map_seed, p->seed4, s.W, s.H, 1, p->BK, pad)) return 1;
+  return 0;
+}
+
+// ---- weight packing -----------------------------------------------------------------------------
+// image layout (= the shared-memory image): [entry][k-half (2)][n (N)][8 k-elements] bf16.
+// C->C: entry = tap*(C/16) + ks, k-half kc covers input channels (2ks+kc)*8 .. +7.
+//   fwd : B[n=co][k=ci]  = W[co][ci][dy][dx]
+//   bwd : B[n=ci][k=co]  = W[co][ci][k-1-dy][k-1-dx]     (data-gradient = conv with flipped taps)
+__global__ void tc_pack_cc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                                  __nv_bfloat16* __restrict__ bwd, int C, int NO, int N, int KS) {
+  // w is OIHW [NO][C][KS][KS]; fwd image has N >= NO output rows (zero padded); bwd needs NO == C == N
+  const int nks = C / 16;
+  const int total = KS * KS * nks * 2 * N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, n = (i / 8) % N, kc = (i / (8 * N)) % 2, ks = (i / (16 * N)) % nks, tap = i / (16 * N * nks);
+    const int dy = tap / KS, dx = tap % KS;
+    const int k = (2 * ks + kc) * 8 + e;
+    if (fwd) fwd[i] = __float2bfloat16(n < NO ? w[(((size_t)n * C + k) * KS + dy) * KS + dx] : 0.f);
+    if (bwd) bwd[i] = __float2bfloat16(w[(((size_t)k * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)]);
+  }
+}
+// 4->C data-gradient of decoder.conv [4][C][k][k]; entry = tap pair (2q, 2q+1); the odd tail
+// reuses the previous tap with zero weights in its first half.  B[n=ci][k=o] (o < 4 real).
+__global__ void tc_pack_in4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img, int C, int KS) {
+  const int kk = KS * KS, npair = (kk + 1) / 2;
+  const int total = npair * 2 * C * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, n = (i / 8) % C, kc = (i / (8 * C)) % 2, q = i / (16 * C);
+    int tap = 2 * q + kc;
+    bool zero = false;
+    if (2 * q + 1 >= kk) {            // odd tail: (kk-2, kk-1) with the first half zeroed
+      tap = kk - 2 + kc;
+      zero = (kc == 0);
+    }
+    const int dy = tap / KS, dx = tap % KS;
+    float v = 0.f;
+    if (!zero && e < 4) v = w[(((size_t)e * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)];
+    img[i] = __float2bfloat16(v);
+  }
+}
+__global__ void tc_ptab_planar_kernel(const float* __restrict__ ptab, float* __restrict__ ptab_c, int HW, int C) {
+  const int total = HW * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, pix = (i / 8) % HW, k = i / (8 * HW);
+    ptab_c[i] = ptab[(size_t)pix * C + k * 8 + e];
+  }
+}
+
+int tc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
+  TcState* st = tc_state(p);
+  const IodineShape& s = p->s;
+  const int C = p->C, KS = s.dec_k;
+  for (int l = 1; l < s.dec_layers; ++l) {
+    tc_pack_cc_kernel<<<64, 256, 0, st_>>>(w->dec_w[l], st->w_fwd[l], st->w_bwd[l], C, C, C, KS);
+    IOD_LAUNCH_CHECK(p);
+  }
+  tc_pack_cc_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_out, nullptr, C, 4, 16, KS);
+  IOD_LAUNCH_CHECK(p);
+  tc_pack_in4_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_in4, C, KS);
+  IOD_LAUNCH_CHECK(p);
+  tc_ptab_planar_kernel<<<256, 256, 0, st_>>>(p->ptab, st->ptab_c, p->HW, C);   // after pack_ptab (same stream)
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// ---- launch -------------------------------------------------------------------------------------
+static uint32_t make_idesc(int N) {
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major A and B,
+  // n_dim = N>>3 @17, m_dim = 128>>4 @24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcParams* q) {
+  const IodineShape& s = p->s;
+  q->nch_in = nch_in;
+  q->nch_out = N / 8;
+  q->H = s.H; q->W = s.W; q->pad = s.dec_k / 2;
+  q->Ps = g.Ps; q->R = g.R; q->m = g.m; q->segs = g.segs; q->TH = g.TH;
+  q->strips = (s.H + g.TH - 1) / g.TH;
+  q->items = p->BK * q->strips;
+  q->idesc = make_idesc(N);
+  q->w_bytes = g.w_bytes;
+  q->box_bytes = g.box_bytes;
+  q->plane_stride16 = g.plane_stride16;
+}
+
+static void fill_entries_cc(const Plan* p, const TcGeom& g, int N, TcParams* q) {
+  const int KS = p->s.dec_k, nks = p->C / 16;
+  int e = 0;
+  for (int tap = 0; tap < KS * KS; ++tap)
+    for (int ks = 0; ks < nks; ++ks, ++e) {
+      q->ent[e].shift = (tap / KS) * g.Ps + (tap % KS);
+      q->ent[e].plane = 2 * ks;
+      q->ent[e].lbo16 = (int32_t)g.plane_stride16;
+      q->ent[e].boff16 = e * 2 * N;
+    }
+  q->n_ent = e;
+}
+
+static void fill_entries_in4(const Plan* p, const TcGeom& g, int N, TcParams* q) {
+  const int KS = p->s.dec_k, kk = KS * KS;
+  auto shift = [&](int tap) { return (tap / KS) * g.Ps + (tap % KS); };
+  int e = 0;
+  for (int a = 0; a < kk; a += 2, ++e) {
+    int ta = a, tb = a + 1;
+    if (tb >= kk) { ta = kk - 2; tb = kk - 1; }
+    q->ent[e].shift = shift(ta);
+    q->ent[e].plane = 0;
+    q->ent[e].lbo16 = shift(tb) - shift(ta);
+    q->ent[e].boff16 = e * 2 * N;
+  }
+  q->n_ent = e;
+}
+
+template <int N, int EPI>
+static int tc_launch_t(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
+  auto kern = conv_tc_kernel<N, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    IOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  const int grid = q.items < p->num_sms ? q.items : p->num_sms;
+  kern<<<grid, TC_THREADS, smem, st_>>>(q);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+template <int EPI>
+static int tc_launch_n(Plan* p, int N, const TcParams& q, size_t smem, cudaStream_t st_) {
+  switch (N) {
+    case 16: return tc_launch_t<16, EPI>(p, q, smem, st_);
+    case 32: return tc_launch_t<32, EPI>(p, q, smem, st_);
+    case 64: return tc_launch_t<64, EPI>(p, q, smem, st_);
+    default: set_error("conv_tc: unsupported N=%d", N); return 1;
+  }
+}
+
+static const CUtensorMap* find_map(Plan* p, const void* buf) {
+  TcState* st = tc_state(p);
+  for (int l = 0; l < p->s.dec_layers; ++l)
+    if (buf == p->act[l]) return &st->map_act[l];
+  for (int i = 0; i < 2; ++i)
+    if (buf == p->gbuf[i]) return &st->map_g[i];
+  if (buf == (const void*)p->seed4) return &st->map_seed;
+  return nullptr;
+}
+
+int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* act_prev, void* out, float* G,
+                   cudaStream_t st_) {
+  (void)G;
+  TcState* st = tc_state(p);
+  const CUtensorMap* map = find_map(p, in);
+  IOD_REQUIRE(map != nullptr, "conv_tc: source buffer has no tensor map");
+  TcParams q;
+  q.tmap = *map;
+  fill_common(p, st->g_cc, p->C / 8, p->C, &q);
+  fill_entries_cc(p, st->g_cc, p->C, &q);
+  q.wimg = dgrad ? st->w_bwd[layer] : st->w_fwd[layer];
+  q.bias = dgrad ? nullptr : p->dec[layer].b;
+  q.actp = reinterpret_cast<const uint4*>(act_prev);
+  q.out = out;
+  if (dgrad) return tc_launch_n<EPI_DGRAD>(p, p->C, q, st->g_cc.smem, st_);
+  return tc_launch_n<EPI_FWD>(p, p->C, q, st->g_cc.smem, st_);
+}
+
+int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st_) {
+  TcState* st = tc_state(p);
+  const CUtensorMap* map = find_map(p, in);
+  IOD_REQUIRE(map != nullptr, "conv_tc: source buffer has no tensor map");
+  TcParams q;
+  q.tmap = *map;
+  fill_common(p, st->g_out, p->C / 8, 16, &q);
+  fill_entries_cc(p, st->g_out, 16, &q);
+  q.wimg = st->w_out;
+  q.bias = p->out_b;
+  q.actp = nullptr;
+  q.out = out4;
+  return tc_launch_t<16, EPI_OUT4>(p, q, st->g_out.smem, st_);
+}
+
+int tc_launch_dgrad_in4(Plan* p, const float* seed8, const void* act_prev, void* gout, cudaStream_t st_) {
+  TcState* st = tc_state(p);
+  (void)seed8;
+  TcParams q;
+  q.tmap = st->map_seed;
+  fill_common(p, st->g_in4, 1, p->C, &q);
+  fill_entries_in4(p, st->g_in4, p->C, &q);
+  q.wimg = st->w_in4;
+  q.bias = nullptr;
+  q.actp = reinterpret_cast<const uint4*>(act_prev);
+  q.out = gout;
+  return tc_launch_n<EPI_DGRAD>(p, p->C, q, st->g_in4.smem, st_);
+}
+
+// ---- helpers around the chunk-planar layout -------------------------------------------------------
+// act0[n][k][y][x][8] = ELU(u[n][class(y,x)][co] + ptab_c[k][y][x][8])   (first decoder layer, collapsed)
+__global__ void __launch_bounds__(256)
+tc_layer1_kernel(const float* __restrict__ u, const float* __restrict__ ptab_c, uint4* __restrict__ act0,
+                 int H, int W, int C, int KS) {
+  const int n = blockIdx.z, k = blockIdx.y;
+  const int P = KS / 2, HW = H * W;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    const int y = pix / W, x = pix - y * W;
+    const int cls = border_class(y, H, P) * KS + border_class(x, W, P);
+    const float4* uv = reinterpret_cast<const float4*>(u + ((size_t)n * KS * KS + cls) * C + k * 8);
+    const float4* pv = reinterpret_cast<const float4*>(ptab_c + ((size_t)k * HW + pix) * 8);
+    const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1), p0 = __ldg(pv), p1 = __ldg(pv + 1);
+    uint4 o;
+    o.x = pack_bf16(elu_f(u0.x + p0.x), elu_f(u0.y + p0.y));
+    o.y = pack_bf16(elu_f(u0.z + p0.z), elu_f(u0.w + p0.w));
+    o.z = pack_bf16(elu_f(u1.x + p1.x), elu_f(u1.y + p1.y));
+    o.w = pack_bf16(elu_f(u1.z + p1.z), elu_f(u1.w + p1.w));
+    act0[((size_t)n * (C / 8) + k) * HW + pix] = o;
+  }
+}
+
+int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st_) {
+  TcState* st = tc_state(p);
+  int gx = (p->HW + 255) / 256;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, p->C / 8, p->BK);
+  tc_layer1_kernel<<<grid, 256, 0, st_>>>(p->u, st->ptab_c, reinterpret_cast<uint4*>(act0), p->s.H, p->s.W, p->C,
+                                          p->s.dec_k);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// G[n][class][co] = sum over pixels of the class of g[n][co/8][y][x][co%8]  (layer-1 dgrad collapse)
+__global__ void __launch_bounds__(256)
+tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, int W, int C, int KS, int rows_per_block) {
+  const int n = blockIdx.z, k = blockIdx.y;
+  const int P = KS / 2, HW = H * W;
+  const int y_lo = blockIdx.x * rows_per_block;
+  const int y_hi = (y_lo + rows_per_block < H) ? y_lo + rows_per_block : H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float red[8][8];
+  float* Gn = G + (size_t)n * KS * KS * C + k * 8;
+  float run[8];
+  int cy_run = -1;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) run[e] = 0.f;
+  auto flush = [&](int cy) {
+    // block-reduce the interior-column run of rows with equal class cy
+#pragma unroll
+    for (int e = 0; e < 8; ++e) run[e] = warp_sum(run[e]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][e] = run[e];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+      atomicAdd(Gn + (size_t)(cy * KS + P) * C + threadIdx.x, t);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) run[e] = 0.f;
+  };
+  for (int y = y_lo; y < y_hi; ++y) {
+    const int cy = border_class(y, H, P);          // block-uniform
+    if (cy != cy_run && cy_run >= 0) flush(cy_run);
+    cy_run = cy;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+      const uint4 v = __ldg(g + ((size_t)n * (C / 8) + k) * HW + (size_t)y * W + x);
+      const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+      const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+      const int cx = border_class(x, W, P);
+      if (cx == P) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) run[e] += f[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(Gn + (size_t)(cy * KS + cx) * C + e, f[e]);
+      }
+    }
+  }
+  if (cy_run >= 0) flush(cy_run);
+}
+
+int tc_launch_class_sum(Plan* p, const void* g, cudaStream_t st_) {
+  const int rpb = 16;
+  dim3 grid((p->s.H + rpb - 1) / rpb, p->C / 8, p->BK);
+  tc_class_sum_kernel<<<grid, 256, 0, st_>>>(reinterpret_cast<const uint4*>(g), p->G, p->s.H, p->s.W, p->C,
+                                             p->s.dec_k, rpb);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// chunk-planar bf16 [n][C/8][HW][8] -> NHWC fp32 [n][HW][C]   (debug reads only)
+__global__ void tc_export_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, size_t total,
+                                 int HW, int C) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t pn = i / C;
+    const int pix = (int)(pn % HW);
+    const size_t n = pn / HW;
+    dst[i] = __bfloat162float(src[((n * (C / 8) + c / 8) * HW + pix) * 8 + c % 8]);
+  }
+}
+
+int tc_export_f32(Plan* p, const void* src_bf16, float* dst, size_t n, cudaStream_t st_) {
+  tc_export_kernel<<<p->num_sms * 4, 256, 0, st_>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, n, p->HW,
+                                                    p->C);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// seed8 (bf16 [n][HW][8], 4 real channels) -> fp32 [n][HW][4]   (debug reads only)
+__global__ void tc_export_seed_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, size_t npix) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix * 4; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[(i / 4) * 8 + i % 4]);
+}
+
+int tc_export_seed(Plan* p, const void* seed8, float* dst, cudaStream_t st_) {
+  tc_export_seed_kernel<<<p->num_sms * 4, 256, 0, st_>>>(reinterpret_cast<const __nv_bfloat16*>(seed8), dst,
+                                                         (size_t)p->BK * p->HW);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+}  // namespace iod

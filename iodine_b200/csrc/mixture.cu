@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(128)
 mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
                float* __restrict__ seed4, float* __restrict__ auxs, float* __restrict__ lik,
                double* __restrict__ stats, double* __restrict__ accum,
-               int K, int HW, float inv_2s2, float inv_s2, float ll_const, int want_grads) {
+               int K, int HW, float inv_2s2, float inv_s2, float ll_const, int want_grads,
+               int seed_bf16) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = pix < HW;
@@ -146,9 +147,15 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
       ax[1] = make_float4(lgr, mpost, gr, gg);
       ax[2] = make_float4(gb, gmk, loo, 0.f);
       // chain to the decoder's raw outputs: sigmoid' and softmax'
-      reinterpret_cast<float4*>(seed4)[sp] =
-          make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g), gb * m_b * (1.f - m_b),
-                      mk * (gmk - mgsum));
+      const float4 sd = make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g),
+                                    gb * m_b * (1.f - m_b), mk * (gmk - mgsum));
+      if (seed_bf16) {   // one 8-channel bf16 plane for the tensor-core data-gradient (conv_tc.cu)
+        __nv_bfloat162 lo = __floats2bfloat162_rn(sd.x, sd.y), hi = __floats2bfloat162_rn(sd.z, sd.w);
+        reinterpret_cast<uint4*>(seed4)[sp] =
+            make_uint4(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi), 0u, 0u);
+      } else {
+        reinterpret_cast<float4*>(seed4)[sp] = sd;
+      }
       a_mean = gr + gg + gb; a_mean2 = gr * gr + gg * gg + gb * gb;
       a_gm = gmk; a_gm2 = gmk * gmk;
       a_loo = loo; a_loo2 = loo * loo;
@@ -197,10 +204,12 @@ int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st) {
   dim3 grid((p->HW + 127) / 128, s.B);
   if (s.K <= 8)
     mixture_kernel<8><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
-                                            p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads);
+                                            p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads,
+                                            s.precision == IODINE_BF16);
   else
     mixture_kernel<16><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
-                                             p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads);
+                                             p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads,
+                                             s.precision == IODINE_BF16);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

@@ -34,7 +34,10 @@ static size_t carve(Plan* p, char* base) {
   const size_t BK = p->BK, HW = p->HW, C = p->C, L = s.L, M = p->M, Cr = p->Cr;
   const size_t eb = act_elem_bytes(p);
   for (int l = 0; l < s.dec_layers; ++l) p->act[l] = take(BK * HW * C * eb);
-  for (int i = 0; i < 2; ++i) p->gbuf[i] = take(s.dec_layers > 1 ? BK * HW * C * eb : 1024);
+  for (int i = 0; i < 2; ++i) {
+    const bool need = s.dec_layers > 1 || (i == 0 && s.precision == IODINE_BF16);
+    p->gbuf[i] = take(need ? BK * HW * C * eb : 1024);
+  }
   p->out4 = (float*)take(BK * HW * 4 * sizeof(float));
   p->seed4 = (float*)take(BK * HW * 4 * sizeof(float));
   p->auxs = (float*)take(BK * HW * 12 * sizeof(float));
@@ -126,9 +129,7 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
     const bool last = (l == 1);
     prof_mark(p, st);
     if (s.precision == IODINE_BF16) {
-      if (tc_launch_conv(p, l, true, p->gbuf[cur], p->act[l - 1], last ? nullptr : p->gbuf[cur ^ 1],
-                         last ? p->G : nullptr, st))
-        return 1;
+      if (tc_launch_conv(p, l, true, p->gbuf[cur], p->act[l - 1], p->gbuf[cur ^ 1], nullptr, st)) return 1;
     } else {
       if (launch_conv_cc(p, (const float*)p->gbuf[cur], p->dec[l].wt, nullptr,
                          (const float*)p->act[l - 1], last ? nullptr : (float*)p->gbuf[cur ^ 1],
@@ -138,6 +139,9 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
     prof_mark(p, st);
     cur ^= 1;
   }
+  // the tensor-core path stores dJ/d(pre-activation 1) and reduces it over the border classes
+  // of the collapsed first layer in a separate bandwidth-bound pass
+  if (s.precision == IODINE_BF16) return tc_launch_class_sum(p, p->gbuf[cur], st);
   return 0;
 }
 
@@ -249,7 +253,6 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
       alloc_f(&p->head_w, 2 * L * M) || alloc_f(&p->head_b, 2 * L) || alloc_f(&p->init_mean, L) ||
       alloc_f(&p->init_logvar, L))
     return 1;
-  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { p->tc_w[l] = nullptr; p->tc_wt[l] = nullptr; }
   if (s.precision == IODINE_BF16 && tc_alloc(p)) return 1;
   p->ws_need = carve(p, nullptr);
   *plan_out = reinterpret_cast<IodinePlan*>(p);
@@ -263,7 +266,6 @@ IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) {
     cudaFree(p->dec[l].w); cudaFree(p->dec[l].wt); cudaFree(p->dec[l].b);
     if (l < p->s.ref_layers) { cudaFree(p->ref_wp[l]); cudaFree(p->ref_b[l]); }
-    cudaFree(p->tc_w[l]); cudaFree(p->tc_wt[l]);
   }
   cudaFree(p->out_w); cudaFree(p->out_wt); cudaFree(p->out_b); cudaFree(p->ref_w0);
   cudaFree(p->mlp_w); cudaFree(p->mlp_b); cudaFree(p->w_ih); cudaFree(p->w_hh); cudaFree(p->b_ih);
@@ -398,7 +400,15 @@ IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, 
   bool act_view = false;
   int act_idx = 0;
   if (!strcmp(name, "out4")) { src = p->out4; bytes = BK * HW * 4 * sizeof(float); }
-  else if (!strcmp(name, "seed4")) { src = p->seed4; bytes = BK * HW * 4 * sizeof(float); }
+  else if (!strcmp(name, "seed4")) {
+    src = p->seed4; bytes = BK * HW * 4 * sizeof(float);
+    if (p->s.precision == IODINE_BF16) {
+      if (bytes_out) *bytes_out = bytes;
+      if (!dst) return 0;
+      IOD_REQUIRE(dst_bytes >= bytes, "destination too small for %s: %zu < %zu", name, dst_bytes, bytes);
+      return tc_export_seed(p, p->seed4, (float*)dst, st);
+    }
+  }
   else if (!strcmp(name, "dz")) { src = p->dz; bytes = BK * p->s.L * sizeof(float); }
   else if (!strcmp(name, "z")) { src = p->z; bytes = BK * p->s.L * sizeof(float); }
   else if (!strcmp(name, "G")) { src = p->G; bytes = BK * p->n_class * p->C * sizeof(float); }

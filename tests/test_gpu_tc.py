@@ -1,0 +1,108 @@
+"""GPU tests of the tcgen05 tensor-core decoder path (precision='bf16', conv_tc.cu).
+
+Two bars:
+  * kernel-level: every decoder buffer of one refinement step (activations, 4-channel output,
+    data-gradient, class sums, dz) against the exact-fp32 FFMA path of the same library on the same
+    inputs, within bf16 rounding accumulated over the layer stack;
+  * path-level (the north-star bar): recon / masks / ELBO of a whole reconstruct() within 1e-3 of
+    the committed golden vectors of the unmodified reference.
+"""
+import pytest
+import torch
+
+from oracle import arch as A
+from oracle import restatement as S
+
+from helpers import golden_state_dict, load_golden, rel_err, seeded_model, t
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL_OUT = 1e-3
+
+
+def _pair(arch, B, sharpen=1.0):
+    m32 = seeded_model(arch, sharpen).to(DEV)
+    m16 = seeded_model(arch, sharpen, precision='bf16').to(DEV)
+    return m32, m16, m32.state_for_debug(B), m16.state_for_debug(B)
+
+
+def _nrm(a, b):
+    """relative L2 error (bf16 noise is judged in the mean, not on the worst element)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize('name,over,B', [
+    ('tiny', dict(dec_layers=3), 2),              # C=16, W=16: flat tiling, several rows per tile
+    ('dsprites', dict(iters=1), 1),               # C=32, W=64, 5 layers
+    ('test5x5', dict(iters=1), 2),                # 5x5 taps, C=32, W=32
+    ('clevr6', dict(iters=1, slots=2), 1),        # C=64, W=128: row-aligned tiles
+    ('tiny', dict(img_size=24, dec_chan=32), 3),  # odd width
+    ('tiny', dict(dec_layers=1), 2),              # no C->C layer: only the 4-channel ends
+])
+def test_decoder_buffers_against_fp32_path(name, over, B):
+    arch = A.arch_by_name(name, **over)
+    m32, m16, e32, e16 = _pair(arch, B, sharpen=2.0)
+    K, L, H, C = arch.SLOTS, arch.DIM_LATENT, arch.IMG_SIZE, arch.DEC.CONV_CHAN
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(B, 3, H, H, generator=g).to(DEV)
+    eps = torch.randn(B, K, L, generator=g).to(DEV)
+    outs = []
+    for eng in (e32, e16):
+        mu, lv, h, c = eng.init_state()
+        terms, _, _ = eng.refine_step(x, eps, mu, lv, h, c)
+        torch.cuda.synchronize()
+        d = {'terms': terms.clone(), 'mu': mu.clone(), 'lv': lv.clone()}
+        for i in range(arch.DEC.CONV_LAYERS):
+            d['act%d' % i] = eng.debug_read('act%d' % i).clone()
+        for nm in ('out4', 'seed4', 'G', 'dz'):
+            d[nm] = eng.debug_read(nm).clone()
+        outs.append(d)
+    ref, got = outs
+    errs = {k: _nrm(got[k], ref[k]) for k in ref}
+    print(name, over, {k: '%.2e' % v for k, v in errs.items()})
+    n = arch.DEC.CONV_LAYERS
+    assert errs['act0'] < 4e-3                       # bf16 rounding of an exact value
+    for i in range(1, n):
+        assert errs['act%d' % i] < 4e-3 * (i + 2), ('act', i, errs)
+    assert errs['out4'] < 4e-3 * (n + 2), errs
+    assert errs['seed4'] < 5e-2, errs                # gradient seeds amplify by 1/sigma^2
+    assert errs['G'] < 5e-2 and errs['dz'] < 5e-2, errs
+    assert errs['terms'] < 1e-3, errs
+
+
+@pytest.mark.parametrize('name', ['tiny_b2', 'tiny_b2_sharp', 'dsprites_b2', 'dsprites_b2_sharp',
+                                  'clevr6_b1', 'clevr6_b1_sharp', 'test5x5_b2_sharp'])
+def test_reconstruct_bf16_against_golden(name):
+    g, arch, B, sharpen, detail = load_golden(name)
+    model = seeded_model(arch, sharpen, precision='bf16').to(DEV)
+    pred, mask, mean = model.reconstruct(t(g['x']).to(DEV), eps=t(g['eps']).to(DEV))
+    torch.cuda.synchronize()
+    e = {'pred': rel_err(pred, g['final_pred']), 'mask': rel_err(mask, g['final_mask']),
+         'mean': rel_err(mean, g['final_mean'])}
+    elbo = model.elbo_per_step(B).cpu()
+    e['elbo'] = max(abs(elbo[i].item() - float(g['s%d_elbo' % i])) / abs(float(g['s%d_elbo' % i]))
+                    for i in range(arch.ITERS))
+    e['z_l2'] = _nrm(model.z, t(g['final_z']))
+    print(name, {k: '%.2e' % v for k, v in e.items()})
+    # the north-star bar is on recon / masks / ELBO; per-slot means are reported, the posterior
+    # sample itself is looser in bf16
+    assert e['pred'] < TOL_OUT and e['mask'] < TOL_OUT and e['elbo'] < TOL_OUT, e
+    assert e['mean'] < 5e-3 and e['z_l2'] < 5e-2, e
+
+
+def test_bf16_full_size_matches_fp32_path_clevr6_b4():
+    """BASELINE config #2 architecture at B=4: bf16 tensor-core path vs the exact path."""
+    arch = A.arch_by_name('clevr6')
+    B = 4
+    m32, m16, _, _ = _pair(arch, B, sharpen=1.0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 3, 128, 128, generator=g).to(DEV)
+    eps = torch.randn(arch.ITERS + 1, B, arch.SLOTS, arch.DIM_LATENT, generator=g).to(DEV)
+    p32, k32, _ = m32.reconstruct(x, eps=eps)
+    e32 = m32.elbo_per_step(B).clone()
+    p16, k16, _ = m16.reconstruct(x, eps=eps)
+    e16 = m16.elbo_per_step(B).clone()
+    errs = {'pred': rel_err(p16, p32), 'mask': rel_err(k16, k32), 'elbo': rel_err(e16, e32)}
+    print({k: '%.2e' % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL_OUT, errs
