@@ -261,7 +261,7 @@ def run_native(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32' if args.precision == 'fp32' else 'bf16 operands / f32 accumulate',
+            'dtype': 'f32' if args.precision == 'fp32' else '%s operands / f32 accumulate' % args.precision,
             'data': 'synthetic',
             'config': {'workload': 'CLEVR6 128x128 K=7 T=5 B=%d per GPU (configs[1]); step = one '
                                    'IODINE.encode() over the batch' % B,

@@ -41,7 +41,8 @@ extern "C" {
 enum IodinePrecision {
   IODINE_FP32 = 0,  /* FFMA, fp32 activations: the exact path                           */
   IODINE_BF16 = 1,  /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate in TMEM)      */
-  IODINE_TF32 = 2   /* reserved: tcgen05 kind::tf32                                     */
+  IODINE_TF32 = 2,  /* reserved: tcgen05 kind::tf32                                     */
+  IODINE_FP16 = 3   /* tcgen05 kind::f16 with fp16 operands (10-bit mantissa), fp32 accumulate */
 };
 
 /* Mirrors the cfg.ARCH fields the reference model reads (iodine.py:10-32,

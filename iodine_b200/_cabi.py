@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libiodine_b200.so')
 
 MAX_LAYERS = 8
-FP32, BF16, TF32 = 0, 1, 2
-PRECISIONS = {'fp32': FP32, 'bf16': BF16}
+FP32, BF16, TF32, FP16 = 0, 1, 2, 3
+PRECISIONS = {'fp32': FP32, 'bf16': BF16, 'fp16': FP16}
 
 EXPORTS = [
     'iodine_abi_version', 'iodine_last_error', 'iodine_plan_create', 'iodine_plan_destroy',

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -95,7 +96,7 @@ struct Plan {
   float *w_ih = nullptr, *w_hh = nullptr, *b_ih = nullptr, *b_hh = nullptr;
   float *head_w = nullptr, *head_b = nullptr;   // [2L, M] (mean rows then logvar rows), [2L]
   float *init_mean = nullptr, *init_logvar = nullptr;
-  void* tc = nullptr;         // tensor-core path state (conv_tc.cu: TcState), IODINE_BF16 only
+  void* tc = nullptr;         // tensor-core path state (conv_tc.cu: TcState), IODINE_BF16 / IODINE_FP16
 
   // ---- workspace carve-up (caller memory)
   void* ws = nullptr;
@@ -132,7 +133,20 @@ struct Plan {
   float* hmean = nullptr;         // [B,K,3,H,W]
 };
 
-inline size_t act_elem_bytes(const Plan* p) { return p->s.precision == IODINE_BF16 ? 2 : 4; }
+// tensor-core modes keep the decoder activations as 16-bit values (bf16 or fp16), chunk-planar
+inline bool tc_mode(const Plan* p) { return p->s.precision == IODINE_BF16 || p->s.precision == IODINE_FP16; }
+inline size_t act_elem_bytes(const Plan* p) { return tc_mode(p) ? 2 : 4; }
+
+// 16-bit pair packing selected at run time (helper kernels) -- f16 != 0: IEEE half, else bfloat16
+__device__ __forceinline__ uint32_t pack_h2(float a, float b, int f16) {
+  if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
 
 // ------------------------------------------------------------------ launchers (conv_f32.cu)
 // stride-1 C->C conv, NHWC fp32.  mode 0: out = ELU(conv + bias); mode 1: out = conv * ELU'(act)

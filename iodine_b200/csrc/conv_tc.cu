@@ -36,23 +36,23 @@ namespace iod {
 // ------------------------------------------------------------------------------------------------
 // parameters of one launch
 // ------------------------------------------------------------------------------------------------
-struct TcEntry {      // one tcgen05.mma per tile
-  int32_t shift;      // flat ring shift of the A run (dy*Ps + dx)
-  int32_t plane;      // first input plane of the K=16 step
-  int32_t lbo16;      // LBO in 16-byte units (plane stride, or tap distance for 8-channel inputs)
-  int32_t boff16;     // start of the step's B image inside the weight block, 16-byte units
-};
-constexpr int TC_MAX_ENTRIES = 56;
 constexpr int TC_MAX_RING = 32;
-constexpr int TC_THREADS = 192;       // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
+// threads: warp 0 TMA, warp 1 MMA + TMEM, then 4 or 8 epilogue warps (two per TMEM lane quadrant,
+// each taking half of the accumulator columns, when N >= 32)
+__host__ __device__ constexpr int tc_epi_warps(int N) { return N >= 32 ? 8 : 4; }
+__host__ __device__ constexpr int tc_threads(int N) { return 64 + 32 * tc_epi_warps(N); }
 constexpr int TC_ACC_STAGES = 4;
 
 enum TcEpi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_OUT4 = 2 };
 
+struct TcMaps {                   // one source buffer: rows are fetched as runs of 128 pixels
+  CUtensorMap full;               // 4-D {2W (8-byte elements), H, planes, BK}, box 256 elements
+  CUtensorMap tail;               // same tensor, box = the remainder of the halo row
+};
+
 struct alignas(64) TcParams {
-  CUtensorMap tmap;               // source activations, 5-D {8, W, H, planes, BK}
-  TcEntry ent[TC_MAX_ENTRIES];
-  int32_t n_ent;
+  TcMaps maps;
+  int32_t f16;                    // 1: IEEE half operands, 0: bfloat16
   int32_t nch_in;                 // input planes
   int32_t nch_out;                // output planes (N/8) for the bf16 epilogues
   int32_t H, W;
@@ -65,7 +65,9 @@ struct alignas(64) TcParams {
   int32_t items;                  // BK * strips
   uint32_t idesc;
   uint32_t w_bytes;               // weight image bytes (multiple of 16)
-  uint32_t box_bytes;             // bytes of one (row, plane) TMA box
+  uint32_t box_bytes;             // bytes of one halo row of one plane ((W + 2 pad) * 16)
+  int32_t n_full;                 // full 128-pixel boxes per halo row
+  int32_t tail_px;                // pixels of the tail box (0 = none)
   uint32_t plane_stride16;        // ring plane stride, 16-byte units
   const void* wimg;               // packed bf16 weights (global), layout = smem image
   const float* bias;              // [N] (EPI_FWD, EPI_OUT4)
@@ -113,12 +115,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     }
   }
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0,
-                                            int c1, int c2, int c3, int c4) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -126,6 +128,17 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -140,8 +153,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
 }
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 // bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, layout type 0.
@@ -159,13 +171,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, u
         "=r"(r[14]), "=r"(r[15])                                                                \
       : "r"(addr))
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
-}
 // ELU with the hardware exponential: |error| <= ~2e-7 absolute, far below bf16 rounding.
 __device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
 
@@ -188,9 +193,73 @@ __device__ __forceinline__ int tc_num_tiles(const TcParams& p, int th) {
   return p.segs ? th * p.segs : ((th - 1) * p.Ps + p.W - 1) / 128 + 1;
 }
 
-template <int N, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+// One tile = KS*KS*NKS tcgen05.mma (M=128, N, K=16), fully unrolled: every descriptor is a
+// warp-uniform base plus compile-time multiples of run-time strides, so the issuing thread spends
+// a few uniform-datapath instructions per MMA (a table lookup per MMA costs more than the MMA).
+//   NKS >  0 : C-channel input, NKS = C/16 K-steps per tap; LBO = plane stride
+//   NKS == 0 : one 8-channel plane, two taps per K=16 step; LBO = flat distance between the taps
+// B image (weights) is [mma][k-half][n][8]: LBO = N (16-byte units), SBO = 128 B for A and B.
+template <int N, int KS, int NKS>
+__device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint32_t abase, uint32_t wrap_at, uint32_t Q,
+                                              uint32_t Ps, uint32_t ps16, uint32_t w_base16, uint32_t idesc) {
+  constexpr uint64_t DESC_HI = (uint64_t)(8u | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+  if constexpr (NKS > 0) {
+    const uint32_t lbo_hi = ps16 << 16;
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx) {
+        const uint32_t shift = (uint32_t)dy * Ps + (uint32_t)dx;
+        const uint32_t a0 = abase + shift - (shift >= wrap_at ? Q : 0u);   // ring wrap
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+          const int e = (dy * KS + dx) * NKS + ks;
+          const uint32_t alo = (a0 + (uint32_t)(2 * ks) * ps16) | lbo_hi;
+          const uint32_t blo = (w_base16 + (uint32_t)(e * 2 * N)) | ((uint32_t)N << 16);
+          tc_mma_bf16(d_tmem, DESC_HI | alo, DESC_HI | blo, idesc, e > 0 ? 1u : 0u);
+        }
+      }
+    }
+  } else {
+    constexpr int KK = KS * KS, NPAIR = (KK + 1) / 2;
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) {
+      const int ta = (2 * q + 1 < KK) ? 2 * q : KK - 2;          // the odd tail re-reads tap KK-2 against zeros
+      const int tb = ta + 1;
+      const uint32_t sa = (uint32_t)(ta / KS) * Ps + (uint32_t)(ta % KS);
+      const uint32_t sb = (uint32_t)(tb / KS) * Ps + (uint32_t)(tb % KS);
+      const uint32_t a0 = abase + sa - (sa >= wrap_at ? Q : 0u);
+      const uint32_t alo = a0 | ((sb - sa) << 16);
+      const uint32_t blo = (w_base16 + (uint32_t)(q * 2 * N)) | ((uint32_t)N << 16);
+      tc_mma_bf16(d_tmem, DESC_HI | alo, DESC_HI | blo, idesc, q > 0 ? 1u : 0u);
+    }
+  }
+}
+
+// walks the (work item, tile) sequence of one CTA; identical in the MMA and epilogue roles
+struct TcTileIter {
+  int item, t, ntiles, n, y0, th;
+  __device__ __forceinline__ void load_item(const TcParams& p) {
+    if (item < p.items) {
+      n = item / p.strips;
+      y0 = (item % p.strips) * p.TH;
+      th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
+      ntiles = tc_num_tiles(p, th);
+    }
+  }
+  __device__ __forceinline__ void init(const TcParams& p) { item = blockIdx.x; t = 0; load_item(p); }
+  __device__ __forceinline__ bool valid(const TcParams& p) const { return item < p.items; }
+  __device__ __forceinline__ void next(const TcParams& p) {
+    if (++t >= ntiles) { item += gridDim.x; t = 0; load_item(p); }
+  }
+};
+
+template <int N, int EPI, int KS, int NKS>
+__global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NTHREADS = tc_threads(N);
+  constexpr int EW = tc_epi_warps(N);
+  constexpr int NC = (EW == 8) ? N / 2 : N;            // accumulator columns per epilogue warp
   constexpr int TMEM_COLS = (TC_ACC_STAGES * N < 32) ? 32 : TC_ACC_STAGES * N;
   const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
   uint8_t* s_w = smem;
@@ -199,15 +268,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   TcSmem* sb = reinterpret_cast<TcSmem*>(s_a + (size_t)p.nch_in * plane_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pad = p.pad, Ps = p.Ps, R = p.R;
+  constexpr int pad = KS / 2;
+  const int Ps = p.Ps, R = p.R;
   const int Q = R * Ps;
+  const int F16 = p.f16;
 
   // ---- one-time setup: zero the ring (no stale NaN patterns under discarded positions),
   //      barriers, TMEM
   {
     uint4* a4 = reinterpret_cast<uint4*>(s_a);
     const int n16 = p.nch_in * (int)p.plane_stride16;
-    for (int i = threadIdx.x; i < n16; i += TC_THREADS) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < n16; i += NTHREADS) a4[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (threadIdx.x == 0) {
@@ -217,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < TC_ACC_STAGES; ++i) {
       mbar_init(smem_u32(&sb->tfull[i]), 1);
-      mbar_init(smem_u32(&sb->tempty[i]), 4);      // one arrive per epilogue warp
+      mbar_init(smem_u32(&sb->tempty[i]), EW);     // one arrive per epilogue warp
     }
     mbar_init(smem_u32(&sb->wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -235,139 +306,158 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp == 0) {
     // =============================================================== TMA producer
-    if (lane == 0) {
-      {  // weights: one shot, resident for the whole kernel
-        const uint32_t wbar = smem_u32(&sb->wbar);
-        mbar_expect_tx(wbar, p.w_bytes);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg);
-        for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
-          const uint32_t n = (p.w_bytes - off < 16384u) ? (p.w_bytes - off) : 16384u;
-          bulk_load_1d(smem_u32(s_w + off), src + off, n, wbar);
-        }
+    // lane 0 owns the barriers; the copies of one halo row (planes x mirror copies x boxes) are
+    // issued by as many lanes in parallel
+    if (lane == 0) {  // weights: one shot, resident for the whole kernel
+      const uint32_t wbar = smem_u32(&sb->wbar);
+      mbar_expect_tx(wbar, p.w_bytes);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg);
+      for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
+        const uint32_t n = (p.w_bytes - off < 16384u) ? (p.w_bytes - off) : 16384u;
+        bulk_load_1d(smem_u32(s_w + off), src + off, n, wbar);
       }
-      const uint32_t a_base = smem_u32(s_a);
-      const uint32_t row_bytes = (uint32_t)Ps * 16u;
-      int g = 0;                                   // global halo-row counter of this CTA
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const int n = item / p.strips, y0 = (item % p.strips) * p.TH;
-        const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
-        const int nrows = th + 2 * pad;
-        for (int j = 0; j < nrows; ++j, ++g) {
-          const int slot = g % R;
-          const uint32_t ph = (uint32_t)(g / R) & 1u;
-          mbar_wait(smem_u32(&sb->empty[slot]), ph ^ 1u, 1);
-          const uint32_t fb = smem_u32(&sb->full[slot]);
-          const bool mir = slot < p.m;
-          mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (mir ? 2u : 1u));
-          const int y = y0 - pad + j;
-          for (int c = 0; c < p.nch_in; ++c) {
-            const uint32_t dst = a_base + (uint32_t)c * plane_bytes + (uint32_t)slot * row_bytes;
-            tma_load_5d(dst, &p.tmap, fb, 0, -pad, y, c, n);
-            if (mir) tma_load_5d(dst + (uint32_t)R * row_bytes, &p.tmap, fb, 0, -pad, y, c, n);
-          }
+    }
+    const uint32_t a_base = smem_u32(s_a);
+    const uint32_t row_bytes = (uint32_t)Ps * 16u;
+    const int nbox = p.n_full + (p.tail_px ? 1 : 0);
+    int g = 0;                                   // global halo-row counter of this CTA
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int n = item / p.strips, y0 = (item % p.strips) * p.TH;
+      const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
+      const int nrows = th + 2 * pad;
+      for (int j = 0; j < nrows; ++j, ++g) {
+        const int slot = g % R;
+        const uint32_t fb = smem_u32(&sb->full[slot]);
+        const int copies = (slot < p.m) ? 2 : 1;
+        if (lane == 0) {
+          mbar_wait(smem_u32(&sb->empty[slot]), ((uint32_t)(g / R) & 1u) ^ 1u, 1);
+          mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (uint32_t)copies);
+        }
+        __syncwarp();
+        const int y = y0 - pad + j;
+        const int per_plane = copies * nbox;
+        for (int i = lane; i < p.nch_in * per_plane; i += 32) {
+          const int c = i / per_plane, rem = i - c * per_plane;
+          const int cp = rem / nbox, k = rem - cp * nbox;
+          const uint32_t dst = a_base + (uint32_t)c * plane_bytes + (uint32_t)(slot + cp * R) * row_bytes +
+                               (uint32_t)k * 2048u;
+          // x is addressed in 8-byte elements (2 per pixel-plane): box k starts at pixel 128k - pad
+          tma_load_4d(dst, (k < p.n_full) ? &p.maps.full : &p.maps.tail, fb, 256 * k - 2 * pad, y, c, n);
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
-      mbar_wait(smem_u32(&sb->wbar), 0, 2);
-      const uint32_t a_base16 = smem_u32(s_a) >> 4;
-      const uint32_t w_base16 = smem_u32(s_w) >> 4;
-      int g0 = 0, rows_ready = 0, rows_freed = 0, tau = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const int y0 = (item % p.strips) * p.TH;
-        const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
-        const int nrows = th + 2 * pad;
-        const int ntiles = tc_num_tiles(p, th);
-        for (int t = 0; t < ntiles; ++t, ++tau) {
-          const int s = tc_tile_start(p, t);
-          int need = (s + 127 + 2 * pad * Ps + 2 * pad) / Ps;
-          if (need > nrows - 1) need = nrows - 1;
-          while (rows_ready <= g0 + need) {
-            mbar_wait(smem_u32(&sb->full[rows_ready % R]), (uint32_t)(rows_ready / R) & 1u, 3);
-            ++rows_ready;
-          }
-          const int stage = tau % TC_ACC_STAGES;
-          mbar_wait(smem_u32(&sb->tempty[stage]), ((uint32_t)(tau / TC_ACC_STAGES) & 1u) ^ 1u, 4);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(stage * N);
-          const int base_pos = ((g0 % R) * Ps + s) % Q;
-          for (int e = 0; e < p.n_ent; ++e) {
-            const TcEntry en = p.ent[e];
-            int pos = base_pos + en.shift;
-            if (pos >= Q) pos -= Q;
-            const uint64_t ad = make_desc(a_base16 + (uint32_t)en.plane * p.plane_stride16 + (uint32_t)pos,
-                                          (uint32_t)en.lbo16, 8u);
-            const uint64_t bd = make_desc(w_base16 + (uint32_t)en.boff16, (uint32_t)N, 8u);
-            tc_mma_bf16(d_tmem, ad, bd, p.idesc, e > 0 ? 1u : 0u);
-          }
-          tc_commit(smem_u32(&sb->tfull[stage]));
-          // rows that no later tile of this CTA reads go back to the producer
-          const int free_upto = (t + 1 < ntiles) ? g0 + tc_tile_start(p, t + 1) / Ps : g0 + nrows;
-          while (rows_freed < free_upto) {
-            tc_commit(smem_u32(&sb->empty[rows_freed % R]));
-            ++rows_freed;
-          }
-        }
-        g0 += nrows;
-      }
-    }
-    __syncwarp();
-  } else {
-    // =============================================================== epilogue (warps 2..5)
-    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
-    const int H = p.H, W = p.W;
-    constexpr int NB = (EPI == EPI_FWD) ? N : 4;
-    float bias_r[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) bias_r[i] = (EPI == EPI_DGRAD) ? 0.f : __ldg(p.bias + i);
-    int tau = 0;
+    // All lanes walk the tile sequence (so the per-tile bases are warp-uniform values); one elected
+    // lane issues the MMAs and commits.
+    const bool leader = elect_one_sync();
+    mbar_wait(smem_u32(&sb->wbar), 0, 2);
+    const uint32_t a_base16 = smem_u32(s_a) >> 4;
+    const uint32_t w_base16 = __shfl_sync(0xffffffffu, smem_u32(s_w) >> 4, 0);
+    int g0 = 0, rows_ready = 0, rows_freed = 0, tau = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int n = item / p.strips, y0 = (item % p.strips) * p.TH;
-      const int th = (H - y0 < p.TH) ? (H - y0) : p.TH;
+      const int y0 = (item % p.strips) * p.TH;
+      const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
+      const int nrows = th + 2 * pad;
       const int ntiles = tc_num_tiles(p, th);
       for (int t = 0; t < ntiles; ++t, ++tau) {
-        const int stage = tau % TC_ACC_STAGES;
-        const int flat = tc_tile_start(p, t) + quad * 32 + lane;
-        const int r = flat / Ps, c = flat - r * Ps;
-        const bool valid = (c < W) && (r < th);
-        const int y = y0 + r;
-        const size_t pix = valid ? ((size_t)y * W + c) : 0;
-        const size_t plane_sz = (size_t)H * W;
-
-        // previous activation for ELU' (issued before the accumulator wait to overlap latency)
-        uint4 av[(EPI == EPI_DGRAD) ? N / 8 : 1];
-        if constexpr (EPI == EPI_DGRAD) {
-#pragma unroll
-          for (int k = 0; k < N / 8; ++k)
-            av[k] = valid ? __ldg(p.actp + ((size_t)n * (N / 8) + k) * plane_sz + pix) : make_uint4(0u, 0u, 0u, 0u);
+        const int s = tc_tile_start(p, t);
+        int need = (s + 127 + 2 * pad * Ps + 2 * pad) / Ps;
+        if (need > nrows - 1) need = nrows - 1;
+        while (rows_ready <= g0 + need) {
+          mbar_wait(smem_u32(&sb->full[rows_ready % R]), (uint32_t)(rows_ready / R) & 1u, 3);
+          ++rows_ready;
         }
-
-        mbar_wait(smem_u32(&sb->tfull[stage]), (uint32_t)(tau / TC_ACC_STAGES) & 1u, 5);
+        const int stage = tau % TC_ACC_STAGES;
+        mbar_wait(smem_u32(&sb->tempty[stage]), ((uint32_t)(tau / TC_ACC_STAGES) & 1u) ^ 1u, 4);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t)(stage * N) + ((uint32_t)(quad * 32) << 16);
-        uint32_t acc[N];
-#pragma unroll
-        for (int q = 0; q < N / 16; ++q) IOD_TMEM_LD16((acc + q * 16), taddr + q * 16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_fence_before();
+        const int base_pos = ((g0 % R) * Ps + s) % Q;
+        const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(stage * N), 0);
+        const uint32_t abase = __shfl_sync(0xffffffffu, a_base16 + (uint32_t)base_pos, 0);
+        const uint32_t wrap_at = __shfl_sync(0xffffffffu, (uint32_t)(Q - base_pos), 0);
+        // rows that no later tile of this CTA reads go back to the producer
+        const int free_upto = (t + 1 < ntiles) ? g0 + tc_tile_start(p, t + 1) / Ps : g0 + nrows;
+        if (leader) {
+          tc_issue_tile<N, KS, NKS>(d_tmem, abase, wrap_at, (uint32_t)Q, (uint32_t)Ps, p.plane_stride16,
+                                    w_base16, p.idesc);
+          tc_commit(smem_u32(&sb->tfull[stage]));
+          for (int rf = rows_freed; rf < free_upto; ++rf) tc_commit(smem_u32(&sb->empty[rf % R]));
+        }
+        if (rows_freed < free_upto) rows_freed = free_upto;
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[stage]));   // accumulator stage is free again
+      }
+      g0 += nrows;
+    }
+  } else {
+    // =============================================================== epilogue warps
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int half = (EW == 8) ? (warp - 2) / 4 : 0;
+    const int col0 = half * NC;                    // first accumulator column / output channel
+    const int k0 = col0 / 8;                       // first output plane
+    const int H = p.H, W = p.W;
+    const size_t plane_sz = (size_t)H * W;
+    constexpr int NB = (EPI == EPI_FWD) ? NC : 4;
+    float bias_r[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) bias_r[i] = (EPI == EPI_DGRAD) ? 0.f : __ldg(p.bias + col0 + i);
 
-        if (!valid) continue;
+    constexpr int NAV = (EPI == EPI_DGRAD) ? NC / 8 : 1;
+    // position of this thread's output pixel in tile `it`, or -1
+    auto pix_of = [&](const TcTileIter& it) -> long long {
+      const int flat = tc_tile_start(p, it.t) + quad * 32 + lane;
+      const int r = flat / Ps, c = flat - r * Ps;
+      if (c >= W || r >= it.th) return -1;
+      return (long long)(it.y0 + r) * W + c;
+    };
+    auto load_prev = [&](const TcTileIter& it, long long pix, uint4* av) {
+#pragma unroll
+      for (int k = 0; k < NAV; ++k)
+        av[k] = (pix >= 0) ? __ldg(p.actp + ((size_t)it.n * (N / 8) + k0 + k) * plane_sz + (size_t)pix)
+                           : make_uint4(0u, 0u, 0u, 0u);
+    };
+
+    TcTileIter cur;
+    cur.init(p);
+    uint4 av[NAV], av_next[NAV];
+    long long pix = cur.valid(p) ? pix_of(cur) : -1;
+    if constexpr (EPI == EPI_DGRAD) {
+      if (cur.valid(p)) load_prev(cur, pix, av);
+    }
+    int tau = 0;
+    while (cur.valid(p)) {
+      // the next tile's previous-activation loads fly while this tile is processed
+      TcTileIter nxt = cur;
+      nxt.next(p);
+      const long long pix_next = nxt.valid(p) ? pix_of(nxt) : -1;
+      if constexpr (EPI == EPI_DGRAD) {
+        if (nxt.valid(p)) load_prev(nxt, pix_next, av_next);
+      }
+
+      const int stage = tau % TC_ACC_STAGES;
+      mbar_wait(smem_u32(&sb->tfull[stage]), (uint32_t)(tau / TC_ACC_STAGES) & 1u, 5);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(stage * N + col0) + ((uint32_t)(quad * 32) << 16);
+      uint32_t acc[NC];
+#pragma unroll
+      for (int q = 0; q < NC / 16; ++q) IOD_TMEM_LD16((acc + q * 16), taddr + q * 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[stage]));   // accumulator stage is free again
+
+      if (pix >= 0) {
         if constexpr (EPI == EPI_OUT4) {
           float4 o;
           o.x = __uint_as_float(acc[0]) + bias_r[0];
           o.y = __uint_as_float(acc[1]) + bias_r[1];
           o.z = __uint_as_float(acc[2]) + bias_r[2];
           o.w = __uint_as_float(acc[3]) + bias_r[3];
-          reinterpret_cast<float4*>(p.out)[(size_t)n * plane_sz + pix] = o;
+          reinterpret_cast<float4*>(p.out)[(size_t)cur.n * plane_sz + (size_t)pix] = o;
         } else {
           uint4* outp = reinterpret_cast<uint4*>(p.out);
 #pragma unroll
-          for (int k = 0; k < N / 8; ++k) {
+          for (int k = 0; k < NC / 8; ++k) {
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[k * 8 + e]);
@@ -378,20 +468,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t aw[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 a = unpack_bf16(aw[e]);
+                const float2 a = unpack_h2(aw[e], F16);
                 v[2 * e] *= elu_grad_from_act(a.x);
                 v[2 * e + 1] *= elu_grad_from_act(a.y);
               }
             }
             uint4 o;
-            o.x = pack_bf16(v[0], v[1]);
-            o.y = pack_bf16(v[2], v[3]);
-            o.z = pack_bf16(v[4], v[5]);
-            o.w = pack_bf16(v[6], v[7]);
-            outp[((size_t)n * (N / 8) + k) * plane_sz + pix] = o;
+            o.x = pack_h2(v[0], v[1], F16);
+            o.y = pack_h2(v[2], v[3], F16);
+            o.z = pack_h2(v[4], v[5], F16);
+            o.w = pack_h2(v[6], v[7], F16);
+            outp[((size_t)cur.n * (N / 8) + k0 + k) * plane_sz + (size_t)pix] = o;
           }
         }
       }
+      cur = nxt;
+      pix = pix_next;
+      if constexpr (EPI == EPI_DGRAD) {
+#pragma unroll
+        for (int k = 0; k < NAV; ++k) av[k] = av_next[k];
+      }
+      ++tau;
     }
   }
 
@@ -414,13 +511,13 @@ struct TcGeom {             // shared-memory geometry of one kernel flavour
 };
 
 struct TcState {
-  CUtensorMap map_act[IODINE_MAX_LAYERS];
-  CUtensorMap map_g[2];
-  CUtensorMap map_seed;
-  __nv_bfloat16* w_fwd[IODINE_MAX_LAYERS];    // layers 1..n-1
-  __nv_bfloat16* w_bwd[IODINE_MAX_LAYERS];
-  __nv_bfloat16* w_out = nullptr;             // decoder.conv forward, N = 16 (4 real rows)
-  __nv_bfloat16* w_in4 = nullptr;             // decoder.conv data-gradient, tap pairs
+  TcMaps map_act[IODINE_MAX_LAYERS];
+  TcMaps map_g[2];
+  TcMaps map_seed;
+  uint16_t* w_fwd[IODINE_MAX_LAYERS];    // layers 1..n-1
+  uint16_t* w_bwd[IODINE_MAX_LAYERS];
+  uint16_t* w_out = nullptr;             // decoder.conv forward, N = 16 (4 real rows)
+  uint16_t* w_in4 = nullptr;             // decoder.conv data-gradient, tap pairs
   float* ptab_c = nullptr;                    // chunk-planar fp32 copy of ptab
   int n_ent_cc = 0, n_ent_in4 = 0;
   TcGeom g_cc, g_out, g_in4;
@@ -445,18 +542,28 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, void* base, int W, int H, int planes, int BK, int pad) {
+// The chunk-planar tensor [n][plane][y][x][8 x bf16] is described to the TMA unit in 8-byte
+// elements (two per pixel-plane): a 16-byte innermost box would cost one L2 request per pixel,
+// 256 elements of 8 bytes fetch 128 pixels (2 KB) per request stream.
+static int make_map1(CUtensorMap* map, void* base, int W, int H, int planes, int BK, int box_px) {
   EncodeTiledFn fn = get_encode_fn();
   IOD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes, (cuuint64_t)BK};
-  cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)planes * H * W * 16};
-  cuuint32_t box[5] = {8, (cuuint32_t)(W + 2 * pad), 1, 1, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)planes, (cuuint64_t)BK};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)planes * H * W * 16};
+  cuuint32_t box[4] = {(cuuint32_t)box_px * 2, 1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IOD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
+}
+
+static int make_map(TcMaps* maps, void* base, int W, int H, int planes, int BK, int pad) {
+  const int pbox = W + 2 * pad;
+  const int n_full = pbox / 128, tail = pbox % 128;
+  if (make_map1(&maps->full, base, W, H, planes, BK, n_full ? 128 : tail)) return 1;
+  return make_map1(&maps->tail, base, W, H, planes, BK, tail ? tail : 128);
 }
 
 static int round_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -465,7 +572,6 @@ static int round_up(int v, int a) { return (v + a - 1) / a * a; }
 static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo_pos, TcGeom* g) {
   const IodineShape& s = p->s;
   const int pad = s.dec_k / 2;
-  if (s.W + 2 * pad > 256) return false;                      // TMA box limit
   g->Ps = round_up(s.W + 2 * pad, 8);
   g->segs = (s.W % 128 == 0) ? s.W / 128 : 0;
   g->w_bytes = (uint32_t)n_ent * 2u * (uint32_t)N * 16u;
@@ -493,10 +599,10 @@ int tc_supported(const Plan* p) {
   const IodineShape& s = p->s;
   const int C = s.dec_chan, kk = s.dec_k * s.dec_k;
   TcGeom g;
-  if (C % 16 != 0) { set_error("IODINE_BF16: DEC.CONV_CHAN=%d must be a multiple of 16", C); return 0; }
+  if (C % 16 != 0) { set_error("16-bit modes: DEC.CONV_CHAN=%d must be a multiple of 16", C); return 0; }
   const int n_cc = kk * (C / 16);
-  if (n_cc > TC_MAX_ENTRIES || !tc_geometry(p, C / 8, C, n_cc, 0, &g)) {
-    set_error("IODINE_BF16: decoder shape (C=%d, k=%d, W=%d) does not fit the tensor-core kernel's shared memory",
+  if (!tc_geometry(p, C / 8, C, n_cc, 0, &g)) {
+    set_error("16-bit modes: decoder shape (C=%d, k=%d, W=%d) does not fit the tensor-core kernel's shared memory",
               C, s.dec_k, s.W);
     return 0;
   }
@@ -552,8 +658,18 @@ int tc_on_workspace(Plan* p) {
 // C->C: entry = tap*(C/16) + ks, k-half kc covers input channels (2ks+kc)*8 .. +7.
 //   fwd : B[n=co][k=ci]  = W[co][ci][dy][dx]
 //   bwd : B[n=ci][k=co]  = W[co][ci][k-1-dy][k-1-dx]     (data-gradient = conv with flipped taps)
-__global__ void tc_pack_cc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
-                                  __nv_bfloat16* __restrict__ bwd, int C, int NO, int N, int KS) {
+__device__ __forceinline__ uint16_t to_h(float v, int f16) {
+  if (f16) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ float from_h(uint16_t u, int f16) {
+  if (f16) return __half2float(*reinterpret_cast<__half*>(&u));
+  return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+}
+
+__global__ void tc_pack_cc_kernel(const float* __restrict__ w, uint16_t* __restrict__ fwd,
+                                  uint16_t* __restrict__ bwd, int C, int NO, int N, int KS, int f16) {
   // w is OIHW [NO][C][KS][KS]; fwd image has N >= NO output rows (zero padded); bwd needs NO == C == N
   const int nks = C / 16;
   const int total = KS * KS * nks * 2 * N * 8;
@@ -561,13 +677,13 @@ __global__ void tc_pack_cc_kernel(const float* __restrict__ w, __nv_bfloat16* __
     const int e = i % 8, n = (i / 8) % N, kc = (i / (8 * N)) % 2, ks = (i / (16 * N)) % nks, tap = i / (16 * N * nks);
     const int dy = tap / KS, dx = tap % KS;
     const int k = (2 * ks + kc) * 8 + e;
-    if (fwd) fwd[i] = __float2bfloat16(n < NO ? w[(((size_t)n * C + k) * KS + dy) * KS + dx] : 0.f);
-    if (bwd) bwd[i] = __float2bfloat16(w[(((size_t)k * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)]);
+    if (fwd) fwd[i] = to_h(n < NO ? w[(((size_t)n * C + k) * KS + dy) * KS + dx] : 0.f, f16);
+    if (bwd) bwd[i] = to_h(w[(((size_t)k * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)], f16);
   }
 }
 // 4->C data-gradient of decoder.conv [4][C][k][k]; entry = tap pair (2q, 2q+1); the odd tail
 // reuses the previous tap with zero weights in its first half.  B[n=ci][k=o] (o < 4 real).
-__global__ void tc_pack_in4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img, int C, int KS) {
+__global__ void tc_pack_in4_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int C, int KS, int f16) {
   const int kk = KS * KS, npair = (kk + 1) / 2;
   const int total = npair * 2 * C * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -581,7 +697,7 @@ __global__ void tc_pack_in4_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int dy = tap / KS, dx = tap % KS;
     float v = 0.f;
     if (!zero && e < 4) v = w[(((size_t)e * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)];
-    img[i] = __float2bfloat16(v);
+    img[i] = to_h(v, f16);
   }
 }
 __global__ void tc_ptab_planar_kernel(const float* __restrict__ ptab, float* __restrict__ ptab_c, int HW, int C) {
@@ -595,14 +711,14 @@ __global__ void tc_ptab_planar_kernel(const float* __restrict__ ptab, float* __r
 int tc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
   TcState* st = tc_state(p);
   const IodineShape& s = p->s;
-  const int C = p->C, KS = s.dec_k;
+  const int C = p->C, KS = s.dec_k, f16 = s.precision == IODINE_FP16;
   for (int l = 1; l < s.dec_layers; ++l) {
-    tc_pack_cc_kernel<<<64, 256, 0, st_>>>(w->dec_w[l], st->w_fwd[l], st->w_bwd[l], C, C, C, KS);
+    tc_pack_cc_kernel<<<64, 256, 0, st_>>>(w->dec_w[l], st->w_fwd[l], st->w_bwd[l], C, C, C, KS, f16);
     IOD_LAUNCH_CHECK(p);
   }
-  tc_pack_cc_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_out, nullptr, C, 4, 16, KS);
+  tc_pack_cc_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_out, nullptr, C, 4, 16, KS, f16);
   IOD_LAUNCH_CHECK(p);
-  tc_pack_in4_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_in4, C, KS);
+  tc_pack_in4_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_in4, C, KS, f16);
   IOD_LAUNCH_CHECK(p);
   tc_ptab_planar_kernel<<<256, 256, 0, st_>>>(p->ptab, st->ptab_c, p->HW, C);   // after pack_ptab (same stream)
   IOD_LAUNCH_CHECK(p);
@@ -610,10 +726,11 @@ int tc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
 }
 
 // ---- launch -------------------------------------------------------------------------------------
-static uint32_t make_idesc(int N) {
+static uint32_t make_idesc(int N, bool f16) {
   // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major A and B,
   // n_dim = N>>3 @17, m_dim = 128>>4 @24
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t fmt = f16 ? 0u : 1u;           // F16F32Format: 0 = F16, 1 = BF16
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcParams* q) {
@@ -624,65 +741,66 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->Ps = g.Ps; q->R = g.R; q->m = g.m; q->segs = g.segs; q->TH = g.TH;
   q->strips = (s.H + g.TH - 1) / g.TH;
   q->items = p->BK * q->strips;
-  q->idesc = make_idesc(N);
+  q->idesc = make_idesc(N, s.precision == IODINE_FP16);
+  q->f16 = s.precision == IODINE_FP16;
   q->w_bytes = g.w_bytes;
   q->box_bytes = g.box_bytes;
+  q->n_full = (s.W + 2 * q->pad) / 128;
+  q->tail_px = (s.W + 2 * q->pad) % 128;
   q->plane_stride16 = g.plane_stride16;
 }
 
-static void fill_entries_cc(const Plan* p, const TcGeom& g, int N, TcParams* q) {
-  const int KS = p->s.dec_k, nks = p->C / 16;
-  int e = 0;
-  for (int tap = 0; tap < KS * KS; ++tap)
-    for (int ks = 0; ks < nks; ++ks, ++e) {
-      q->ent[e].shift = (tap / KS) * g.Ps + (tap % KS);
-      q->ent[e].plane = 2 * ks;
-      q->ent[e].lbo16 = (int32_t)g.plane_stride16;
-      q->ent[e].boff16 = e * 2 * N;
-    }
-  q->n_ent = e;
-}
-
-static void fill_entries_in4(const Plan* p, const TcGeom& g, int N, TcParams* q) {
-  const int KS = p->s.dec_k, kk = KS * KS;
-  auto shift = [&](int tap) { return (tap / KS) * g.Ps + (tap % KS); };
-  int e = 0;
-  for (int a = 0; a < kk; a += 2, ++e) {
-    int ta = a, tb = a + 1;
-    if (tb >= kk) { ta = kk - 2; tb = kk - 1; }
-    q->ent[e].shift = shift(ta);
-    q->ent[e].plane = 0;
-    q->ent[e].lbo16 = shift(tb) - shift(ta);
-    q->ent[e].boff16 = e * 2 * N;
-  }
-  q->n_ent = e;
-}
-
-template <int N, int EPI>
-static int tc_launch_t(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
-  auto kern = conv_tc_kernel<N, EPI>;
+// dispatch on the compile-time shape <N, EPI, KS, NKS>
+template <int N, int EPI, int KS, int NKS>
+static int tc_launch_k(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
+  auto kern = conv_tc_kernel<N, EPI, KS, NKS>;
   static bool attr_done = false;
   if (!attr_done) {
     IOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
   const int grid = q.items < p->num_sms ? q.items : p->num_sms;
-  kern<<<grid, TC_THREADS, smem, st_>>>(q);
+  kern<<<grid, tc_threads(N), smem, st_>>>(q);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
+// C -> C layers (forward / data-gradient): N = C, NKS = C/16
 template <int EPI>
-static int tc_launch_n(Plan* p, int N, const TcParams& q, size_t smem, cudaStream_t st_) {
-  switch (N) {
-    case 16: return tc_launch_t<16, EPI>(p, q, smem, st_);
-    case 32: return tc_launch_t<32, EPI>(p, q, smem, st_);
-    case 64: return tc_launch_t<64, EPI>(p, q, smem, st_);
-    default: set_error("conv_tc: unsupported N=%d", N); return 1;
-  }
+static int tc_launch_cc(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
+  const int C = p->C, KS = p->s.dec_k;
+  if (KS == 3 && C == 64) return tc_launch_k<64, EPI, 3, 4>(p, q, smem, st_);
+  if (KS == 3 && C == 32) return tc_launch_k<32, EPI, 3, 2>(p, q, smem, st_);
+  if (KS == 3 && C == 16) return tc_launch_k<16, EPI, 3, 1>(p, q, smem, st_);
+  if (KS == 5 && C == 32) return tc_launch_k<32, EPI, 5, 2>(p, q, smem, st_);
+  if (KS == 5 && C == 16) return tc_launch_k<16, EPI, 5, 1>(p, q, smem, st_);
+  set_error("conv_tc: unsupported C=%d k=%d", C, KS);
+  return 1;
+}
+// decoder.conv forward: N = 16 (4 real outputs), NKS = C/16
+static int tc_launch_o4(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
+  const int C = p->C, KS = p->s.dec_k;
+  if (KS == 3 && C == 64) return tc_launch_k<16, EPI_OUT4, 3, 4>(p, q, smem, st_);
+  if (KS == 3 && C == 32) return tc_launch_k<16, EPI_OUT4, 3, 2>(p, q, smem, st_);
+  if (KS == 3 && C == 16) return tc_launch_k<16, EPI_OUT4, 3, 1>(p, q, smem, st_);
+  if (KS == 5 && C == 32) return tc_launch_k<16, EPI_OUT4, 5, 2>(p, q, smem, st_);
+  if (KS == 5 && C == 16) return tc_launch_k<16, EPI_OUT4, 5, 1>(p, q, smem, st_);
+  set_error("conv_tc: unsupported C=%d k=%d", C, KS);
+  return 1;
+}
+// decoder.conv data-gradient: one 8-channel input plane, tap pairs (NKS = 0), N = C
+static int tc_launch_i4(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
+  const int C = p->C, KS = p->s.dec_k;
+  if (KS == 3 && C == 64) return tc_launch_k<64, EPI_DGRAD, 3, 0>(p, q, smem, st_);
+  if (KS == 3 && C == 32) return tc_launch_k<32, EPI_DGRAD, 3, 0>(p, q, smem, st_);
+  if (KS == 3 && C == 16) return tc_launch_k<16, EPI_DGRAD, 3, 0>(p, q, smem, st_);
+  if (KS == 5 && C == 32) return tc_launch_k<32, EPI_DGRAD, 5, 0>(p, q, smem, st_);
+  if (KS == 5 && C == 16) return tc_launch_k<16, EPI_DGRAD, 5, 0>(p, q, smem, st_);
+  set_error("conv_tc: unsupported C=%d k=%d", C, KS);
+  return 1;
 }
 
-static const CUtensorMap* find_map(Plan* p, const void* buf) {
+static const TcMaps* find_map(Plan* p, const void* buf) {
   TcState* st = tc_state(p);
   for (int l = 0; l < p->s.dec_layers; ++l)
     if (buf == p->act[l]) return &st->map_act[l];
@@ -696,54 +814,51 @@ int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* a
                    cudaStream_t st_) {
   (void)G;
   TcState* st = tc_state(p);
-  const CUtensorMap* map = find_map(p, in);
+  const TcMaps* map = find_map(p, in);
   IOD_REQUIRE(map != nullptr, "conv_tc: source buffer has no tensor map");
   TcParams q;
-  q.tmap = *map;
+  q.maps = *map;
   fill_common(p, st->g_cc, p->C / 8, p->C, &q);
-  fill_entries_cc(p, st->g_cc, p->C, &q);
   q.wimg = dgrad ? st->w_bwd[layer] : st->w_fwd[layer];
   q.bias = dgrad ? nullptr : p->dec[layer].b;
   q.actp = reinterpret_cast<const uint4*>(act_prev);
   q.out = out;
-  if (dgrad) return tc_launch_n<EPI_DGRAD>(p, p->C, q, st->g_cc.smem, st_);
-  return tc_launch_n<EPI_FWD>(p, p->C, q, st->g_cc.smem, st_);
+  if (dgrad) return tc_launch_cc<EPI_DGRAD>(p, q, st->g_cc.smem, st_);
+  return tc_launch_cc<EPI_FWD>(p, q, st->g_cc.smem, st_);
 }
 
 int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st_) {
   TcState* st = tc_state(p);
-  const CUtensorMap* map = find_map(p, in);
+  const TcMaps* map = find_map(p, in);
   IOD_REQUIRE(map != nullptr, "conv_tc: source buffer has no tensor map");
   TcParams q;
-  q.tmap = *map;
+  q.maps = *map;
   fill_common(p, st->g_out, p->C / 8, 16, &q);
-  fill_entries_cc(p, st->g_out, 16, &q);
   q.wimg = st->w_out;
   q.bias = p->out_b;
   q.actp = nullptr;
   q.out = out4;
-  return tc_launch_t<16, EPI_OUT4>(p, q, st->g_out.smem, st_);
+  return tc_launch_o4(p, q, st->g_out.smem, st_);
 }
 
 int tc_launch_dgrad_in4(Plan* p, const float* seed8, const void* act_prev, void* gout, cudaStream_t st_) {
   TcState* st = tc_state(p);
   (void)seed8;
   TcParams q;
-  q.tmap = st->map_seed;
+  q.maps = st->map_seed;
   fill_common(p, st->g_in4, 1, p->C, &q);
-  fill_entries_in4(p, st->g_in4, p->C, &q);
   q.wimg = st->w_in4;
   q.bias = nullptr;
   q.actp = reinterpret_cast<const uint4*>(act_prev);
   q.out = gout;
-  return tc_launch_n<EPI_DGRAD>(p, p->C, q, st->g_in4.smem, st_);
+  return tc_launch_i4(p, q, st->g_in4.smem, st_);
 }
 
 // ---- helpers around the chunk-planar layout -------------------------------------------------------
 // act0[n][k][y][x][8] = ELU(u[n][class(y,x)][co] + ptab_c[k][y][x][8])   (first decoder layer, collapsed)
 __global__ void __launch_bounds__(256)
 tc_layer1_kernel(const float* __restrict__ u, const float* __restrict__ ptab_c, uint4* __restrict__ act0,
-                 int H, int W, int C, int KS) {
+                 int H, int W, int C, int KS, int f16) {
   const int n = blockIdx.z, k = blockIdx.y;
   const int P = KS / 2, HW = H * W;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
@@ -753,10 +868,10 @@ tc_layer1_kernel(const float* __restrict__ u, const float* __restrict__ ptab_c, 
     const float4* pv = reinterpret_cast<const float4*>(ptab_c + ((size_t)k * HW + pix) * 8);
     const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1), p0 = __ldg(pv), p1 = __ldg(pv + 1);
     uint4 o;
-    o.x = pack_bf16(elu_f(u0.x + p0.x), elu_f(u0.y + p0.y));
-    o.y = pack_bf16(elu_f(u0.z + p0.z), elu_f(u0.w + p0.w));
-    o.z = pack_bf16(elu_f(u1.x + p1.x), elu_f(u1.y + p1.y));
-    o.w = pack_bf16(elu_f(u1.z + p1.z), elu_f(u1.w + p1.w));
+    o.x = pack_h2(elu_f(u0.x + p0.x), elu_f(u0.y + p0.y), f16);
+    o.y = pack_h2(elu_f(u0.z + p0.z), elu_f(u0.w + p0.w), f16);
+    o.z = pack_h2(elu_f(u1.x + p1.x), elu_f(u1.y + p1.y), f16);
+    o.w = pack_h2(elu_f(u1.z + p1.z), elu_f(u1.w + p1.w), f16);
     act0[((size_t)n * (C / 8) + k) * HW + pix] = o;
   }
 }
@@ -767,14 +882,15 @@ int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st_) {
   if (gx > 64) gx = 64;
   dim3 grid(gx, p->C / 8, p->BK);
   tc_layer1_kernel<<<grid, 256, 0, st_>>>(p->u, st->ptab_c, reinterpret_cast<uint4*>(act0), p->s.H, p->s.W, p->C,
-                                          p->s.dec_k);
+                                          p->s.dec_k, p->s.precision == IODINE_FP16);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
 // G[n][class][co] = sum over pixels of the class of g[n][co/8][y][x][co%8]  (layer-1 dgrad collapse)
 __global__ void __launch_bounds__(256)
-tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, int W, int C, int KS, int rows_per_block) {
+tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, int W, int C, int KS, int rows_per_block,
+                    int f16) {
   const int n = blockIdx.z, k = blockIdx.y;
   const int P = KS / 2, HW = H * W;
   const int y_lo = blockIdx.x * rows_per_block;
@@ -809,7 +925,7 @@ tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, i
     cy_run = cy;
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
       const uint4 v = __ldg(g + ((size_t)n * (C / 8) + k) * HW + (size_t)y * W + x);
-      const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+      const float2 a = unpack_h2(v.x, f16), b = unpack_h2(v.y, f16), c = unpack_h2(v.z, f16), d = unpack_h2(v.w, f16);
       const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
       const int cx = border_class(x, W, P);
       if (cx == P) {
@@ -828,39 +944,39 @@ int tc_launch_class_sum(Plan* p, const void* g, cudaStream_t st_) {
   const int rpb = 16;
   dim3 grid((p->s.H + rpb - 1) / rpb, p->C / 8, p->BK);
   tc_class_sum_kernel<<<grid, 256, 0, st_>>>(reinterpret_cast<const uint4*>(g), p->G, p->s.H, p->s.W, p->C,
-                                             p->s.dec_k, rpb);
+                                             p->s.dec_k, rpb, p->s.precision == IODINE_FP16);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
 // chunk-planar bf16 [n][C/8][HW][8] -> NHWC fp32 [n][HW][C]   (debug reads only)
-__global__ void tc_export_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, size_t total,
-                                 int HW, int C) {
+__global__ void tc_export_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, size_t total,
+                                 int HW, int C, int f16) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const size_t pn = i / C;
     const int pix = (int)(pn % HW);
     const size_t n = pn / HW;
-    dst[i] = __bfloat162float(src[((n * (C / 8) + c / 8) * HW + pix) * 8 + c % 8]);
+    dst[i] = from_h(src[((n * (C / 8) + c / 8) * HW + pix) * 8 + c % 8], f16);
   }
 }
 
 int tc_export_f32(Plan* p, const void* src_bf16, float* dst, size_t n, cudaStream_t st_) {
-  tc_export_kernel<<<p->num_sms * 4, 256, 0, st_>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, n, p->HW,
-                                                    p->C);
+  tc_export_kernel<<<p->num_sms * 4, 256, 0, st_>>>(reinterpret_cast<const uint16_t*>(src_bf16), dst, n, p->HW,
+                                                    p->C, p->s.precision == IODINE_FP16);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
 // seed8 (bf16 [n][HW][8], 4 real channels) -> fp32 [n][HW][4]   (debug reads only)
-__global__ void tc_export_seed_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, size_t npix) {
+__global__ void tc_export_seed_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, size_t npix, int f16) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix * 4; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = __bfloat162float(src[(i / 4) * 8 + i % 4]);
+    dst[i] = from_h(src[(i / 4) * 8 + i % 4], f16);
 }
 
 int tc_export_seed(Plan* p, const void* seed8, float* dst, cudaStream_t st_) {
-  tc_export_seed_kernel<<<p->num_sms * 4, 256, 0, st_>>>(reinterpret_cast<const __nv_bfloat16*>(seed8), dst,
-                                                         (size_t)p->BK * p->HW);
+  tc_export_seed_kernel<<<p->num_sms * 4, 256, 0, st_>>>(reinterpret_cast<const uint16_t*>(seed8), dst,
+                                                         (size_t)p->BK * p->HW, p->s.precision == IODINE_FP16);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

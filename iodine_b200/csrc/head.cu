@@ -222,7 +222,7 @@ int launch_sample_l1(Plan* p, const float* mu, const float* logvar, const float*
   IOD_LAUNCH_CHECK(p);
   const int per = p->HW * (p->C / 4);
   dim3 grid((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256, p->BK);
-  if (s.precision == IODINE_BF16) return tc_launch_layer1(p, act0, st);
+  if (tc_mode(p)) return tc_launch_layer1(p, act0, st);
   layer1_kernel<float><<<grid, 256, 0, st>>>(p->u, p->ptab, act0, s.H, s.W, p->C, s.dec_k);
   IOD_LAUNCH_CHECK(p);
   return 0;

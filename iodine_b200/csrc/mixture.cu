@@ -21,7 +21,7 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
                float* __restrict__ seed4, float* __restrict__ auxs, float* __restrict__ lik,
                double* __restrict__ stats, double* __restrict__ accum,
                int K, int HW, float inv_2s2, float inv_s2, float ll_const, int want_grads,
-               int seed_bf16) {
+               int seed_half /* 0: fp32 float4, 1: bf16 x8, 2: fp16 x8 */) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = pix < HW;
@@ -149,10 +149,9 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
       // chain to the decoder's raw outputs: sigmoid' and softmax'
       const float4 sd = make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g),
                                     gb * m_b * (1.f - m_b), mk * (gmk - mgsum));
-      if (seed_bf16) {   // one 8-channel bf16 plane for the tensor-core data-gradient (conv_tc.cu)
-        __nv_bfloat162 lo = __floats2bfloat162_rn(sd.x, sd.y), hi = __floats2bfloat162_rn(sd.z, sd.w);
-        reinterpret_cast<uint4*>(seed4)[sp] =
-            make_uint4(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi), 0u, 0u);
+      if (seed_half) {   // one 8-channel 16-bit plane for the tensor-core data-gradient (conv_tc.cu)
+        reinterpret_cast<uint4*>(seed4)[sp] = make_uint4(pack_h2(sd.x, sd.y, seed_half == 2),
+                                                         pack_h2(sd.z, sd.w, seed_half == 2), 0u, 0u);
       } else {
         reinterpret_cast<float4*>(seed4)[sp] = sd;
       }
@@ -205,11 +204,11 @@ int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st) {
   if (s.K <= 8)
     mixture_kernel<8><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
                                             p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads,
-                                            s.precision == IODINE_BF16);
+                                            tc_mode(p) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0);
   else
     mixture_kernel<16><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
                                              p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads,
-                                             s.precision == IODINE_BF16);
+                                             tc_mode(p) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

@@ -35,7 +35,7 @@ static size_t carve(Plan* p, char* base) {
   const size_t eb = act_elem_bytes(p);
   for (int l = 0; l < s.dec_layers; ++l) p->act[l] = take(BK * HW * C * eb);
   for (int i = 0; i < 2; ++i) {
-    const bool need = s.dec_layers > 1 || (i == 0 && s.precision == IODINE_BF16);
+    const bool need = s.dec_layers > 1 || (i == 0 && tc_mode(p));
     p->gbuf[i] = take(need ? BK * HW * C * eb : 1024);
   }
   p->out4 = (float*)take(BK * HW * 4 * sizeof(float));
@@ -102,7 +102,7 @@ static int decoder_forward(Plan* p, const float* mu, const float* lv, const floa
   if (launch_sample_l1(p, mu, lv, eps, z_in, (float*)p->act[0], st)) return 1;
   for (int l = 1; l < s.dec_layers; ++l) {
     prof_mark(p, st);
-    if (s.precision == IODINE_BF16) {
+    if (tc_mode(p)) {
       if (tc_launch_conv(p, l, false, p->act[l - 1], nullptr, p->act[l], nullptr, st)) return 1;
     } else {
       if (launch_conv_cc(p, (const float*)p->act[l - 1], p->dec[l].w, p->dec[l].b, nullptr,
@@ -111,7 +111,7 @@ static int decoder_forward(Plan* p, const float* mu, const float* lv, const floa
     }
     prof_mark(p, st);
   }
-  if (s.precision == IODINE_BF16) return tc_launch_out4(p, p->act[s.dec_layers - 1], p->out4, st);
+  if (tc_mode(p)) return tc_launch_out4(p, p->act[s.dec_layers - 1], p->out4, st);
   return launch_conv_out4(p, (const float*)p->act[s.dec_layers - 1], p->out4, st);
 }
 
@@ -119,7 +119,7 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
   const IodineShape& s = p->s;
   const int n = s.dec_layers;
   IOD_CHECK_CUDA(cudaMemsetAsync(p->G, 0, (size_t)p->BK * p->n_class * p->C * sizeof(float), st));
-  if (s.precision == IODINE_BF16) {
+  if (tc_mode(p)) {
     if (tc_launch_dgrad_in4(p, p->seed4, p->act[n - 1], p->gbuf[0], st)) return 1;
   } else {
     if (launch_dgrad_in4(p, p->seed4, (const float*)p->act[n - 1], (float*)p->gbuf[0], st)) return 1;
@@ -128,7 +128,7 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
   for (int l = n - 1; l >= 1; --l) {
     const bool last = (l == 1);
     prof_mark(p, st);
-    if (s.precision == IODINE_BF16) {
+    if (tc_mode(p)) {
       if (tc_launch_conv(p, l, true, p->gbuf[cur], p->act[l - 1], p->gbuf[cur ^ 1], nullptr, st)) return 1;
     } else {
       if (launch_conv_cc(p, (const float*)p->gbuf[cur], p->dec[l].wt, nullptr,
@@ -141,7 +141,7 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
   }
   // the tensor-core path stores dJ/d(pre-activation 1) and reduces it over the border classes
   // of the collapsed first layer in a separate bandwidth-bound pass
-  if (s.precision == IODINE_BF16) return tc_launch_class_sum(p, p->gbuf[cur], st);
+  if (tc_mode(p)) return tc_launch_class_sum(p, p->gbuf[cur], st);
   return 0;
 }
 
@@ -218,7 +218,8 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
   IOD_REQUIRE(s.ref_stride == 1 || s.ref_stride == 2, "unsupported REF.STRIDE=%d", s.ref_stride);
   IOD_REQUIRE(s.H >= 2 * s.dec_k && s.W >= 2 * s.dec_k, "image %dx%d too small for kernel %d", s.H, s.W, s.dec_k);
   IOD_REQUIRE(s.mlp_units >= 1 && s.T >= 0 && s.sigma > 0.f, "bad MLP_UNITS/ITERS/SIGMA");
-  IOD_REQUIRE(s.precision == IODINE_FP32 || s.precision == IODINE_BF16, "unsupported precision %d", s.precision);
+  IOD_REQUIRE(s.precision == IODINE_FP32 || s.precision == IODINE_BF16 || s.precision == IODINE_FP16,
+              "unsupported precision %d", s.precision);
 
   Plan* p = new Plan();
   p->s = s;
@@ -233,7 +234,7 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
     p->ref_w[l + 1] = (p->ref_w[l] + 2 * pad - s.ref_k) / s.ref_stride + 1;
     IOD_REQUIRE(p->ref_h[l + 1] >= 1 && p->ref_w[l + 1] >= 1, "refine layer %d output is empty", l);
   }
-  if (s.precision == IODINE_BF16) {
+  if (tc_mode(p)) {
     if (!tc_supported(p)) { delete p; return 1; }
   }
   const size_t C = p->C, L = s.L, M = p->M, Cr = p->Cr, kk = (size_t)s.dec_k * s.dec_k,
@@ -253,7 +254,7 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
       alloc_f(&p->head_w, 2 * L * M) || alloc_f(&p->head_b, 2 * L) || alloc_f(&p->init_mean, L) ||
       alloc_f(&p->init_logvar, L))
     return 1;
-  if (s.precision == IODINE_BF16 && tc_alloc(p)) return 1;
+  if (tc_mode(p) && tc_alloc(p)) return 1;
   p->ws_need = carve(p, nullptr);
   *plan_out = reinterpret_cast<IodinePlan*>(p);
   return 0;
@@ -290,7 +291,7 @@ IODINE_API int iodine_plan_set_workspace(IodinePlan* plan, void* workspace, size
   IOD_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
   p->ws = workspace; p->ws_bytes = bytes;
   carve(p, (char*)workspace);
-  if (p->s.precision == IODINE_BF16 && tc_on_workspace(p)) return 1;
+  if (tc_mode(p) && tc_on_workspace(p)) return 1;
   return 0;
 }
 
@@ -299,7 +300,7 @@ IODINE_API int iodine_plan_set_weights(IodinePlan* plan, const IodineWeights* w,
   IOD_REQUIRE(p && w, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (launch_setup_weights(p, w, st)) return 1;
-  if (p->s.precision == IODINE_BF16 && tc_setup_weights(p, w, st)) return 1;
+  if (tc_mode(p) && tc_setup_weights(p, w, st)) return 1;
   p->weights_set = true;
   return 0;
 }
@@ -402,7 +403,7 @@ IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, 
   if (!strcmp(name, "out4")) { src = p->out4; bytes = BK * HW * 4 * sizeof(float); }
   else if (!strcmp(name, "seed4")) {
     src = p->seed4; bytes = BK * HW * 4 * sizeof(float);
-    if (p->s.precision == IODINE_BF16) {
+    if (tc_mode(p)) {
       if (bytes_out) *bytes_out = bytes;
       if (!dst) return 0;
       IOD_REQUIRE(dst_bytes >= bytes, "destination too small for %s: %zu < %zu", name, dst_bytes, bytes);
@@ -429,7 +430,7 @@ IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, 
   if (bytes_out) *bytes_out = bytes;
   if (!dst) return 0;
   IOD_REQUIRE(dst_bytes >= bytes, "destination too small for %s: %zu < %zu", name, dst_bytes, bytes);
-  if (act_view && p->s.precision == IODINE_BF16) return tc_export_f32(p, src, (float*)dst, BK * HW * p->C, st);
+  if (act_view && tc_mode(p)) return tc_export_f32(p, src, (float*)dst, BK * HW * p->C, st);
   IOD_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
