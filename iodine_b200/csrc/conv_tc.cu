@@ -186,9 +186,6 @@ struct TcSmem {                    // tail of the dynamic shared memory block
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ int tc_tile_start(const TcParams& p, int t) {
-  return p.segs ? (t / p.segs) * p.Ps + (t % p.segs) * 128 : t * 128;
-}
 __device__ __forceinline__ int tc_num_tiles(const TcParams& p, int th) {
   return p.segs ? th * p.segs : ((th - 1) * p.Ps + p.W - 1) / 128 + 1;
 }
@@ -203,20 +200,21 @@ template <int N, int KS, int NKS>
 __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint32_t abase, uint32_t wrap_at, uint32_t Q,
                                               uint32_t Ps, uint32_t ps16, uint32_t w_base16, uint32_t idesc) {
   constexpr uint64_t DESC_HI = (uint64_t)(8u | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+  // start addresses stay below 2^14, so the LBO field can be OR-ed in once and offsets added after
+  const uint32_t wb = w_base16 | ((uint32_t)N << 16);
   if constexpr (NKS > 0) {
-    const uint32_t lbo_hi = ps16 << 16;
+    const uint32_t ab = abase | (ps16 << 16);
 #pragma unroll
     for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
       for (int dx = 0; dx < KS; ++dx) {
         const uint32_t shift = (uint32_t)dy * Ps + (uint32_t)dx;
-        const uint32_t a0 = abase + shift - (shift >= wrap_at ? Q : 0u);   // ring wrap
+        const uint32_t a0 = ab + shift - (shift >= wrap_at ? Q : 0u);   // ring wrap
 #pragma unroll
         for (int ks = 0; ks < NKS; ++ks) {
           const int e = (dy * KS + dx) * NKS + ks;
-          const uint32_t alo = (a0 + (uint32_t)(2 * ks) * ps16) | lbo_hi;
-          const uint32_t blo = (w_base16 + (uint32_t)(e * 2 * N)) | ((uint32_t)N << 16);
-          tc_mma_bf16(d_tmem, DESC_HI | alo, DESC_HI | blo, idesc, e > 0 ? 1u : 0u);
+          tc_mma_bf16(d_tmem, DESC_HI | (a0 + (uint32_t)(2 * ks) * ps16), DESC_HI | (wb + (uint32_t)(e * 2 * N)),
+                      idesc, e > 0 ? 1u : 0u);
         }
       }
     }
@@ -229,28 +227,38 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint32_t abase, u
       const uint32_t sa = (uint32_t)(ta / KS) * Ps + (uint32_t)(ta % KS);
       const uint32_t sb = (uint32_t)(tb / KS) * Ps + (uint32_t)(tb % KS);
       const uint32_t a0 = abase + sa - (sa >= wrap_at ? Q : 0u);
-      const uint32_t alo = a0 | ((sb - sa) << 16);
-      const uint32_t blo = (w_base16 + (uint32_t)(q * 2 * N)) | ((uint32_t)N << 16);
-      tc_mma_bf16(d_tmem, DESC_HI | alo, DESC_HI | blo, idesc, q > 0 ? 1u : 0u);
+      tc_mma_bf16(d_tmem, DESC_HI | (a0 | ((sb - sa) << 16)), DESC_HI | (wb + (uint32_t)(q * 2 * N)), idesc,
+                  q > 0 ? 1u : 0u);
     }
   }
 }
 
-// walks the (work item, tile) sequence of one CTA; identical in the MMA and epilogue roles
+// Walks the (work item, tile) sequence of one CTA; identical in every role.  A tile starts at flat
+// position row*Ps + rem of its item's halo block; all stepping is incremental (an integer division
+// costs the single issuing thread more than an MMA).
 struct TcTileIter {
   int item, t, ntiles, n, y0, th;
+  int row, rem, seg;
   __device__ __forceinline__ void load_item(const TcParams& p) {
     if (item < p.items) {
-      n = item / p.strips;
-      y0 = (item % p.strips) * p.TH;
+      n = item / p.strips;                       // one division per work item (>= 8 tiles)
+      y0 = (item - n * p.strips) * p.TH;
       th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
       ntiles = tc_num_tiles(p, th);
     }
+    t = 0; row = 0; rem = 0; seg = 0;
   }
-  __device__ __forceinline__ void init(const TcParams& p) { item = blockIdx.x; t = 0; load_item(p); }
+  __device__ __forceinline__ void init(const TcParams& p) { item = blockIdx.x; load_item(p); }
   __device__ __forceinline__ bool valid(const TcParams& p) const { return item < p.items; }
+  __device__ __forceinline__ bool last_of_item() const { return t + 1 >= ntiles; }
   __device__ __forceinline__ void next(const TcParams& p) {
-    if (++t >= ntiles) { item += gridDim.x; t = 0; load_item(p); }
+    if (++t >= ntiles) { item += gridDim.x; load_item(p); return; }
+    if (p.segs) {
+      if (++seg == p.segs) { seg = 0; rem = 0; ++row; } else rem += 128;
+    } else {
+      rem += 128;
+      while (rem >= p.Ps) { rem -= p.Ps; ++row; }
+    }
   }
 };
 
@@ -320,30 +328,45 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     const uint32_t a_base = smem_u32(s_a);
     const uint32_t row_bytes = (uint32_t)Ps * 16u;
     const int nbox = p.n_full + (p.tail_px ? 1 : 0);
-    int g = 0;                                   // global halo-row counter of this CTA
+    // copy i of a halo row = (plane c, mirror copy cp, box k); lanes own copies lane and lane + 32
+    // (planes <= 8, copies <= 2, boxes <= 3).  Mapped once: no divisions in the row loop.
+    uint32_t cp_off[2], cp_c[2], cp_x[2];
+    bool cp_mir[2], cp_on[2], cp_tail[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int i = lane + 32 * j;
+      const int k = i % nbox, cc = i / nbox;
+      const int cp = cc & 1, c = cc >> 1;
+      cp_on[j] = c < p.nch_in;
+      cp_mir[j] = cp != 0;
+      cp_tail[j] = k >= p.n_full;
+      cp_c[j] = (uint32_t)c;
+      cp_x[j] = (uint32_t)(256 * k - 2 * pad);   // 8-byte elements (2 per pixel-plane): box k starts at pixel 128k - pad
+      cp_off[j] = (uint32_t)c * plane_bytes + (uint32_t)(cp * R) * row_bytes + (uint32_t)k * 2048u;
+    }
+    int slot = 0;
+    uint32_t phase = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int n = item / p.strips, y0 = (item % p.strips) * p.TH;
+      const int n = item / p.strips, y0 = (item - n * p.strips) * p.TH;
       const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
       const int nrows = th + 2 * pad;
-      for (int j = 0; j < nrows; ++j, ++g) {
-        const int slot = g % R;
+      for (int j = 0; j < nrows; ++j) {
         const uint32_t fb = smem_u32(&sb->full[slot]);
-        const int copies = (slot < p.m) ? 2 : 1;
+        const bool mirrored = slot < p.m;
         if (lane == 0) {
-          mbar_wait(smem_u32(&sb->empty[slot]), ((uint32_t)(g / R) & 1u) ^ 1u, 1);
-          mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (uint32_t)copies);
+          mbar_wait(smem_u32(&sb->empty[slot]), phase ^ 1u, 1);
+          mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (mirrored ? 2u : 1u));
         }
         __syncwarp();
         const int y = y0 - pad + j;
-        const int per_plane = copies * nbox;
-        for (int i = lane; i < p.nch_in * per_plane; i += 32) {
-          const int c = i / per_plane, rem = i - c * per_plane;
-          const int cp = rem / nbox, k = rem - cp * nbox;
-          const uint32_t dst = a_base + (uint32_t)c * plane_bytes + (uint32_t)(slot + cp * R) * row_bytes +
-                               (uint32_t)k * 2048u;
-          // x is addressed in 8-byte elements (2 per pixel-plane): box k starts at pixel 128k - pad
-          tma_load_4d(dst, (k < p.n_full) ? &p.maps.full : &p.maps.tail, fb, 256 * k - 2 * pad, y, c, n);
+        const uint32_t dst_row = a_base + (uint32_t)slot * row_bytes;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (cp_on[q] && (mirrored || !cp_mir[q]))
+            tma_load_4d(dst_row + cp_off[q], cp_tail[q] ? &p.maps.tail : &p.maps.full, fb, (int)cp_x[q], y,
+                        (int)cp_c[q], n);
         }
+        if (++slot == R) { slot = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
@@ -355,39 +378,54 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     mbar_wait(smem_u32(&sb->wbar), 0, 2);
     const uint32_t a_base16 = smem_u32(s_a) >> 4;
     const uint32_t w_base16 = __shfl_sync(0xffffffffu, smem_u32(s_w) >> 4, 0);
-    int g0 = 0, rows_ready = 0, rows_freed = 0, tau = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int y0 = (item % p.strips) * p.TH;
-      const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
-      const int nrows = th + 2 * pad;
-      const int ntiles = tc_num_tiles(p, th);
-      for (int t = 0; t < ntiles; ++t, ++tau) {
-        const int s = tc_tile_start(p, t);
-        int need = (s + 127 + 2 * pad * Ps + 2 * pad) / Ps;
-        if (need > nrows - 1) need = nrows - 1;
-        while (rows_ready <= g0 + need) {
-          mbar_wait(smem_u32(&sb->full[rows_ready % R]), (uint32_t)(rows_ready / R) & 1u, 3);
-          ++rows_ready;
-        }
-        const int stage = tau % TC_ACC_STAGES;
-        mbar_wait(smem_u32(&sb->tempty[stage]), ((uint32_t)(tau / TC_ACC_STAGES) & 1u) ^ 1u, 4);
-        tc_fence_after();
-        const int base_pos = ((g0 % R) * Ps + s) % Q;
-        const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(stage * N), 0);
-        const uint32_t abase = __shfl_sync(0xffffffffu, a_base16 + (uint32_t)base_pos, 0);
-        const uint32_t wrap_at = __shfl_sync(0xffffffffu, (uint32_t)(Q - base_pos), 0);
-        // rows that no later tile of this CTA reads go back to the producer
-        const int free_upto = (t + 1 < ntiles) ? g0 + tc_tile_start(p, t + 1) / Ps : g0 + nrows;
-        if (leader) {
-          tc_issue_tile<N, KS, NKS>(d_tmem, abase, wrap_at, (uint32_t)Q, (uint32_t)Ps, p.plane_stride16,
-                                    w_base16, p.idesc);
-          tc_commit(smem_u32(&sb->tfull[stage]));
-          for (int rf = rows_freed; rf < free_upto; ++rf) tc_commit(smem_u32(&sb->empty[rf % R]));
-        }
-        if (rows_freed < free_upto) rows_freed = free_upto;
-        __syncwarp();
+    // ring bookkeeping in (slot, phase) form; g_* count halo rows since the kernel started
+    int g0 = 0, slot0 = 0;                         // first halo row of the current item
+    int g_ready = 0, rs = 0; uint32_t rph = 0;     // rows known to have landed
+    int g_freed = 0, fs = 0;                       // rows handed back to the producer
+    int stage = 0; uint32_t sph = 0;               // accumulator stage
+    TcTileIter it;
+    it.init(p);
+    while (it.valid(p)) {
+      const int nrows = it.th + 2 * pad;
+      // last halo row this tile reads: row of (start + 127 + max tap shift)
+      int need = it.row + 2 * pad;
+      for (int v = it.rem + 127 + 2 * pad; v >= Ps; v -= Ps) ++need;
+      if (need > nrows - 1) need = nrows - 1;
+      while (g_ready <= g0 + need) {
+        mbar_wait(smem_u32(&sb->full[rs]), rph, 3);
+        ++g_ready;
+        if (++rs == R) { rs = 0; rph ^= 1u; }
       }
-      g0 += nrows;
+      mbar_wait(smem_u32(&sb->tempty[stage]), sph ^ 1u, 4);
+      tc_fence_after();
+      int prow = slot0 + it.row;                   // ring slot of the tile's first row
+      while (prow >= R) prow -= R;
+      const int base_pos = prow * Ps + it.rem;     // < Q
+      const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(stage * N), 0);
+      const uint32_t abase = __shfl_sync(0xffffffffu, a_base16 + (uint32_t)base_pos, 0);
+      const uint32_t wrap_at = __shfl_sync(0xffffffffu, (uint32_t)(Q - base_pos), 0);
+      const bool last = it.last_of_item();
+      it.next(p);
+      // rows that no later tile of this CTA reads go back to the producer
+      const int free_upto = last ? g0 + nrows : g0 + it.row;
+      if (leader) {
+        tc_issue_tile<N, KS, NKS>(d_tmem, abase, wrap_at, (uint32_t)Q, (uint32_t)Ps, p.plane_stride16, w_base16,
+                                  p.idesc);
+        tc_commit(smem_u32(&sb->tfull[stage]));
+        int f = fs;
+        for (int rf = g_freed; rf < free_upto; ++rf) {
+          tc_commit(smem_u32(&sb->empty[f]));
+          if (++f == R) f = 0;
+        }
+      }
+      while (g_freed < free_upto) { ++g_freed; if (++fs == R) fs = 0; }
+      if (++stage == TC_ACC_STAGES) { stage = 0; sph ^= 1u; }
+      if (last) {
+        g0 += nrows;
+        slot0 += nrows;
+        while (slot0 >= R) slot0 -= R;
+      }
+      __syncwarp();
     }
   } else {
     // =============================================================== epilogue warps
@@ -405,8 +443,8 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     constexpr int NAV = (EPI == EPI_DGRAD) ? NC / 8 : 1;
     // position of this thread's output pixel in tile `it`, or -1
     auto pix_of = [&](const TcTileIter& it) -> long long {
-      const int flat = tc_tile_start(p, it.t) + quad * 32 + lane;
-      const int r = flat / Ps, c = flat - r * Ps;
+      int r = it.row, c = it.rem + quad * 32 + lane;
+      while (c >= Ps) { c -= Ps; ++r; }
       if (c >= W || r >= it.th) return -1;
       return (long long)(it.y0 + r) * W + c;
     };
@@ -424,7 +462,8 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     if constexpr (EPI == EPI_DGRAD) {
       if (cur.valid(p)) load_prev(cur, pix, av);
     }
-    int tau = 0;
+    int stage = 0;
+    uint32_t sph = 0;
     while (cur.valid(p)) {
       // the next tile's previous-activation loads fly while this tile is processed
       TcTileIter nxt = cur;
@@ -434,8 +473,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         if (nxt.valid(p)) load_prev(nxt, pix_next, av_next);
       }
 
-      const int stage = tau % TC_ACC_STAGES;
-      mbar_wait(smem_u32(&sb->tfull[stage]), (uint32_t)(tau / TC_ACC_STAGES) & 1u, 5);
+      mbar_wait(smem_u32(&sb->tfull[stage]), sph, 5);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(stage * N + col0) + ((uint32_t)(quad * 32) << 16);
       uint32_t acc[NC];
@@ -488,7 +526,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
 #pragma unroll
         for (int k = 0; k < NAV; ++k) av[k] = av_next[k];
       }
-      ++tau;
+      if (++stage == TC_ACC_STAGES) { stage = 0; sph ^= 1u; }
     }
   }
 
