@@ -28,6 +28,7 @@
 // N = 16 (the smallest N of an M=128 UMMA; 12 zero columns), its data-gradient (4 -> C) packs TWO taps into one K=16 step by
 // pointing LBO at the flat distance between the taps (one 8-channel plane, 4 real channels).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -53,6 +54,7 @@ struct TcMaps {                   // one source buffer: rows are fetched as runs
 struct alignas(64) TcParams {
   TcMaps maps;
   int32_t f16;                    // 1: IEEE half operands, 0: bfloat16
+  int32_t dbg;                    // IODINE_TC_DEBUG bit mask (timing experiments only; results are wrong when set)
   int32_t nch_in;                 // input planes
   int32_t nch_out;                // output planes (N/8) for the bf16 epilogues
   int32_t H, W;
@@ -355,9 +357,11 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         const bool mirrored = slot < p.m;
         if (lane == 0) {
           mbar_wait(smem_u32(&sb->empty[slot]), phase ^ 1u, 1);
-          mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (mirrored ? 2u : 1u));
+          if (p.dbg & 4) mbar_arrive(fb);
+          else mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (mirrored ? 2u : 1u));
         }
         __syncwarp();
+        if (p.dbg & 4) { if (++slot == R) { slot = 0; phase ^= 1u; } continue; }
         const int y = y0 - pad + j;
         const uint32_t dst_row = a_base + (uint32_t)slot * row_bytes;
 #pragma unroll
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     auto load_prev = [&](const TcTileIter& it, long long pix, uint4* av) {
 #pragma unroll
       for (int k = 0; k < NAV; ++k)
-        av[k] = (pix >= 0) ? __ldg(p.actp + ((size_t)it.n * (N / 8) + k0 + k) * plane_sz + (size_t)pix)
+        av[k] = (pix >= 0 && !(p.dbg & 8)) ? __ldg(p.actp + ((size_t)it.n * (N / 8) + k0 + k) * plane_sz + (size_t)pix)
                            : make_uint4(0u, 0u, 0u, 0u);
     };
 
@@ -477,14 +481,19 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(stage * N + col0) + ((uint32_t)(quad * 32) << 16);
       uint32_t acc[NC];
+      if (p.dbg & 1) {
 #pragma unroll
-      for (int q = 0; q < NC / 16; ++q) IOD_TMEM_LD16((acc + q * 16), taddr + q * 16);
+        for (int q = 0; q < NC; ++q) acc[q] = 0u;
+      } else {
+#pragma unroll
+        for (int q = 0; q < NC / 16; ++q) IOD_TMEM_LD16((acc + q * 16), taddr + q * 16);
+      }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[stage]));   // accumulator stage is free again
 
-      if (pix >= 0) {
+      if (pix >= 0 && !(p.dbg & 2)) {
         if constexpr (EPI == EPI_OUT4) {
           float4 o;
           o.x = __uint_as_float(acc[0]) + bias_r[0];
@@ -781,6 +790,10 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->items = p->BK * q->strips;
   q->idesc = make_idesc(N, s.precision == IODINE_FP16);
   q->f16 = s.precision == IODINE_FP16;
+  {
+    static const int dbg = getenv("IODINE_TC_DEBUG") ? atoi(getenv("IODINE_TC_DEBUG")) : 0;
+    q->dbg = dbg;
+  }
   q->w_bytes = g.w_bytes;
   q->box_bytes = g.box_bytes;
   q->n_full = (s.W + 2 * q->pad) / 128;
