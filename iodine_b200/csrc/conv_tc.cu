@@ -38,10 +38,16 @@ namespace iod {
 // parameters of one launch
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_MAX_RING = 32;
-// threads: warp 0 TMA, warp 1 MMA + TMEM, then 4 or 8 epilogue warps (two per TMEM lane quadrant,
-// each taking half of the accumulator columns, when N >= 32)
+// threads: warp 0 TMA, warps 1..TC_ISSUERS MMA issuers (warp 1 also owns TMEM), then 4 or 8 epilogue
+// warps (two per TMEM lane quadrant, each taking half of the accumulator columns, when N >= 32).
+// Several issuers because ONE thread cannot feed the tensor pipe on these shapes: a tile is 36
+// distinct (A,B) descriptor pairs, ~7 issue cycles per uniform-datapath instruction and ~6
+// instructions per MMA measured, against 48 cycles of tensor-pipe time per M=128,N=64,K=16 MMA
+// (tools/umma_probe.cu).  Issuer w takes tiles w, w+TC_ISSUERS, ... of the CTA's tile sequence; a
+// tile owns one accumulator stage, so issuers never share an accumulator.
+constexpr int TC_ISSUERS = 2;
 __host__ __device__ constexpr int tc_epi_warps(int N) { return N >= 32 ? 8 : 4; }
-__host__ __device__ constexpr int tc_threads(int N) { return 64 + 32 * tc_epi_warps(N); }
+__host__ __device__ constexpr int tc_threads(int N) { return 32 * (1 + TC_ISSUERS) + 32 * tc_epi_warps(N); }
 constexpr int TC_ACC_STAGES = 4;
 
 enum TcEpi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_OUT4 = 2 };
@@ -62,7 +68,8 @@ struct alignas(64) TcParams {
   int32_t Ps;                     // ring row pitch, positions
   int32_t R, m;                   // ring rows, mirrored rows
   int32_t segs;                   // W/128 when tiles are row aligned, 0 = flat tiling
-  int32_t TH;                     // image rows per work item
+  int32_t TH;                     // image rows per work item (divides H: every item is TH rows)
+  int32_t NT;                     // tiles per work item
   int32_t strips;                 // ceil(H / TH)
   int32_t items;                  // BK * strips
   uint32_t idesc;
@@ -71,6 +78,7 @@ struct alignas(64) TcParams {
   int32_t n_full;                 // full 128-pixel boxes per halo row
   int32_t tail_px;                // pixels of the tail box (0 = none)
   uint32_t plane_stride16;        // ring plane stride, 16-byte units
+  uint32_t a_off[16];             // A-descriptor offset of (dx, K-step): dx + 2*ks*plane_stride16 (read as constants)
   const void* wimg;               // packed bf16 weights (global), layout = smem image
   const float* bias;              // [N] (EPI_FWD, EPI_OUT4)
   const uint4* actp;              // chunk-planar previous activation (EPI_DGRAD)
@@ -192,31 +200,33 @@ __device__ __forceinline__ int tc_num_tiles(const TcParams& p, int th) {
   return p.segs ? th * p.segs : ((th - 1) * p.Ps + p.W - 1) / 128 + 1;
 }
 
-// One tile = KS*KS*NKS tcgen05.mma (M=128, N, K=16), fully unrolled: every descriptor is a
-// warp-uniform base plus compile-time multiples of run-time strides, so the issuing thread spends
-// a few uniform-datapath instructions per MMA (a table lookup per MMA costs more than the MMA).
+// One tile = KS*KS*NKS tcgen05.mma (M=128, N, K=16), fully unrolled.  rb[dy] is the ring position
+// (16-byte units, LBO field already OR-ed in) of the tile's first pixel in halo row dy, with the ring
+// wrap resolved per ROW by the caller: every descriptor is then one uniform add of a compile-time
+// multiple of a run-time stride, so the issuing thread spends a few uniform-datapath instructions
+// per MMA (measured: per-tap wrap selects made the issue loop, not the tensor pipe, the bound).
 //   NKS >  0 : C-channel input, NKS = C/16 K-steps per tap; LBO = plane stride
 //   NKS == 0 : one 8-channel plane, two taps per K=16 step; LBO = flat distance between the taps
 // B image (weights) is [mma][k-half][n][8]: LBO = N (16-byte units), SBO = 128 B for A and B.
-template <int N, int KS, int NKS>
-__device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint32_t abase, uint32_t wrap_at, uint32_t Q,
-                                              uint32_t Ps, uint32_t ps16, uint32_t w_base16, uint32_t idesc) {
+//   PST16 > 0: the plane stride is a compile-time constant (geometry-specialised instantiation): every A
+//   offset becomes an immediate, which is what keeps ptxas from hoisting/spilling uniform registers.
+template <int N, int KS, int NKS, int PST16>
+__device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, const uint32_t (&rb)[KS], uint32_t Ps,
+                                              const uint32_t (&a_off)[16], uint32_t w_base16, uint32_t idesc) {
   constexpr uint64_t DESC_HI = (uint64_t)(8u | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
   // start addresses stay below 2^14, so the LBO field can be OR-ed in once and offsets added after
   const uint32_t wb = w_base16 | ((uint32_t)N << 16);
   if constexpr (NKS > 0) {
-    const uint32_t ab = abase | (ps16 << 16);
 #pragma unroll
     for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
       for (int dx = 0; dx < KS; ++dx) {
-        const uint32_t shift = (uint32_t)dy * Ps + (uint32_t)dx;
-        const uint32_t a0 = ab + shift - (shift >= wrap_at ? Q : 0u);   // ring wrap
 #pragma unroll
         for (int ks = 0; ks < NKS; ++ks) {
           const int e = (dy * KS + dx) * NKS + ks;
-          tc_mma_bf16(d_tmem, DESC_HI | (a0 + (uint32_t)(2 * ks) * ps16), DESC_HI | (wb + (uint32_t)(e * 2 * N)),
-                      idesc, e > 0 ? 1u : 0u);
+          const uint32_t off = PST16 ? (uint32_t)(dx + 2 * ks * PST16) : a_off[dx * NKS + ks];
+          tc_mma_bf16(d_tmem, DESC_HI | (rb[dy] + off),
+                      DESC_HI | (wb + (uint32_t)(e * 2 * N)), idesc, e > 0 ? 1u : 0u);
         }
       }
     }
@@ -228,9 +238,8 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint32_t abase, u
       const int tb = ta + 1;
       const uint32_t sa = (uint32_t)(ta / KS) * Ps + (uint32_t)(ta % KS);
       const uint32_t sb = (uint32_t)(tb / KS) * Ps + (uint32_t)(tb % KS);
-      const uint32_t a0 = abase + sa - (sa >= wrap_at ? Q : 0u);
-      tc_mma_bf16(d_tmem, DESC_HI | (a0 | ((sb - sa) << 16)), DESC_HI | (wb + (uint32_t)(q * 2 * N)), idesc,
-                  q > 0 ? 1u : 0u);
+      tc_mma_bf16(d_tmem, DESC_HI | ((rb[ta / KS] + (uint32_t)(ta % KS)) | ((sb - sa) << 16)),
+                  DESC_HI | (wb + (uint32_t)(q * 2 * N)), idesc, q > 0 ? 1u : 0u);
     }
   }
 }
@@ -241,6 +250,7 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint32_t abase, u
 struct TcTileIter {
   int item, t, ntiles, n, y0, th;
   int row, rem, seg;
+  int ps = 0;                                    // compile-time ring pitch of a specialised kernel (0: p.Ps)
   __device__ __forceinline__ void load_item(const TcParams& p) {
     if (item < p.items) {
       n = item / p.strips;                       // one division per work item (>= 8 tiles)
@@ -255,16 +265,18 @@ struct TcTileIter {
   __device__ __forceinline__ bool last_of_item() const { return t + 1 >= ntiles; }
   __device__ __forceinline__ void next(const TcParams& p) {
     if (++t >= ntiles) { item += gridDim.x; load_item(p); return; }
+    const int Ps = ps ? ps : p.Ps;
     if (p.segs) {
       if (++seg == p.segs) { seg = 0; rem = 0; ++row; } else rem += 128;
     } else {
       rem += 128;
-      while (rem >= p.Ps) { rem -= p.Ps; ++row; }
+      while (rem >= Ps) { rem -= Ps; ++row; }
     }
   }
 };
 
-template <int N, int EPI, int KS, int NKS>
+// PS / PST16: ring pitch and plane stride as compile-time constants (0 = read them from the parameters).
+template <int N, int EPI, int KS, int NKS, int PS, int PST16>
 __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NTHREADS = tc_threads(N);
@@ -274,12 +286,13 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
   const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
   uint8_t* s_w = smem;
   uint8_t* s_a = smem + w_region;
-  const uint32_t plane_bytes = p.plane_stride16 * 16u;
+  const uint32_t plane_stride16 = PST16 ? (uint32_t)PST16 : p.plane_stride16;
+  const uint32_t plane_bytes = plane_stride16 * 16u;
   TcSmem* sb = reinterpret_cast<TcSmem*>(s_a + (size_t)p.nch_in * plane_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int pad = KS / 2;
-  const int Ps = p.Ps, R = p.R;
+  const int Ps = PS ? PS : p.Ps, R = p.R;
   const int Q = R * Ps;
   const int F16 = p.f16;
 
@@ -287,14 +300,14 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
   //      barriers, TMEM
   {
     uint4* a4 = reinterpret_cast<uint4*>(s_a);
-    const int n16 = p.nch_in * (int)p.plane_stride16;
+    const int n16 = p.nch_in * (int)plane_stride16;
     for (int i = threadIdx.x; i < n16; i += NTHREADS) a4[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; ++i) {
       mbar_init(smem_u32(&sb->full[i]), 1);
-      mbar_init(smem_u32(&sb->empty[i]), 1);
+      mbar_init(smem_u32(&sb->empty[i]), TC_ISSUERS);   // every issuer hands every row back once
     }
     for (int i = 0; i < TC_ACC_STAGES; ++i) {
       mbar_init(smem_u32(&sb->tfull[i]), 1);
@@ -374,47 +387,79 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // =============================================================== MMA issuer
+  } else if (warp <= TC_ISSUERS) {
+    // =============================================================== MMA issuers
     // All lanes walk the tile sequence (so the per-tile bases are warp-uniform values); one elected
-    // lane issues the MMAs and commits.
-    const bool leader = elect_one_sync();
+    // lane issues the MMAs and commits.  Issuer w = warp-1 owns tiles w, w+TC_ISSUERS, ...
+    const int w = warp - 1;
+    // lane 0 rather than elect.sync on purpose: behind a plain lane test ptxas wraps every UTCHMMA in its
+    // own small issue block, which keeps descriptor arithmetic next to its MMA; with elect.sync it hoists
+    // all 2*KS*KS*NKS descriptors above the first MMA and spills uniform registers (measured slower)
+    const bool leader = (lane == 0);
     mbar_wait(smem_u32(&sb->wbar), 0, 2);
     const uint32_t a_base16 = smem_u32(s_a) >> 4;
-    const uint32_t w_base16 = __shfl_sync(0xffffffffu, smem_u32(s_w) >> 4, 0);
+    const uint32_t w_base16 = smem_u32(s_w) >> 4;
+    // Lean tile iterator: every work item is TH rows (TH divides H), so a tile is (item ordinal k, tile t)
+    // with constant tiles / halo rows per item, stepped without divisions.
+    const int NT = p.NT, nrows = p.TH + 2 * pad, segs = p.segs;
+    const int my_items = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    int k = 0, t = 0, row = 0, rem = 0, seg = 0;
     // ring bookkeeping in (slot, phase) form; g_* count halo rows since the kernel started
-    int g0 = 0, slot0 = 0;                         // first halo row of the current item
+    int g0 = 0, slot0 = 0;                         // first halo row of the iterator's current item
     int g_ready = 0, rs = 0; uint32_t rph = 0;     // rows known to have landed
-    int g_freed = 0, fs = 0;                       // rows handed back to the producer
-    int stage = 0; uint32_t sph = 0;               // accumulator stage
-    TcTileIter it;
-    it.init(p);
-    while (it.valid(p)) {
-      const int nrows = it.th + 2 * pad;
+    int g_freed = 0, fs = 0;                       // rows this issuer has handed back to the producer
+    int tcnt = 0;                                  // index of the iterator's tile in the CTA's sequence
+    auto advance = [&]() {
+      ++tcnt;
+      if (++t == NT) {
+        t = 0; row = 0; rem = 0; seg = 0; ++k;
+        g0 += nrows;
+        slot0 += nrows;
+        while (slot0 >= R) slot0 -= R;
+      } else if (segs) {
+        if (++seg == segs) { seg = 0; rem = 0; ++row; } else rem += 128;
+      } else {
+        rem += 128;
+        while (rem >= Ps) { rem -= Ps; ++row; }
+      }
+    };
+    for (int i = 0; i < w && k < my_items; ++i) advance();
+    while (k < my_items) {
       // last halo row this tile reads: row of (start + 127 + max tap shift)
-      int need = it.row + 2 * pad;
-      for (int v = it.rem + 127 + 2 * pad; v >= Ps; v -= Ps) ++need;
+      int need = row + 2 * pad;
+      for (int v = rem + 127 + 2 * pad; v >= Ps; v -= Ps) ++need;
       if (need > nrows - 1) need = nrows - 1;
       while (g_ready <= g0 + need) {
         mbar_wait(smem_u32(&sb->full[rs]), rph, 3);
         ++g_ready;
         if (++rs == R) { rs = 0; rph ^= 1u; }
       }
+      const int stage = tcnt % TC_ACC_STAGES;
+      const uint32_t sph = (uint32_t)(tcnt / TC_ACC_STAGES) & 1u;
       mbar_wait(smem_u32(&sb->tempty[stage]), sph ^ 1u, 4);
       tc_fence_after();
-      int prow = slot0 + it.row;                   // ring slot of the tile's first row
-      while (prow >= R) prow -= R;
-      const int base_pos = prow * Ps + it.rem;     // < Q
+      // ring position of the tile's first pixel in each of its KS halo rows (wrap resolved per row; the
+      // mirrored rows behind the ring end keep every 128-run contiguous)
+      uint32_t rb[KS];
+      {
+        int pr = slot0 + row;
+        while (pr >= R) pr -= R;
+        const uint32_t lbo_or = (NKS > 0) ? (plane_stride16 << 16) : 0u;
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy) {
+          rb[dy] = __shfl_sync(0xffffffffu, (a_base16 + (uint32_t)(pr * Ps + rem)) | lbo_or, 0);
+          if (++pr == R) pr = 0;
+        }
+      }
       const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(stage * N), 0);
-      const uint32_t abase = __shfl_sync(0xffffffffu, a_base16 + (uint32_t)base_pos, 0);
-      const uint32_t wrap_at = __shfl_sync(0xffffffffu, (uint32_t)(Q - base_pos), 0);
-      const bool last = it.last_of_item();
-      it.next(p);
-      // rows that no later tile of this CTA reads go back to the producer
-      const int free_upto = last ? g0 + nrows : g0 + it.row;
+      // re-derived per tile on purpose: a loop-invariant weight base makes ptxas hoist all KS*KS*NKS B
+      // descriptors into vector registers and pay an R2UR (plus uniform-register spills) per MMA
+      const uint32_t wb_t = __shfl_sync(0xffffffffu, w_base16, 0);
+      // step to this issuer's next tile: rows below its first row are not read by this issuer again
+      for (int i = 0; i < TC_ISSUERS && k < my_items; ++i) advance();
+      const int free_upto = (k < my_items) ? g0 + row : g0;
       if (leader) {
-        tc_issue_tile<N, KS, NKS>(d_tmem, abase, wrap_at, (uint32_t)Q, (uint32_t)Ps, p.plane_stride16, w_base16,
-                                  p.idesc);
+        tc_issue_tile<N, KS, NKS, PST16>(d_tmem, rb, (uint32_t)Ps, p.a_off, wb_t, p.idesc);
         tc_commit(smem_u32(&sb->tfull[stage]));
         int f = fs;
         for (int rf = g_freed; rf < free_upto; ++rf) {
@@ -423,18 +468,21 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         }
       }
       while (g_freed < free_upto) { ++g_freed; if (++fs == R) fs = 0; }
-      if (++stage == TC_ACC_STAGES) { stage = 0; sph ^= 1u; }
-      if (last) {
-        g0 += nrows;
-        slot0 += nrows;
-        while (slot0 >= R) slot0 -= R;
-      }
       __syncwarp();
     }
+    // an issuer that ran out of tiles early still owes its arrival on the remaining rows
+    if (leader) {
+      int f = fs;
+      for (int rf = g_freed; rf < g0; ++rf) {
+        tc_commit(smem_u32(&sb->empty[f]));
+        if (++f == R) f = 0;
+      }
+    }
+    __syncwarp();
   } else {
     // =============================================================== epilogue warps
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
-    const int half = (EW == 8) ? (warp - 2) / 4 : 0;
+    const int half = (EW == 8) ? (warp - 1 - TC_ISSUERS) / 4 : 0;
     const int col0 = half * NC;                    // first accumulator column / output channel
     const int k0 = col0 / 8;                       // first output plane
     const int H = p.H, W = p.W;
@@ -460,6 +508,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     };
 
     TcTileIter cur;
+    cur.ps = PS;
     cur.init(p);
     uint4 av[NAV], av_next[NAV];
     long long pix = cur.valid(p) ? pix_of(cur) : -1;
@@ -623,7 +672,7 @@ static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo
   g->segs = (s.W % 128 == 0) ? s.W / 128 : 0;
   g->w_bytes = (uint32_t)n_ent * 2u * (uint32_t)N * 16u;
   g->box_bytes = (uint32_t)(s.W + 2 * pad) * 16u;
-  g->m = (127 + max_lbo_pos + g->Ps - 1) / g->Ps;
+  g->m = (127 + 2 * pad + max_lbo_pos + g->Ps - 1) / g->Ps;   // rows mirrored behind the ring end
   const size_t row_bytes = (size_t)nch_in * g->Ps * 16;
   const size_t budget = (size_t)227 * 1024 - round_up((int)g->w_bytes, 1024) - 1024 - sizeof(TcSmem);
   int rows = (int)(budget / row_bytes);
@@ -635,8 +684,8 @@ static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo
   g->plane_stride16 = (uint32_t)(R + g->m) * g->Ps;
   if (g->plane_stride16 >= 16384u) return false;              // LBO field is 14 bits
   // rows per work item: balance the grid (items >> SMs) against halo re-reads
-  int TH = 8;
-  if (s.H < 8) TH = s.H;
+  int TH = 8;                                                  // largest divisor of H that is <= 8
+  while (s.H % TH != 0) --TH;
   g->TH = TH;
   g->smem = (size_t)round_up((int)g->w_bytes, 1024) + (size_t)nch_in * g->plane_stride16 * 16 + sizeof(TcSmem) + 64;
   return g->smem <= (size_t)227 * 1024;
@@ -799,12 +848,19 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->n_full = (s.W + 2 * q->pad) / 128;
   q->tail_px = (s.W + 2 * q->pad) % 128;
   q->plane_stride16 = g.plane_stride16;
+  q->NT = g.segs ? g.TH * g.segs : ((g.TH - 1) * g.Ps + s.W - 1) / 128 + 1;
+  const int nks = nch_in / 2, ks_dim = s.dec_k;
+  for (int i = 0; i < 16; ++i) q->a_off[i] = 0;
+  if (nks > 0)
+    for (int dx = 0; dx < ks_dim; ++dx)
+      for (int ks = 0; ks < nks; ++ks)
+        if (dx * nks + ks < 16) q->a_off[dx * nks + ks] = (uint32_t)dx + (uint32_t)(2 * ks) * g.plane_stride16;
 }
 
 // dispatch on the compile-time shape <N, EPI, KS, NKS>
-template <int N, int EPI, int KS, int NKS>
-static int tc_launch_k(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
-  auto kern = conv_tc_kernel<N, EPI, KS, NKS>;
+template <int N, int EPI, int KS, int NKS, int PS, int PST16>
+static int tc_launch_g(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
+  auto kern = conv_tc_kernel<N, EPI, KS, NKS, PS, PST16>;
   static bool attr_done = false;
   if (!attr_done) {
     IOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -814,6 +870,21 @@ static int tc_launch_k(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_
   kern<<<grid, tc_threads(N), smem, st_>>>(q);
   IOD_LAUNCH_CHECK(p);
   return 0;
+}
+
+// Geometry-specialised instantiations for the shapes the reference's configs use (ring pitch and plane
+// stride baked in as immediates); any other shape runs the generic kernel.  The constants are what
+// tc_geometry() yields for: W=128 k=3 C=64 (configs/clevr6*.yaml) and W=64 k=3 C=32 (configs/dsprites*.yaml).
+template <int N, int EPI, int KS, int NKS>
+static int tc_launch_k(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
+  const int ps = q.Ps, pst = (int)q.plane_stride16;
+  if constexpr (KS == 3 && NKS == 4 && N == 64) { if (ps == 136 && pst == 1224) return tc_launch_g<N, EPI, KS, NKS, 136, 1224>(p, q, smem, st_); }
+  if constexpr (KS == 3 && NKS == 4 && N == 16) { if (ps == 136 && pst == 1632) return tc_launch_g<N, EPI, KS, NKS, 136, 1632>(p, q, smem, st_); }
+  if constexpr (KS == 3 && NKS == 0 && N == 64) { if (ps == 136 && pst == 4624) return tc_launch_g<N, EPI, KS, NKS, 136, 4624>(p, q, smem, st_); }
+  if constexpr (KS == 3 && NKS == 2 && (N == 32 || N == 16)) { if (ps == 72 && pst == 2448) return tc_launch_g<N, EPI, KS, NKS, 72, 2448>(p, q, smem, st_); }
+  if constexpr (KS == 3 && NKS == 0 && N == 32) { if (ps == 72 && pst == 2520) return tc_launch_g<N, EPI, KS, NKS, 72, 2520>(p, q, smem, st_); }
+  if (getenv("IODINE_TC_VERBOSE")) fprintf(stderr, "conv_tc: generic kernel for N=%d EPI=%d KS=%d NKS=%d (Ps=%d, plane stride %d)\n", N, EPI, KS, NKS, ps, pst);
+  return tc_launch_g<N, EPI, KS, NKS, 0, 0>(p, q, smem, st_);
 }
 
 // C -> C layers (forward / data-gradient): N = C, NKS = C/16
