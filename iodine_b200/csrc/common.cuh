@@ -97,6 +97,7 @@ struct Plan {
   float *head_w = nullptr, *head_b = nullptr;   // [2L, M] (mean rows then logvar rows), [2L]
   float *init_mean = nullptr, *init_logvar = nullptr;
   void* tc = nullptr;         // tensor-core path state (conv_tc.cu: TcState), IODINE_BF16 / IODINE_FP16
+  void* rtc = nullptr;        // refinement-encoder tensor-core state (refine_tc.cu: RtcState)
 
   // ---- workspace carve-up (caller memory)
   void* ws = nullptr;
@@ -109,7 +110,9 @@ struct Plan {
   float* auxs = nullptr;          // [BK,H,W,12] per-slot raw aux channels
   float* lik = nullptr;           // [B,H,W] raw pixel likelihood
   float* enc20 = nullptr;         // [BK,H,W,20] normalised refinement input (17 + 3 pad)
-  float* rbuf[2];                 // refine conv ping-pong
+  float* rbuf[2];                 // refine conv ping-pong (fp32 path)
+  void* enc16 = nullptr;          // [BK,2,H,W,8] 16-bit chunk-planar refinement input, 15 data channels (16-bit modes)
+  void* r16[2];                   // refine conv ping-pong, 16-bit chunk-planar (16-bit modes)
   float* z = nullptr;             // [BK,L]
   float* u = nullptr;             // [BK,n_class,C]
   float* G = nullptr;             // [BK,n_class,C] class-wise pixel sums of dJ/d(pre-act 1)
@@ -132,6 +135,9 @@ struct Plan {
   float* hmask = nullptr;         // [B,K,1,H,W]
   float* hmean = nullptr;         // [B,K,3,H,W]
 };
+
+// split-K factor of the LSTM gate GEMM (head.cu); the gates buffer holds that many partial sums
+constexpr int LSTM_KSPLIT = 4;
 
 // tensor-core modes keep the decoder activations as 16-bit values (bf16 or fp16), chunk-planar
 inline bool tc_mode(const Plan* p) { return p->s.precision == IODINE_BF16 || p->s.precision == IODINE_FP16; }
@@ -162,6 +168,7 @@ int launch_refine_convs(Plan* p, const float* x, cudaStream_t st);
 int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st);
 int launch_recombine(Plan* p, float* pred, float* mask, float* mean, cudaStream_t st);
 int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st);
+int launch_assemble16(Plan* p, const float* x, cudaStream_t st);   // 16-bit modes: writes p->enc16
 
 // ------------------------------------------------------------------ launchers (head.cu)
 int launch_sample_l1(Plan* p, const float* mu, const float* logvar, const float* eps,
@@ -189,5 +196,13 @@ int tc_export_seed(Plan* p, const void* seed8, float* dst, cudaStream_t st);
 // sums of the last data-gradient (its inverse)
 int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st);
 int tc_launch_class_sum(Plan* p, const void* g, cudaStream_t st);
+
+// ------------------------------------------------------------------ refine_tc.cu (tcgen05 refinement encoder)
+int rtc_supported(const Plan* p);
+int rtc_alloc(Plan* p);
+void rtc_free(Plan* p);
+bool rtc_enabled(const Plan* p);       // 16-bit mode and every refine layer fits the tensor-core kernel
+int rtc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st);
+int rtc_launch_refine_convs(Plan* p, cudaStream_t st);   // p->enc16 -> p->pool
 
 }  // namespace iod

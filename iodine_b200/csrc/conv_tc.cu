@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace iod {
 
@@ -84,105 +85,6 @@ struct alignas(64) TcParams {
   const uint4* actp;              // chunk-planar previous activation (EPI_DGRAD)
   void* out;                      // chunk-planar bf16 (uint4 per position-plane) or fp32 out4
 };
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// A deadlock must become a launch failure, never a hung GPU: bounded wait, then trap.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("conv_tc: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, (int)blockIdx.x,
-             (int)threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0,
-                                            int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "elect.sync _|P1, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, P1;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
-}
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-// bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, layout type 0.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, uint32_t sbo16) {
-  return (uint64_t)(addr16 & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) |
-         ((uint64_t)(sbo16 & 0x3FFFu) << 32) | (1ull << 46);
-}
-
-#define IOD_TMEM_LD16(r, addr)                                                                  \
-  asm volatile(                                                                                 \
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                 \
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                          \
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),      \
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), \
-        "=r"(r[14]), "=r"(r[15])                                                                \
-      : "r"(addr))
-
-// ELU with the hardware exponential: |error| <= ~2e-7 absolute, far below bf16 rounding.
-__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
@@ -978,38 +880,51 @@ int tc_launch_dgrad_in4(Plan* p, const float* seed8, const void* act_prev, void*
 
 // ---- helpers around the chunk-planar layout -------------------------------------------------------
 // act0[n][k][y][x][8] = ELU(u[n][class(y,x)][co] + ptab_c[k][y][x][8])   (first decoder layer, collapsed)
+// A thread owns one (pixel, 8-channel plane) and walks TC_L1_NB slot-images with the coordinate-table
+// values in registers (the table is read once per group of images, not once per image).
+constexpr int TC_L1_NB = 8;
 __global__ void __launch_bounds__(256)
 tc_layer1_kernel(const float* __restrict__ u, const float* __restrict__ ptab_c, uint4* __restrict__ act0,
-                 int H, int W, int C, int KS, int f16) {
-  const int n = blockIdx.z, k = blockIdx.y;
+                 int H, int W, int C, int KS, int BK, int f16) {
+  const int k = blockIdx.y;
   const int P = KS / 2, HW = H * W;
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
-    const int y = pix / W, x = pix - y * W;
-    const int cls = border_class(y, H, P) * KS + border_class(x, W, P);
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const int y = pix / W, x = pix - y * W;
+  const int cls = border_class(y, H, P) * KS + border_class(x, W, P);
+  const float4* pv = reinterpret_cast<const float4*>(ptab_c + ((size_t)k * HW + pix) * 8);
+  const float4 p0 = __ldg(pv), p1 = __ldg(pv + 1);
+  const int n0 = blockIdx.z * TC_L1_NB;
+  const int n1 = (n0 + TC_L1_NB < BK) ? n0 + TC_L1_NB : BK;
+#pragma unroll 4
+  for (int n = n0; n < n1; ++n) {
     const float4* uv = reinterpret_cast<const float4*>(u + ((size_t)n * KS * KS + cls) * C + k * 8);
-    const float4* pv = reinterpret_cast<const float4*>(ptab_c + ((size_t)k * HW + pix) * 8);
-    const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1), p0 = __ldg(pv), p1 = __ldg(pv + 1);
+    const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
     uint4 o;
-    o.x = pack_h2(elu_f(u0.x + p0.x), elu_f(u0.y + p0.y), f16);
-    o.y = pack_h2(elu_f(u0.z + p0.z), elu_f(u0.w + p0.w), f16);
-    o.z = pack_h2(elu_f(u1.x + p1.x), elu_f(u1.y + p1.y), f16);
-    o.w = pack_h2(elu_f(u1.z + p1.z), elu_f(u1.w + p1.w), f16);
+    // hardware exponential: |error| ~1e-7 absolute, far below the 16-bit rounding that follows (the
+    // libm expm1f made this bandwidth-bound kernel compute-bound)
+    o.x = pack_h2(elu_fast(u0.x + p0.x), elu_fast(u0.y + p0.y), f16);
+    o.y = pack_h2(elu_fast(u0.z + p0.z), elu_fast(u0.w + p0.w), f16);
+    o.z = pack_h2(elu_fast(u1.x + p1.x), elu_fast(u1.y + p1.y), f16);
+    o.w = pack_h2(elu_fast(u1.z + p1.z), elu_fast(u1.w + p1.w), f16);
     act0[((size_t)n * (C / 8) + k) * HW + pix] = o;
   }
 }
 
 int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st_) {
   TcState* st = tc_state(p);
-  int gx = (p->HW + 255) / 256;
-  if (gx > 64) gx = 64;
-  dim3 grid(gx, p->C / 8, p->BK);
+  dim3 grid((p->HW + 255) / 256, p->C / 8, (p->BK + TC_L1_NB - 1) / TC_L1_NB);
   tc_layer1_kernel<<<grid, 256, 0, st_>>>(p->u, st->ptab_c, reinterpret_cast<uint4*>(act0), p->s.H, p->s.W, p->C,
-                                          p->s.dec_k, p->s.precision == IODINE_FP16);
+                                          p->s.dec_k, p->BK, p->s.precision == IODINE_FP16);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
 // G[n][class][co] = sum over pixels of the class of g[n][co/8][y][x][co%8]  (layer-1 dgrad collapse)
+// The block walks its rows in maximal runs of equal row class.  Inside a run a thread owns column
+// x = tid % min(W,256) and every (256/W)-th row, four loads in flight; its column class is fixed, so
+// interior columns are block-reduced once per run and the 2*(k/2) border columns flush their own sums:
+// a handful of atomics per (block, run) instead of one per border pixel.
 __global__ void __launch_bounds__(256)
 tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, int W, int C, int KS, int rows_per_block,
                     int f16) {
@@ -1020,12 +935,56 @@ tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, i
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ float red[8][8];
   float* Gn = G + (size_t)n * KS * KS * C + k * 8;
-  float run[8];
-  int cy_run = -1;
+  const uint4* gp = g + ((size_t)n * (C / 8) + k) * HW;
+  const int Wc = W < 256 ? W : 256;
+  const int nsub = 256 / Wc;                        // rows in flight per pass (1 when W >= 256)
+  const int x0 = threadIdx.x % Wc, ysub = threadIdx.x / Wc;
+  const bool active = ysub < nsub;
+  const int cx0 = border_class(x0, W, P);
+  float run[8], brun[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) run[e] = 0.f;
-  auto flush = [&](int cy) {
-    // block-reduce the interior-column run of rows with equal class cy
+  for (int e = 0; e < 8; ++e) { run[e] = 0.f; brun[e] = 0.f; }
+  auto add = [&](const uint4& v, float* acc) {
+    const float2 a = unpack_h2(v.x, f16), b = unpack_h2(v.y, f16), c = unpack_h2(v.z, f16), d = unpack_h2(v.w, f16);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+    acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  };
+  int y = y_lo;
+  while (y < y_hi) {
+    const int cy = border_class(y, H, P);            // block-uniform run [y, y_end) of equal row class
+    int y_end = y + 1;
+    while (y_end < y_hi && border_class(y_end, H, P) == cy) ++y_end;
+    if (active) {
+      for (int yy = y + ysub; yy < y_end; yy += 4 * nsub) {
+        uint4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int yq = yy + q * nsub;
+          v[q] = (yq < y_end) ? __ldg(gp + (size_t)yq * W + x0) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) add(v[q], cx0 == P ? run : brun);
+        for (int x = x0 + 256; x < W; x += 256) {     // W > 256 only
+          for (int q = 0; q < 4; ++q) {
+            const int yq = yy + q * nsub;
+            if (yq >= y_end) break;
+            const uint4 w = __ldg(gp + (size_t)yq * W + x);
+            const int cx = border_class(x, W, P);
+            if (cx == P) add(w, run);
+            else {
+              float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              add(w, t);
+              for (int e = 0; e < 8; ++e) atomicAdd(Gn + (size_t)(cy * KS + cx) * C + e, t[e]);
+            }
+          }
+        }
+      }
+    }
+    // flush the run
+    if (active && cx0 != P) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { atomicAdd(Gn + (size_t)(cy * KS + cx0) * C + e, brun[e]); brun[e] = 0.f; }
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) run[e] = warp_sum(run[e]);
     __syncthreads();
@@ -1040,30 +999,12 @@ tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, i
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) run[e] = 0.f;
-  };
-  for (int y = y_lo; y < y_hi; ++y) {
-    const int cy = border_class(y, H, P);          // block-uniform
-    if (cy != cy_run && cy_run >= 0) flush(cy_run);
-    cy_run = cy;
-    for (int x = threadIdx.x; x < W; x += blockDim.x) {
-      const uint4 v = __ldg(g + ((size_t)n * (C / 8) + k) * HW + (size_t)y * W + x);
-      const float2 a = unpack_h2(v.x, f16), b = unpack_h2(v.y, f16), c = unpack_h2(v.z, f16), d = unpack_h2(v.w, f16);
-      const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-      const int cx = border_class(x, W, P);
-      if (cx == P) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) run[e] += f[e];
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(Gn + (size_t)(cy * KS + cx) * C + e, f[e]);
-      }
-    }
+    y = y_end;
   }
-  if (cy_run >= 0) flush(cy_run);
 }
 
 int tc_launch_class_sum(Plan* p, const void* g, cudaStream_t st_) {
-  const int rpb = 16;
+  const int rpb = 32;
   dim3 grid((p->s.H + rpb - 1) / rpb, p->C / 8, p->BK);
   tc_class_sum_kernel<<<grid, 256, 0, st_>>>(reinterpret_cast<const uint4*>(g), p->G, p->s.H, p->s.W, p->C,
                                              p->s.dec_k, rpb, p->s.precision == IODINE_FP16);

@@ -234,7 +234,7 @@ int launch_sample_l1(Plan* p, const float* mu, const float* logvar, const float*
 // dz[n][ci] = sum_{cls,co} wsum[cls][co][ci] * G[n][cls][co]      (layer-1 dgrad, collapsed)
 // dmu = dz - mu ; dlogvar = dz * 0.5 exp(logvar/2) eps - 0.5 (exp(logvar) - 1)   (row A4)
 // xin[n][M + ...] = [mu, logvar, LN3(dmu), LN3(dlogvar)]   (iodine.py:253-275; unbiased std)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 post_grads_kernel(const float* __restrict__ G, const float* __restrict__ wsum,
                   const float* __restrict__ mu, const float* __restrict__ logvar,
                   const float* __restrict__ eps, float* __restrict__ dz_out,
@@ -244,14 +244,33 @@ post_grads_kernel(const float* __restrict__ G, const float* __restrict__ wsum,
   float* sG = sm;            // [NCC]
   float* sa = sm + NCC;      // [L] dmu
   float* sb = sa + L;        // [L] dlogvar
+  float* sp = sb + L;        // [parts][L] partial dz
   __shared__ float red[8];
   const int n = blockIdx.x;
   for (int i = threadIdx.x; i < NCC; i += blockDim.x) sG[i] = G[(size_t)n * NCC + i];
   __syncthreads();
+  // dz: thread (part, ci) sums every parts-th (class, channel) row of wsum (coalesced over ci)
+  const int parts = (int)blockDim.x / L > 0 ? (int)blockDim.x / L : 1;
+  {
+    const int part = threadIdx.x / L, ci0 = threadIdx.x % L;
+    if (part < parts) {
+      for (int ci = ci0; ci < L; ci += (parts > 1 ? L : (int)blockDim.x)) {
+        float d0 = 0.f, d1 = 0.f;
+        int o = part;
+        for (; o + parts < NCC; o += 2 * parts) {
+          d0 = fmaf(__ldg(wsum + (size_t)o * L + ci), sG[o], d0);
+          d1 = fmaf(__ldg(wsum + (size_t)(o + parts) * L + ci), sG[o + parts], d1);
+        }
+        if (o < NCC) d0 = fmaf(__ldg(wsum + (size_t)o * L + ci), sG[o], d0);
+        sp[part * L + ci] = d0 + d1;
+      }
+    }
+  }
+  __syncthreads();
   float klp = 0.f;
   for (int ci = threadIdx.x; ci < L; ci += blockDim.x) {
     float d = 0.f;
-    for (int o = 0; o < NCC; ++o) d = fmaf(wsum[(size_t)o * L + ci], sG[o], d);
+    for (int q = 0; q < parts; ++q) d += sp[q * L + ci];
     const float m = mu[(size_t)n * L + ci], lv = logvar[(size_t)n * L + ci], e = eps[(size_t)n * L + ci];
     dz_out[(size_t)n * L + ci] = d;
     sa[ci] = d - m;
@@ -293,8 +312,9 @@ int launch_post_grads(Plan* p, const float* mu, const float* logvar, const float
                       float* latent_out, cudaStream_t st) {
   (void)latent_out;
   const int ncc = p->n_class * p->C, L = p->s.L;
-  const size_t smem = (size_t)(ncc + 2 * L) * sizeof(float);
-  post_grads_kernel<<<p->BK, 128, smem, st>>>(p->G, p->wsum, mu, logvar, eps, p->dz, p->xin, p->accum,
+  const int parts = 256 / L > 0 ? 256 / L : 1;
+  const size_t smem = (size_t)(ncc + 2 * L + parts * L) * sizeof(float);
+  post_grads_kernel<<<p->BK, 256, smem, st>>>(p->G, p->wsum, mu, logvar, eps, p->dz, p->xin, p->accum,
                                               L, ncc, p->M, p->s.layernorm);
   IOD_LAUNCH_CHECK(p);
   return 0;
@@ -323,56 +343,70 @@ int launch_kl(Plan* p, const float* mu, const float* logvar, cudaStream_t st) {
 // =====================================================================================
 // Y[N][O] (ldy) = act( X[N][I] (ldx) * W[O][I]^T + b  [+ X2[N][I2] * W2[O][I2]^T + b2] )
 // ACT: 0 none, 1 ELU(ELU(.)) (MLP's own ELU at iodine.py:565 and the extra one at 485)
-template <int ACT>
+// RM = rows per thread (tile = 16*RM rows x 64 columns): small row tiles keep all SMs busy when N is
+// only a few hundred slot-images.
+template <int ACT, int RM>
 __global__ void __launch_bounds__(256)
 linear_kernel(const float* __restrict__ X, int ldx, int I, const float* __restrict__ Wt,
               const float* __restrict__ b, const float* __restrict__ X2, int ldx2, int I2,
               const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ Y,
-              int ldy, int N, int O) {
-  constexpr int TM = 64, TN = 64, TK = 16;
+              int ldy, int N, int O, int kchunk, size_t zstride) {
+  constexpr int TM = 16 * RM, TN = 64, TK = 16;
   __shared__ float sx[TK][TM + 4];
   __shared__ float sw[TK][TN + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int r0 = blockIdx.y * TM, c0 = blockIdx.x * TN;
-  float acc[4][4];
+  float acc[RM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // split-K: block z owns [z*kc, (z+1)*kc) of the concatenated reduction axis [X | X2] and writes its
+  // partial sums to Y + z*zstride (summed by the consumer; deterministic, no atomics)
+  const int kc = (int)kchunk, kz_lo = (int)blockIdx.z * kc, kz_hi = kz_lo + kc;
+  Y += (size_t)blockIdx.z * zstride;
   for (int pass = 0; pass < 2; ++pass) {
     const float* Xp = pass ? X2 : X;
     const float* Wp = pass ? W2 : Wt;
     const int ld = pass ? ldx2 : ldx, In = pass ? I2 : I;
     if (!Xp) continue;
-    for (int k0 = 0; k0 < In; k0 += TK) {
+    const int base = pass ? I : 0;                       // offset of this operand on the concatenated axis
+    const int lo = (kz_lo > base ? kz_lo : base) - base;
+    const int hi = ((kz_hi < base + In) ? kz_hi : base + In) - base;
+    for (int k0 = lo; k0 < hi; k0 += TK) {
       __syncthreads();
       for (int i = threadIdx.x; i < TM * TK; i += 256) {
         const int kk = i % TK, r = i / TK;
-        sx[kk][r] = (r0 + r < N && k0 + kk < In) ? Xp[(size_t)(r0 + r) * ld + k0 + kk] : 0.f;
-        sw[kk][r] = (c0 + r < O && k0 + kk < In) ? Wp[(size_t)(c0 + r) * In + k0 + kk] : 0.f;
+        sx[kk][r] = (r0 + r < N && k0 + kk < hi) ? Xp[(size_t)(r0 + r) * ld + k0 + kk] : 0.f;
+      }
+      for (int i = threadIdx.x; i < TN * TK; i += 256) {
+        const int kk = i % TK, r = i / TK;
+        sw[kk][r] = (c0 + r < O && k0 + kk < hi) ? Wp[(size_t)(c0 + r) * In + k0 + kk] : 0.f;
       }
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < TK; ++kk) {
-        float xv[4], wv[4];
+        float xv[RM], wv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { xv[i] = sx[kk][ty * 4 + i]; wv[i] = sw[kk][tx * 4 + i]; }
+        for (int i = 0; i < RM; ++i) xv[i] = sx[kk][ty * RM + i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) wv[i] = sw[kk][tx * 4 + i];
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int r = r0 + ty * RM + i;
     if (r >= N) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = c0 + tx * 4 + j;
       if (c >= O) continue;
-      float v = acc[i][j] + b[c] + (b2 ? b2[c] : 0.f);
+      float v = acc[i][j] + (blockIdx.z == 0 ? b[c] + (b2 ? b2[c] : 0.f) : 0.f);
       if (ACT == 1) v = elu_f(elu_f(v));
       Y[(size_t)r * ldy + c] = v;
     }
@@ -380,13 +414,17 @@ linear_kernel(const float* __restrict__ X, int ldx, int I, const float* __restri
 }
 
 // LSTMCell pointwise (torch gate order i,f,g,o): c' = s(f) c + s(i) tanh(g), h' = s(o) tanh(c')
+// gates arrive as `parts` split-K partial sums [parts][N][4M]
 __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __restrict__ h,
-                                      float* __restrict__ c, int N, int M) {
+                                      float* __restrict__ c, int N, int M, int parts) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * M; i += gridDim.x * blockDim.x) {
     const int n = i / M, j = i % M;
-    const float* g = gates + (size_t)n * 4 * M;
-    const float ig = sigmoid_f(g[j]), fg = sigmoid_f(g[M + j]), gg = tanhf(g[2 * M + j]),
-                og = sigmoid_f(g[3 * M + j]);
+    float gs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < parts; ++q) {
+      const float* g = gates + ((size_t)q * N + n) * 4 * M;
+      gs[0] += g[j]; gs[1] += g[M + j]; gs[2] += g[2 * M + j]; gs[3] += g[3 * M + j];
+    }
+    const float ig = sigmoid_f(gs[0]), fg = sigmoid_f(gs[1]), gg = tanhf(gs[2]), og = sigmoid_f(gs[3]);
     const float cn = fg * c[i] + ig * gg;
     c[i] = cn;
     h[i] = og * tanhf(cn);
@@ -407,23 +445,24 @@ int launch_head(Plan* p, float* mu, float* logvar, float* h, float* c, cudaStrea
   const int N = p->BK, M = p->M, L = p->s.L, Cr = p->Cr, I = M + 4 * L;
   // MLP + double ELU, written into the first M columns of xin (torch.cat at iodine.py:487)
   {
-    dim3 grid((M + 63) / 64, (N + 63) / 64);
-    linear_kernel<1><<<grid, 256, 0, st>>>(p->pool, Cr, Cr, p->mlp_w, p->mlp_b, nullptr, 0, 0, nullptr,
-                                           nullptr, p->xin, I, N, M);
+    dim3 grid((M + 63) / 64, (N + 15) / 16);
+    linear_kernel<1, 1><<<grid, 256, 0, st>>>(p->pool, Cr, Cr, p->mlp_w, p->mlp_b, nullptr, 0, 0, nullptr,
+                                              nullptr, p->xin, I, N, M, Cr, 0);
     IOD_LAUNCH_CHECK(p);
   }
   {
-    dim3 grid((4 * M + 63) / 64, (N + 63) / 64);
-    linear_kernel<0><<<grid, 256, 0, st>>>(p->xin, I, I, p->w_ih, p->b_ih, h, M, M, p->w_hh, p->b_hh,
-                                           p->gates, 4 * M, N, 4 * M);
+    const int ktot = I + M, kchunk = ((ktot + LSTM_KSPLIT - 1) / LSTM_KSPLIT + 15) / 16 * 16;
+    dim3 grid((4 * M + 63) / 64, (N + 63) / 64, LSTM_KSPLIT);
+    linear_kernel<0, 4><<<grid, 256, 0, st>>>(p->xin, I, I, p->w_ih, p->b_ih, h, M, M, p->w_hh, p->b_hh,
+                                              p->gates, 4 * M, N, 4 * M, kchunk, (size_t)N * 4 * M);
     IOD_LAUNCH_CHECK(p);
   }
-  lstm_pointwise_kernel<<<(N * M + 255) / 256, 256, 0, st>>>(p->gates, h, c, N, M);
+  lstm_pointwise_kernel<<<(N * M + 255) / 256, 256, 0, st>>>(p->gates, h, c, N, M, LSTM_KSPLIT);
   IOD_LAUNCH_CHECK(p);
   {  // both heads read the CELL state (iodine.py:488-492); delta reuses the gates buffer
-    dim3 grid((2 * L + 63) / 64, (N + 63) / 64);
-    linear_kernel<0><<<grid, 256, 0, st>>>(c, M, M, p->head_w, p->head_b, nullptr, 0, 0, nullptr, nullptr,
-                                           p->gates, 2 * L, N, 2 * L);
+    dim3 grid((2 * L + 63) / 64, (N + 15) / 16);
+    linear_kernel<0, 1><<<grid, 256, 0, st>>>(c, M, M, p->head_w, p->head_b, nullptr, 0, 0, nullptr, nullptr,
+                                              p->gates, 2 * L, N, 2 * L, M, 0);
     IOD_LAUNCH_CHECK(p);
   }
   update_kernel<<<(N * L + 255) / 256, 256, 0, st>>>(p->gates, mu, logvar, N, L);

@@ -270,16 +270,81 @@ int launch_assemble(Plan* p, const float* x, cudaStream_t st) {
   return 0;
 }
 
+// 16-bit modes: the same stack for the tensor-core refinement encoder (refine_tc.cu) -- the 15 DATA channels
+// in reference order, chunk-planar 16-bit [n][2][H][W][8] (plane 0 = channels 0-7, plane 1 = 8-14 + one zero).
+// The two coordinate channels (15, 16) do not depend on the data; their convolution is folded into the
+// per-position bias table of the encoder's first layer.
+__global__ void __launch_bounds__(256)
+assemble16_kernel(const float* __restrict__ auxs, const float* __restrict__ lik,
+                  const float* __restrict__ x, const double* __restrict__ stats,
+                  uint4* __restrict__ enc16, int K, int HW, int layernorm, int f16) {
+  const int n = blockIdx.y, b = n / K;
+  __shared__ float s_mu[4], s_is[4];
+  if (threadIdx.x < 4) {
+    float mu = 0.f, is = 1.f;
+    if (layernorm) {
+      const double cnt = (threadIdx.x == 0) ? 3.0 * HW : (double)HW;
+      const double sum = stats[((size_t)n * 4 + threadIdx.x) * 2 + 0];
+      const double sq = stats[((size_t)n * 4 + threadIdx.x) * 2 + 1];
+      const double m = sum / cnt;
+      double var = sq / cnt - m * m;
+      if (var < 0.0) var = 0.0;
+      mu = (float)m;
+      is = 1.f / ((float)sqrt(var) + 1e-5f);
+    }
+    s_mu[threadIdx.x] = mu; s_is[threadIdx.x] = is;
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const float4* ax = reinterpret_cast<const float4*>(auxs) + ((size_t)n * HW + pix) * 3;
+  const float4 a0 = ax[0], a1 = ax[1], a2 = ax[2];
+  const float xr = x[((size_t)b * 3 + 0) * HW + pix], xg = x[((size_t)b * 3 + 1) * HW + pix],
+              xb = x[((size_t)b * 3 + 2) * HW + pix];
+  const float lk = lik[(size_t)b * HW + pix];
+  uint4 o0, o1;
+  o0.x = pack_h2(xr, xg, f16);
+  o0.y = pack_h2(xb, a0.x, f16);
+  o0.z = pack_h2(a0.y, a0.z, f16);
+  o0.w = pack_h2(a0.w, a1.x, f16);
+  o1.x = pack_h2(a1.y, (a1.z - s_mu[0]) * s_is[0], f16);
+  o1.y = pack_h2((a1.w - s_mu[0]) * s_is[0], (a2.x - s_mu[0]) * s_is[0], f16);
+  o1.z = pack_h2((a2.y - s_mu[1]) * s_is[1], (lk - s_mu[2]) * s_is[2], f16);
+  o1.w = pack_h2((a2.z - s_mu[3]) * s_is[3], 0.f, f16);
+  enc16[((size_t)n * 2 + 0) * HW + pix] = o0;
+  enc16[((size_t)n * 2 + 1) * HW + pix] = o1;
+}
+
+int launch_assemble16(Plan* p, const float* x, cudaStream_t st) {
+  dim3 grid((p->HW + 255) / 256, p->BK);
+  assemble16_kernel<<<grid, 256, 0, st>>>(p->auxs, p->lik, x, p->stats, reinterpret_cast<uint4*>(p->enc16), p->s.K,
+                                          p->HW, p->s.layernorm, p->s.precision == IODINE_FP16);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
 // tests only: reference layout [B,K,17,H,W] followed by latent [B,K,4L]
-__global__ void export_aux_kernel(const float* __restrict__ enc20, const float* __restrict__ xin,
-                                  float* __restrict__ aux_out, int BK, int HW, int M, int L4) {
+__global__ void export_aux_kernel(const float* __restrict__ enc20, const uint16_t* __restrict__ enc16,
+                                  const float* __restrict__ xin, float* __restrict__ aux_out, int BK, int H, int W,
+                                  int M, int L4, int f16) {
+  const int HW = H * W;
   const size_t total = (size_t)BK * 17 * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const int pix = i % HW;
     const int c = (i / HW) % 17;
     const int n = i / ((size_t)HW * 17);
-    aux_out[i] = enc20[((size_t)n * HW + pix) * 20 + c];
+    if (!enc16) {
+      aux_out[i] = enc20[((size_t)n * HW + pix) * 20 + c];
+    } else if (c < 15) {
+      const uint16_t u = enc16[(((size_t)n * 2 + c / 8) * HW + pix) * 8 + c % 8];
+      aux_out[i] = f16 ? __half2float(*reinterpret_cast<const __half*>(&u))
+                       : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+    } else {                                       // coordinate channels are implicit in the 16-bit modes
+      const int yy = pix / W, xx = pix % W;
+      aux_out[i] = (c == 15) ? ((W > 1) ? -1.f + 2.f * (float)xx / (float)(W - 1) : -1.f)
+                             : ((H > 1) ? -1.f + 2.f * (float)yy / (float)(H - 1) : -1.f);
+    }
   }
   const size_t tl = (size_t)BK * L4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tl;
@@ -291,8 +356,10 @@ __global__ void export_aux_kernel(const float* __restrict__ enc20, const float* 
 
 int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st) {
   (void)x;
-  export_aux_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->enc20, p->xin, aux_out, p->BK, p->HW, p->M,
-                                                    4 * p->s.L);
+  const bool rtc = rtc_enabled(p);
+  export_aux_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->enc20, rtc ? reinterpret_cast<const uint16_t*>(p->enc16) : nullptr,
+                                                    p->xin, aux_out, p->BK, p->s.H, p->s.W, p->M, 4 * p->s.L,
+                                                    p->s.precision == IODINE_FP16);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

@@ -2,6 +2,7 @@
 // per-step kernel sequence that replaces IODINE.encode/decode/reconstruct/elbo
 // (reference lib/modeling/iodine.py:59-241).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -41,12 +42,16 @@ static size_t carve(Plan* p, char* base) {
   p->out4 = (float*)take(BK * HW * 4 * sizeof(float));
   p->seed4 = (float*)take(BK * HW * 4 * sizeof(float));
   p->auxs = (float*)take(BK * HW * 12 * sizeof(float));
-  p->enc20 = (float*)take(BK * HW * 20 * sizeof(float));
+  const bool rtc = rtc_enabled(p);
+  p->enc20 = (float*)take(rtc ? 1024 : BK * HW * 20 * sizeof(float));
+  p->enc16 = take(rtc ? BK * HW * 32 : 1024);
   p->lik = (float*)take((size_t)s.B * HW * sizeof(float));
   size_t r0 = (size_t)p->ref_h[1] * p->ref_w[1] * Cr;
   size_t r1 = s.ref_layers > 1 ? (size_t)p->ref_h[2] * p->ref_w[2] * Cr : 256;
-  p->rbuf[0] = (float*)take(BK * r0 * sizeof(float));
-  p->rbuf[1] = (float*)take(BK * r1 * sizeof(float));
+  p->rbuf[0] = (float*)take(rtc ? 1024 : BK * r0 * sizeof(float));
+  p->rbuf[1] = (float*)take(rtc ? 1024 : BK * r1 * sizeof(float));
+  p->r16[0] = take(rtc ? BK * r0 * 2 : 1024);
+  p->r16[1] = take(rtc ? BK * r1 * 2 : 1024);
   p->z = (float*)take(BK * L * sizeof(float));
   p->u = (float*)take(BK * p->n_class * C * sizeof(float));
   p->G = (float*)take(BK * p->n_class * C * sizeof(float));
@@ -55,7 +60,7 @@ static size_t carve(Plan* p, char* base) {
   p->accum = (double*)take(2 * sizeof(double));
   p->pool = (float*)take(BK * Cr * sizeof(float));
   p->xin = (float*)take(BK * (M + 4 * L) * sizeof(float));
-  p->gates = (float*)take(BK * 4 * M * sizeof(float));
+  p->gates = (float*)take((size_t)LSTM_KSPLIT * BK * 4 * M * sizeof(float));
   p->st_mean = (float*)take(BK * L * sizeof(float));
   p->st_logvar = (float*)take(BK * L * sizeof(float));
   p->st_h = (float*)take(BK * M * sizeof(float));
@@ -151,8 +156,13 @@ static int refine_step(Plan* p, const float* x, const float* eps_t, float* mu, f
   if (launch_mixture(p, x, true, st)) return 1;
   if (decoder_dgrad(p, st)) return 1;
   if (launch_post_grads(p, mu, lv, eps_t, nullptr, st)) return 1;
-  if (launch_assemble(p, x, st)) return 1;
-  if (launch_refine_convs(p, p->enc20, st)) return 1;
+  if (rtc_enabled(p)) {
+    if (launch_assemble16(p, x, st)) return 1;
+    if (rtc_launch_refine_convs(p, st)) return 1;
+  } else {
+    if (launch_assemble(p, x, st)) return 1;
+    if (launch_refine_convs(p, p->enc20, st)) return 1;
+  }
   if (aux_out && launch_export_aux(p, x, aux_out, st)) return 1;
   if (launch_head(p, mu, lv, h, c, st)) return 1;
   if (terms_out) {
@@ -255,6 +265,7 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
       alloc_f(&p->init_logvar, L))
     return 1;
   if (tc_mode(p) && tc_alloc(p)) return 1;
+  if (tc_mode(p) && !getenv("IODINE_REFINE_FFMA") && rtc_alloc(p)) return 1;
   p->ws_need = carve(p, nullptr);
   *plan_out = reinterpret_cast<IodinePlan*>(p);
   return 0;
@@ -273,6 +284,7 @@ IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
   cudaFree(p->b_hh); cudaFree(p->head_w); cudaFree(p->head_b); cudaFree(p->init_mean);
   cudaFree(p->init_logvar);
   tc_free(p);
+  rtc_free(p);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   delete p;
   return 0;
@@ -301,6 +313,7 @@ IODINE_API int iodine_plan_set_weights(IodinePlan* plan, const IodineWeights* w,
   cudaStream_t st = (cudaStream_t)stream;
   if (launch_setup_weights(p, w, st)) return 1;
   if (tc_mode(p) && tc_setup_weights(p, w, st)) return 1;
+  if (rtc_enabled(p) && rtc_setup_weights(p, w, st)) return 1;
   p->weights_set = true;
   return 0;
 }

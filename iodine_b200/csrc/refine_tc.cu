@@ -1,0 +1,427 @@
+// refine_tc.cu -- tcgen05 convolutions of the refinement encoder (16-bit precision modes).
+//
+// Replaces RefinementNetwork.forward's conv stack (reference lib/modeling/iodine.py:480, MultiLayerConv
+// with stride, 583/592) and the tail of get_input_encoding (iodine.py:277-340) that builds its input.
+//
+// The encoder's convolutions are STRIDED (ARCH.REF.STRIDE = 2), so the flat-ring trick of conv_tc.cu does
+// not apply (a run of output pixels is not a run of input pixels).  They are also small (1.8 % of the
+// path's FLOPs, outputs of 64x64 down to 8x8 per slot-image).  Formulation:
+//   * implicit GEMM, M = 128 consecutive OUTPUT positions of the flattened (slot-image, y, x) space,
+//     N = Cout, K = taps x Cin; accumulator in TMEM;
+//   * four producer warps gather the A operand one TAP at a time with 16-byte cp.async copies (zero
+//     fill outside the image = the zero padding) straight into the no-swizzle K-major core-matrix
+//     layout (one 2 KB block of 128 positions x 8 channels per channel group), several taps in flight
+//     through a ring of stages; cp.async completion -> fence.proxy.async -> mbarrier arrive hands a
+//     stage to the tensor core;
+//   * one thread issues Cin/16 tcgen05.mma per tap against the resident weight image, tcgen05.commit
+//     frees the stage;
+//   * four epilogue warps read TMEM, add the bias (layer 0: a per-position table that also carries the
+//     two coordinate channels, whose convolution does not depend on the data), apply ELU and store the
+//     16-bit chunk-planar activation of the next layer.
+// Layer 0 therefore contracts over 15 data channels padded to 16 (one K step per tap) instead of 17.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace iod {
+
+constexpr int RTC_STAGES = 6;      // A-operand ring (one tap of one tile per stage)
+constexpr int RTC_LAG = 3;         // cp.async groups a producer thread keeps in flight
+constexpr int RTC_ACC = 4;         // TMEM accumulator stages
+constexpr int RTC_THREADS = 128 + 32 + 128;
+
+struct RtcParams {
+  const uint4* in;       // chunk-planar [n][cin_planes][Hin][Win] (uint4 = 8 channels of one pixel)
+  uint4* out;            // chunk-planar [n][N/8][Hout][Wout]
+  const void* wimg;      // [tap][ks][k-half][n][8] 16-bit
+  const float* bias;     // [N]                     (tab == nullptr)
+  const float* tab;      // [Hout*Wout][N] bias + coordinate-channel convolution (layer 0) or nullptr
+  uint32_t w_bytes;
+  int32_t Hin, Win, Hout, Wout, S, pad, KS;
+  int32_t cin_planes;
+  int32_t total;         // BK * Hout * Wout output positions
+  int32_t tiles;
+  int32_t f16;
+  uint32_t idesc;
+};
+
+struct RtcSmem {
+  uint64_t full[RTC_STAGES];
+  uint64_t empty[RTC_STAGES];
+  uint64_t tfull[RTC_ACC];
+  uint64_t tempty[RTC_ACC];
+  uint64_t wbar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int N, int NKS>
+__global__ void __launch_bounds__(RTC_THREADS, 1) refine_tc_kernel(const __grid_constant__ RtcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int TMEM_COLS = (RTC_ACC * N < 32) ? 32 : RTC_ACC * N;
+  constexpr uint32_t STAGE_BYTES = (uint32_t)(2 * NKS) * 2048u;       // cin_planes x (128 positions x 16 B)
+  const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
+  uint8_t* s_w = smem;
+  uint8_t* s_a = smem + w_region;
+  RtcSmem* sb = reinterpret_cast<RtcSmem*>(s_a + (size_t)RTC_STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntaps = p.KS * p.KS;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RTC_STAGES; ++i) {
+      mbar_init(smem_u32(&sb->full[i]), 128);      // every producer thread arrives
+      mbar_init(smem_u32(&sb->empty[i]), 1);       // tcgen05.commit
+    }
+    for (int i = 0; i < RTC_ACC; ++i) {
+      mbar_init(smem_u32(&sb->tfull[i]), 1);
+      mbar_init(smem_u32(&sb->tempty[i]), 4);      // one arrive per epilogue warp
+    }
+    mbar_init(smem_u32(&sb->wbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sb->tmem_base)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sb->tmem_base;
+  const int HWo = p.Hout * p.Wout;
+
+  if (warp < 4) {
+    // =============================================================== producers (gather)
+    const int tid = threadIdx.x;                   // = position inside the tile
+    const uint32_t a_base = smem_u32(s_a) + (uint32_t)tid * 16u;
+    const size_t plane_in = (size_t)p.Hin * p.Win;
+    int stage = 0;
+    uint32_t phase = 0;
+    int issued = 0, arrived_stage = 0;             // groups committed; stage of the oldest un-arrived group
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      const int pos = tile * 128 + tid;
+      const bool valid = pos < p.total;
+      const int n = valid ? pos / HWo : 0;
+      const int r = valid ? pos - n * HWo : 0;
+      const int y = r / p.Wout, x = r - y * p.Wout;
+      const uint4* in_n = p.in + (size_t)n * (2 * NKS) * plane_in;
+      int dy = 0, dx = 0;
+      for (int tap = 0; tap < ntaps; ++tap) {
+        mbar_wait(smem_u32(&sb->empty[stage]), phase ^ 1u, 11);
+        const int iy = y * p.S + dy - p.pad, ix = x * p.S + dx - p.pad;
+        const bool inb = valid && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+        const uint4* src = inb ? in_n + (size_t)iy * p.Win + ix : p.in;
+        const uint32_t dst = a_base + (uint32_t)stage * STAGE_BYTES;
+        const uint32_t nbytes = inb ? 16u : 0u;    // 0: cp.async writes 16 zero bytes (the zero padding)
+#pragma unroll
+        for (int g = 0; g < 2 * NKS; ++g) cp_async16(dst + (uint32_t)g * 2048u, src + (size_t)g * plane_in, nbytes);
+        cp_async_commit();
+        ++issued;
+        if (issued > RTC_LAG) {                    // the group committed RTC_LAG groups ago has landed
+          cp_async_wait<RTC_LAG>();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(smem_u32(&sb->full[arrived_stage]));
+          if (++arrived_stage == RTC_STAGES) arrived_stage = 0;
+        }
+        if (++stage == RTC_STAGES) { stage = 0; phase ^= 1u; }
+        if (++dx == p.KS) { dx = 0; ++dy; }
+      }
+    }
+    // drain
+    cp_async_wait<0>();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int left = issued < RTC_LAG ? issued : RTC_LAG;
+    for (int i = 0; i < left; ++i) {
+      mbar_arrive(smem_u32(&sb->full[arrived_stage]));
+      if (++arrived_stage == RTC_STAGES) arrived_stage = 0;
+    }
+  } else if (warp == 4) {
+    // =============================================================== MMA issuer (+ weight load)
+    if (lane == 0) {
+      const uint32_t wbar = smem_u32(&sb->wbar);
+      mbar_expect_tx(wbar, p.w_bytes);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg);
+      for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
+        const uint32_t nb = (p.w_bytes - off < 16384u) ? (p.w_bytes - off) : 16384u;
+        bulk_load_1d(smem_u32(s_w + off), src + off, nb, wbar);
+      }
+      mbar_wait(wbar, 0, 12);
+      constexpr uint64_t DESC_HI = (uint64_t)(8u | (1u << 14)) << 32;      // SBO = 128 B, version 1
+      const uint32_t a16 = (smem_u32(s_a) >> 4) | (128u << 16);           // LBO = 2 KB between the K halves
+      const uint32_t w16 = (smem_u32(s_w) >> 4) | ((uint32_t)N << 16);    // LBO = N (16-byte units)
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&sb->tempty[acc]), aph ^ 1u, 13);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+        for (int tap = 0; tap < ntaps; ++tap) {
+          mbar_wait(smem_u32(&sb->full[stage]), phase, 14);
+          tc_fence_after();
+          const uint32_t a0 = a16 + (uint32_t)stage * (STAGE_BYTES >> 4);
+          const uint32_t b0 = w16 + (uint32_t)(tap * NKS) * (uint32_t)(2 * N);
+#pragma unroll
+          for (int ks = 0; ks < NKS; ++ks)
+            tc_mma_bf16(d_tmem, DESC_HI | (a0 + (uint32_t)ks * 256u), DESC_HI | (b0 + (uint32_t)(ks * 2 * N)), p.idesc,
+                        (tap | ks) ? 1u : 0u);
+          tc_commit(smem_u32(&sb->empty[stage]));
+          if (++stage == RTC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(smem_u32(&sb->tfull[acc]));
+        if (++acc == RTC_ACC) { acc = 0; aph ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================================== epilogue warps
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int F16 = p.f16;
+    int acc = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      const int pos = tile * 128 + quad * 32 + lane;
+      const bool valid = pos < p.total;
+      const int n = valid ? pos / HWo : 0;
+      const int r = valid ? pos - n * HWo : 0;
+      mbar_wait(smem_u32(&sb->tfull[acc]), aph, 15);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        constexpr int NC = (N < 32) ? N : 32;
+        uint32_t v[NC];
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * N + c0) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int q = 0; q < NC / 16; ++q) IOD_TMEM_LD16((v + q * 16), taddr + q * 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 >= N) {                         // last read of this accumulator stage
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[acc]));
+        }
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < NC / 8; ++k) {
+            float f[8];
+            const int c = c0 + k * 8;
+            const float4* bp = reinterpret_cast<const float4*>(p.tab ? p.tab + (size_t)r * N + c : p.bias + c);
+            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = elu_fast(__uint_as_float(v[k * 8 + e]) + bb[e]);
+            uint4 o;
+            o.x = pack_h2(f[0], f[1], F16);
+            o.y = pack_h2(f[2], f[3], F16);
+            o.z = pack_h2(f[4], f[5], F16);
+            o.w = pack_h2(f[6], f[7], F16);
+            p.out[((size_t)n * (N / 8) + (c >> 3)) * HWo + r] = o;
+          }
+        }
+      }
+      if (++acc == RTC_ACC) { acc = 0; aph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct RtcState {
+  uint16_t* w[IODINE_MAX_LAYERS];     // packed weight images
+  uint32_t w_bytes[IODINE_MAX_LAYERS];
+  int cin[IODINE_MAX_LAYERS];         // contracted channels per layer (16 for layer 0, Cr after)
+  float* tab0 = nullptr;              // [H1*W1][Cr] layer-0 bias + coordinate-channel table
+  bool ok = false;
+};
+
+static RtcState* rtc_state(Plan* p) { return reinterpret_cast<RtcState*>(p->rtc); }
+
+static size_t rtc_smem_bytes(uint32_t w_bytes, int nks) {
+  return (size_t)((w_bytes + 1023u) & ~1023u) + (size_t)RTC_STAGES * (2 * nks) * 2048 + sizeof(RtcSmem) + 64;
+}
+
+// 1 if every refine layer fits the tensor-core kernel (otherwise the FFMA path of conv_f32.cu runs)
+int rtc_supported(const Plan* p) {
+  const IodineShape& s = p->s;
+  const int Cr = p->Cr, kk = s.ref_k * s.ref_k;
+  if (Cr != 16 && Cr != 32 && Cr != 64) return 0;
+  for (int l = 0; l < s.ref_layers; ++l) {
+    const int cin = l == 0 ? 16 : Cr;
+    const uint32_t wb = (uint32_t)kk * (cin / 16) * 2u * (uint32_t)Cr * 16u;
+    if (rtc_smem_bytes(wb, cin / 16) > (size_t)227 * 1024) return 0;
+  }
+  return 1;
+}
+
+int rtc_alloc(Plan* p) {
+  RtcState* st = new RtcState();
+  p->rtc = st;
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { st->w[l] = nullptr; st->w_bytes[l] = 0; st->cin[l] = 0; }
+  st->ok = rtc_supported(p) != 0;
+  if (!st->ok) return 0;
+  const IodineShape& s = p->s;
+  const int Cr = p->Cr, kk = s.ref_k * s.ref_k;
+  for (int l = 0; l < s.ref_layers; ++l) {
+    st->cin[l] = l == 0 ? 16 : Cr;
+    st->w_bytes[l] = (uint32_t)kk * (st->cin[l] / 16) * 2u * (uint32_t)Cr * 16u;
+    IOD_CHECK_CUDA(cudaMalloc((void**)&st->w[l], st->w_bytes[l]));
+  }
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->tab0, (size_t)p->ref_h[1] * p->ref_w[1] * Cr * sizeof(float)));
+  return 0;
+}
+
+void rtc_free(Plan* p) {
+  RtcState* st = rtc_state(p);
+  if (!st) return;
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) cudaFree(st->w[l]);
+  cudaFree(st->tab0);
+  delete st;
+  p->rtc = nullptr;
+}
+
+bool rtc_enabled(const Plan* p) {
+  const RtcState* st = reinterpret_cast<const RtcState*>(p->rtc);
+  return st && st->ok;
+}
+
+// weight image [tap][ks][k-half][n][8]; w is OIHW [Cr][CI][k][k], only input channels < cin_real are used
+__global__ void rtc_pack_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int Cr, int CI, int cin_real,
+                                int cin, int KS, int f16) {
+  const int nks = cin / 16;
+  const int total = KS * KS * nks * 2 * Cr * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, n = (i / 8) % Cr, kc = (i / (8 * Cr)) % 2, ks = (i / (16 * Cr)) % nks, tap = i / (16 * Cr * nks);
+    const int k = (2 * ks + kc) * 8 + e;
+    const float v = k < cin_real ? w[((size_t)n * CI + k) * KS * KS + tap] : 0.f;
+    if (f16) { __half h = __float2half_rn(v); img[i] = *reinterpret_cast<uint16_t*>(&h); }
+    else { __nv_bfloat16 h = __float2bfloat16(v); img[i] = *reinterpret_cast<uint16_t*>(&h); }
+  }
+}
+
+// tab0[y][x][co] = bias[co] + zero-padded strided conv of the two coordinate planes (input channels 15, 16 of
+// the refinement input: x = linspace(-1,1,W) along W, y along H; iodine.py:334-339)
+__global__ void rtc_tab0_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ tab,
+                                int Cr, int KS, int S, int H, int W, int Ho, int Wo) {
+  const int P = KS / 2;
+  const int total = Ho * Wo * Cr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % Cr, x = (i / Cr) % Wo, y = i / (Cr * Wo);
+    float s = b[co];
+    for (int dy = 0; dy < KS; ++dy) {
+      const int iy = y * S + dy - P;
+      if (iy < 0 || iy >= H) continue;
+      const float cyv = (H > 1) ? -1.f + 2.f * (float)iy / (float)(H - 1) : -1.f;
+      for (int dx = 0; dx < KS; ++dx) {
+        const int ix = x * S + dx - P;
+        if (ix < 0 || ix >= W) continue;
+        const float cxv = (W > 1) ? -1.f + 2.f * (float)ix / (float)(W - 1) : -1.f;
+        s += w[(((size_t)co * 17 + 15) * KS + dy) * KS + dx] * cxv + w[(((size_t)co * 17 + 16) * KS + dy) * KS + dx] * cyv;
+      }
+    }
+    tab[i] = s;
+  }
+}
+
+int rtc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
+  RtcState* st = rtc_state(p);
+  if (!st || !st->ok) return 0;
+  const IodineShape& s = p->s;
+  const int Cr = p->Cr, f16 = s.precision == IODINE_FP16;
+  for (int l = 0; l < s.ref_layers; ++l) {
+    rtc_pack_kernel<<<32, 256, 0, st_>>>(w->ref_w[l], st->w[l], Cr, l == 0 ? 17 : Cr, l == 0 ? 15 : Cr, st->cin[l], s.ref_k,
+                                         f16);
+    IOD_LAUNCH_CHECK(p);
+  }
+  rtc_tab0_kernel<<<128, 256, 0, st_>>>(w->ref_w[0], w->ref_b[0], st->tab0, Cr, s.ref_k, s.ref_stride, s.H, s.W, p->ref_h[1],
+                                        p->ref_w[1]);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+template <int N, int NKS>
+static int rtc_launch_t(Plan* p, const RtcParams& q, cudaStream_t st_) {
+  auto kern = refine_tc_kernel<N, NKS>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    IOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  const int grid = q.tiles < p->num_sms ? q.tiles : p->num_sms;
+  kern<<<grid, RTC_THREADS, rtc_smem_bytes(q.w_bytes, NKS), st_>>>(q);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// global average pool of the last layer (F.adaptive_avg_pool2d, iodine.py:481) from the chunk-planar layout
+__global__ void rtc_pool_kernel(const uint4* __restrict__ in, float* __restrict__ pool, int HWo, int C, int f16) {
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x / 32; k < C / 8; k += blockDim.x / 32) {
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x % 32; i < HWo; i += 32) {
+      const uint4 v = __ldg(in + ((size_t)n * (C / 8) + k) * HWo + i);
+      const float2 a = unpack_h2(v.x, f16), b = unpack_h2(v.y, f16), c = unpack_h2(v.z, f16), d = unpack_h2(v.w, f16);
+      s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y; s[6] += d.x; s[7] += d.y;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = warp_sum(s[e]);
+    if (threadIdx.x % 32 == 0)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pool[(size_t)n * C + k * 8 + e] = s[e] / (float)HWo;
+  }
+}
+
+// All refine conv layers on the tensor cores: enc16 (assemble16, mixture.cu) -> ... -> pool[BK][Cr]
+int rtc_launch_refine_convs(Plan* p, cudaStream_t st_) {
+  RtcState* st = rtc_state(p);
+  const IodineShape& s = p->s;
+  const int Cr = p->Cr;
+  const void* cur = p->enc16;
+  for (int l = 0; l < s.ref_layers; ++l) {
+    RtcParams q;
+    q.in = reinterpret_cast<const uint4*>(cur);
+    q.out = reinterpret_cast<uint4*>(p->r16[l & 1]);
+    q.wimg = st->w[l];
+    q.w_bytes = st->w_bytes[l];
+    q.bias = p->ref_b[l];
+    q.tab = l == 0 ? st->tab0 : nullptr;
+    q.Hin = p->ref_h[l]; q.Win = p->ref_w[l]; q.Hout = p->ref_h[l + 1]; q.Wout = p->ref_w[l + 1];
+    q.S = s.ref_stride; q.pad = s.ref_k / 2; q.KS = s.ref_k;
+    q.cin_planes = st->cin[l] / 8;
+    q.total = p->BK * q.Hout * q.Wout;
+    q.tiles = (q.total + 127) / 128;
+    q.f16 = s.precision == IODINE_FP16;
+    const uint32_t fmt = q.f16 ? 0u : 1u;
+    q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cr >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int nks = st->cin[l] / 16;
+    int rc = 1;
+    set_error("refine_tc: unsupported ref_chan=%d / K-steps %d", Cr, nks);
+#define RTC_CASE(n, k) if (Cr == n && nks == k) rc = rtc_launch_t<n, k>(p, q, st_);
+    RTC_CASE(64, 1) RTC_CASE(64, 4) RTC_CASE(32, 1) RTC_CASE(32, 2) RTC_CASE(16, 1)
+#undef RTC_CASE
+    if (rc) return 1;
+    cur = p->r16[l & 1];
+  }
+  const int HWo = p->ref_h[s.ref_layers] * p->ref_w[s.ref_layers];
+  rtc_pool_kernel<<<p->BK, 256, 0, st_>>>(reinterpret_cast<const uint4*>(cur), p->pool, HWo, Cr,
+                                          s.precision == IODINE_FP16);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+}  // namespace iod

@@ -56,7 +56,7 @@ def test_decoder_buffers_against_fp32_path(name, over, B, prec):
         d = {'terms': terms.clone(), 'mu': mu.clone(), 'lv': lv.clone()}
         for i in range(arch.DEC.CONV_LAYERS):
             d['act%d' % i] = eng.debug_read('act%d' % i).clone()
-        for nm in ('out4', 'seed4', 'G', 'dz'):
+        for nm in ('out4', 'seed4', 'G', 'dz', 'pool'):
             d[nm] = eng.debug_read(nm).clone()
         outs.append(d)
     ref, got = outs
@@ -70,6 +70,7 @@ def test_decoder_buffers_against_fp32_path(name, over, B, prec):
     assert errs['out4'] < u * (n + 2), errs
     assert errs['seed4'] < 12 * u, errs              # gradient seeds amplify by 1/sigma^2
     assert errs['G'] < 12 * u and errs['dz'] < 12 * u, errs
+    assert errs['pool'] < 12 * u, errs             # tcgen05 refinement encoder (refine_tc.cu) vs FFMA
     assert errs['terms'] < 1e-3, errs
 
 
