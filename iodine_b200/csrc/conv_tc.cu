@@ -50,6 +50,8 @@ constexpr int TC_ISSUERS = 2;
 __host__ __device__ constexpr int tc_epi_warps(int N) { return N >= 32 ? 8 : 4; }
 __host__ __device__ constexpr int tc_threads(int N) { return 32 * (1 + TC_ISSUERS) + 32 * tc_epi_warps(N); }
 constexpr int TC_ACC_STAGES = 4;
+constexpr int TC_RS_UNIT = 5;        // input rows per issue unit of the row-streaming variant (<= 16, < ring rows)
+constexpr int TC_RS_SLOTS = 8;       // accumulator slots of the row-streaming variant (one per output row in flight)
 
 enum TcEpi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_OUT4 = 2 };
 
@@ -74,6 +76,7 @@ struct alignas(64) TcParams {
   int32_t strips;                 // ceil(H / TH)
   int32_t items;                  // BK * strips
   uint32_t idesc;
+  uint32_t idesc_n[8];            // row-streaming: instruction descriptor for c accumulator blocks (N = c * Cout)
   uint32_t w_bytes;               // weight image bytes (multiple of 16)
   uint32_t box_bytes;             // bytes of one halo row of one plane ((W + 2 pad) * 16)
   int32_t n_full;                 // full 128-pixel boxes per halo row
@@ -81,6 +84,8 @@ struct alignas(64) TcParams {
   uint32_t plane_stride16;        // ring plane stride, 16-byte units
   uint32_t a_off[16];             // A-descriptor offset of (dx, K-step): dx + 2*ks*plane_stride16 (read as constants)
   const void* wimg;               // packed bf16 weights (global), layout = smem image
+  const uint4* in;                // row-streaming: chunk-planar source activation (1-D bulk row copies)
+  const uint4* zero_row;          // row-streaming: W x 16 zero bytes (rows outside the image)
   const float* bias;              // [N] (EPI_FWD, EPI_OUT4)
   const uint4* actp;              // chunk-planar previous activation (EPI_DGRAD)
   void* out;                      // chunk-planar bf16 (uint4 per position-plane) or fp32 out4
@@ -92,8 +97,8 @@ struct alignas(64) TcParams {
 struct TcSmem {                    // tail of the dynamic shared memory block
   uint64_t full[TC_MAX_RING];
   uint64_t empty[TC_MAX_RING];
-  uint64_t tfull[TC_ACC_STAGES];
-  uint64_t tempty[TC_ACC_STAGES];
+  uint64_t tfull[TC_RS_SLOTS];
+  uint64_t tempty[TC_RS_SLOTS];
   uint64_t wbar;
   uint32_t tmem_base;
 };
@@ -146,6 +151,49 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, const uint32_t (&
   }
 }
 
+// Row-streaming issue (W == 128: a tile is one output row, ring row j is the input row of the strip).
+// Input row j contributes to the KS output rows q = j-(KS-1) .. j through tap rows dy = j-q, and all of
+// them read the SAME A operand (the row, shifted by dx) -- so one tcgen05.mma per (dx, K-step) with
+// N = KS*Cout updates KS accumulators at once: B is the weight blocks [dy=KS-1 | ... | dy=0] stacked along N,
+// D is KS consecutive 64-column accumulator slots (slot = output row mod TC_RS_SLOTS).  M=128,N=192,K=16
+// costs 96 tensor cycles against 3 x 48 for three N=64 instructions that would each re-read A from shared
+// memory (tools/umma_probe.cu): the layer runs at the MMA floor instead of the operand-bandwidth bound.
+//   c0 / c1 : accumulator blocks before / after the slot ring wraps (c0 >= 1), first block = weight block boff
+//   has_new : the LAST block is a fresh accumulator: its first contribution (step e == 0) must overwrite.
+// WRAP: the accumulator blocks straddle the end of the slot ring (second run from slot 0) -- a compile-time
+// flag so that the common case carries no predicated-off instructions; id0/id1/id1n/idn are the instruction
+// descriptors (N = blocks * Cout) loaded once per row, not once per MMA.
+template <int N, int KS, int NKS, int PST16, bool WRAP>
+__device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, uint32_t rb, const uint32_t (&a_off)[16],
+                                             uint32_t w_base16, int c0, int c1, int boff, bool has_new, int n0, int n1,
+                                             uint32_t id_c0, uint32_t id_c1, uint32_t id_n0, uint32_t id_n1, uint32_t id_1) {
+  constexpr uint64_t DESC_HI = (uint64_t)(8u | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+  constexpr uint32_t NB = (uint32_t)(KS * N);                        // rows of one K half of a weight entry
+  const uint32_t wb = (w_base16 + (uint32_t)boff * (uint32_t)N) | (NB << 16);   // LBO = NB (16-byte units)
+  const uint32_t wb1 = wb + (uint32_t)c0 * (uint32_t)N;                          // first block after the wrap
+  // step 0: old blocks accumulate (n0 / n1 of them per run), the new block (last of the last run) overwrites
+  const uint32_t dn = WRAP ? tmem_base + (uint32_t)((c1 - 1) * N) : d0 + (uint32_t)((c0 - 1) * N);
+  const uint32_t wn = WRAP ? wb1 + (uint32_t)((c1 - 1) * N) : wb + (uint32_t)((c0 - 1) * N);
+#pragma unroll
+  for (int dx = 0; dx < KS; ++dx) {
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      const int e = dx * NKS + ks;
+      const uint32_t off = PST16 ? (uint32_t)(dx + 2 * ks * PST16) : a_off[dx * NKS + ks];
+      const uint64_t ad = DESC_HI | (rb + off);
+      const uint32_t eo = (uint32_t)e * 2u * NB;
+      if (e == 0) {
+        if (n0 > 0) tc_mma_bf16(d0, ad, DESC_HI | (wb + eo), id_n0, 1u);
+        if (WRAP && n1 > 0) tc_mma_bf16(tmem_base, ad, DESC_HI | (wb1 + eo), id_n1, 1u);
+        if (has_new) tc_mma_bf16(dn, ad, DESC_HI | (wn + eo), id_1, 0u);
+      } else {
+        tc_mma_bf16(d0, ad, DESC_HI | (wb + eo), id_c0, 1u);
+        if (WRAP) tc_mma_bf16(tmem_base, ad, DESC_HI | (wb1 + eo), id_c1, 1u);
+      }
+    }
+  }
+}
+
 // Walks the (work item, tile) sequence of one CTA; identical in every role.  A tile starts at flat
 // position row*Ps + rem of its item's halo block; all stepping is incremental (an integer division
 // costs the single issuing thread more than an MMA).
@@ -178,13 +226,15 @@ struct TcTileIter {
 };
 
 // PS / PST16: ring pitch and plane stride as compile-time constants (0 = read them from the parameters).
-template <int N, int EPI, int KS, int NKS, int PS, int PST16>
+// RS: row-streaming variant (W == 128, one tile per output row): see tc_issue_row.
+template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS>
 __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NTHREADS = tc_threads(N);
   constexpr int EW = tc_epi_warps(N);
   constexpr int NC = (EW == 8) ? N / 2 : N;            // accumulator columns per epilogue warp
-  constexpr int TMEM_COLS = (TC_ACC_STAGES * N < 32) ? 32 : TC_ACC_STAGES * N;
+  constexpr int ACC = RS ? TC_RS_SLOTS : TC_ACC_STAGES;       // accumulator stages (TMEM)
+  constexpr int TMEM_COLS = (ACC * N < 32) ? 32 : ACC * N;
   const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
   uint8_t* s_w = smem;
   uint8_t* s_a = smem + w_region;
@@ -208,10 +258,10 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; ++i) {
-      mbar_init(smem_u32(&sb->full[i]), 1);
-      mbar_init(smem_u32(&sb->empty[i]), TC_ISSUERS);   // every issuer hands every row back once
+      mbar_init(smem_u32(&sb->full[i]), RS ? 2 : 1);   // row-streaming: two producer warps
+      mbar_init(smem_u32(&sb->empty[i]), RS ? 1 : TC_ISSUERS);   // every issuer hands every row back once
     }
-    for (int i = 0; i < TC_ACC_STAGES; ++i) {
+    for (int i = 0; i < ACC; ++i) {
       mbar_init(smem_u32(&sb->tfull[i]), 1);
       mbar_init(smem_u32(&sb->tempty[i]), EW);     // one arrive per epilogue warp
     }
@@ -229,7 +279,56 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = sb->tmem_base;
 
-  if (warp == 0) {
+  if (RS && (warp == 0 || warp == 2)) {
+    // =============================================================== producers, row-streaming
+    // W == 128: the left/right halo columns of a ring row are always zero padding, so they are never
+    // loaded (the ring is zeroed once) and a halo row is one contiguous 2 KB run per 8-channel plane:
+    // plain 1-D bulk copies, half of the planes per producer warp (a tensor-map copy costs ~110-140 issue
+    // cycles, and 16 of them per row -- 8 planes x (128-pixel box + 2-pixel tail) -- made a single
+    // producer the bound of the layer).  Rows above / below the image are copied from a zero row.
+    if constexpr (RS) {
+      const int pw = warp >> 1;                    // producer 0 / 1
+      if (warp == 0 && lane == 0) {                // weights: one shot, resident for the whole kernel
+        const uint32_t wbar = smem_u32(&sb->wbar);
+        mbar_expect_tx(wbar, p.w_bytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg);
+        for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
+          const uint32_t n = (p.w_bytes - off < 16384u) ? (p.w_bytes - off) : 16384u;
+          bulk_load_1d(smem_u32(s_w + off), src + off, n, wbar);
+        }
+      }
+      const bool prod_leader = elect_one_sync();
+      const int c_lo = (p.nch_in * pw) / 2, c_hi = (p.nch_in * (pw + 1)) / 2;     // this producer's planes
+      const uint32_t row_bytes = (uint32_t)Ps * 16u, run_bytes = (uint32_t)p.W * 16u;
+      const uint32_t a_base = smem_u32(s_a) + (uint32_t)pad * 16u;               // interior starts after the left halo
+      const size_t plane_px = (size_t)p.H * p.W;
+      int slot = 0;
+      uint32_t phase = 0;
+      if (prod_leader) {
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+          const int n = item / p.strips, y0 = (item - n * p.strips) * p.TH;
+          const int nrows = p.TH + 2 * pad;
+          for (int j = 0; j < nrows; ++j) {
+            const uint32_t fb = smem_u32(&sb->full[slot]);
+            mbar_wait(smem_u32(&sb->empty[slot]), phase ^ 1u, 1);
+            mbar_expect_tx(fb, run_bytes * (uint32_t)(c_hi - c_lo));             // (arrives even with no plane)
+            const int y = y0 - pad + j;
+            const bool inside = y >= 0 && y < p.H;
+            const uint4* src = inside ? p.in + ((size_t)n * p.nch_in + c_lo) * plane_px + (size_t)y * p.W : p.zero_row;
+            const size_t sstep = inside ? plane_px : 0;
+            uint32_t dst = a_base + (uint32_t)slot * row_bytes + (uint32_t)c_lo * plane_bytes;
+            for (int c = c_lo; c < c_hi; ++c) {
+              bulk_load_1d(dst, src, run_bytes, fb);
+              src += sstep;
+              dst += plane_bytes;
+            }
+            if (++slot == R) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 0) {
     // =============================================================== TMA producer
     // lane 0 owns the barriers; the copies of one halo row (planes x mirror copies x boxes) are
     // issued by as many lanes in parallel
@@ -245,24 +344,14 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     const uint32_t a_base = smem_u32(s_a);
     const uint32_t row_bytes = (uint32_t)Ps * 16u;
     const int nbox = p.n_full + (p.tail_px ? 1 : 0);
-    // copy i of a halo row = (plane c, mirror copy cp, box k); lanes own copies lane and lane + 32
-    // (planes <= 8, copies <= 2, boxes <= 3).  Mapped once: no divisions in the row loop.
-    uint32_t cp_off[2], cp_c[2], cp_x[2];
-    bool cp_mir[2], cp_on[2], cp_tail[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int i = lane + 32 * j;
-      const int k = i % nbox, cc = i / nbox;
-      const int cp = cc & 1, c = cc >> 1;
-      cp_on[j] = c < p.nch_in;
-      cp_mir[j] = cp != 0;
-      cp_tail[j] = k >= p.n_full;
-      cp_c[j] = (uint32_t)c;
-      cp_x[j] = (uint32_t)(256 * k - 2 * pad);   // 8-byte elements (2 per pixel-plane): box k starts at pixel 128k - pad
-      cp_off[j] = (uint32_t)c * plane_bytes + (uint32_t)(cp * R) * row_bytes + (uint32_t)k * 2048u;
-    }
+    // One elected lane issues every copy of a halo row (planes x boxes, plus the mirror copies) with
+    // uniform-register arithmetic: spreading the copies over lanes serialises them anyway (each UTMALDG is
+    // issued per active lane) and cost ~110 cycles per copy, which made the producer the bound of the layer.
+    const bool prod_leader = elect_one_sync();
     int slot = 0;
     uint32_t phase = 0;
+    long long tp_wait = 0, tp_all0 = clock64();
+    int tp_rows = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int n = item / p.strips, y0 = (item - n * p.strips) * p.TH;
       const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
@@ -270,25 +359,113 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       for (int j = 0; j < nrows; ++j) {
         const uint32_t fb = smem_u32(&sb->full[slot]);
         const bool mirrored = slot < p.m;
-        if (lane == 0) {
+        ++tp_rows;
+        if (prod_leader) {
+          const long long tw0 = clock64();
           mbar_wait(smem_u32(&sb->empty[slot]), phase ^ 1u, 1);
-          if (p.dbg & 4) mbar_arrive(fb);
-          else mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (mirrored ? 2u : 1u));
-        }
-        __syncwarp();
-        if (p.dbg & 4) { if (++slot == R) { slot = 0; phase ^= 1u; } continue; }
-        const int y = y0 - pad + j;
-        const uint32_t dst_row = a_base + (uint32_t)slot * row_bytes;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (cp_on[q] && (mirrored || !cp_mir[q]))
-            tma_load_4d(dst_row + cp_off[q], cp_tail[q] ? &p.maps.tail : &p.maps.full, fb, (int)cp_x[q], y,
-                        (int)cp_c[q], n);
+          tp_wait += clock64() - tw0;
+          if (p.dbg & 4) {
+            mbar_arrive(fb);
+          } else {
+            mbar_expect_tx(fb, p.box_bytes * (uint32_t)p.nch_in * (mirrored ? 2u : 1u));
+            const int y = y0 - pad + j;
+            const uint32_t dst_row = a_base + (uint32_t)slot * row_bytes;
+            const uint32_t mir = (uint32_t)R * row_bytes;
+            for (int c = 0; c < p.nch_in; ++c) {
+              const uint32_t d = dst_row + (uint32_t)c * plane_bytes;
+              for (int k = 0; k < nbox; ++k) {
+                const CUtensorMap* mp = (k >= p.n_full) ? &p.maps.tail : &p.maps.full;
+                const int x8 = 256 * k - 2 * pad;    // 8-byte elements (2 per pixel-plane): box k starts at pixel 128k - pad
+                tma_load_4d(d + (uint32_t)k * 2048u, mp, fb, x8, y, c, n);
+                if (mirrored) tma_load_4d(d + mir + (uint32_t)k * 2048u, mp, fb, x8, y, c, n);
+              }
+            }
+          }
         }
         if (++slot == R) { slot = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
+    if ((p.dbg & 16) && prod_leader && blockIdx.x == 0)
+      printf("conv_tc producer cta 0: rows %d total %lld cycles, waiting for free ring rows %lld\n", tp_rows, clock64() - tp_all0, tp_wait);
+  } else if (RS && warp == 1) {
+    // =============================================================== MMA issuer, row-streaming
+    // One thread: input rows are consumed strictly in order, each exactly once.
+    if constexpr (RS) {
+      if (warp == 1) {
+        const bool leader = elect_one_sync();      // 12-14 MMAs per row: few enough descriptors for ptxas to keep in uniform registers
+        mbar_wait(smem_u32(&sb->wbar), 0, 2);
+        const uint32_t a_base16 = smem_u32(s_a) >> 4;
+        const uint32_t w_base16 = smem_u32(s_w) >> 4;
+        const int TH = p.TH, nrows = TH + 2 * pad;
+        const int my_items = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        int slot = 0; uint32_t rph = 0;            // ring slot / phase of the next input row
+        int qg = 0;                                // output rows (tiles) of all previous items of this CTA
+        long long t_full = 0, t_tempty = 0, t_issue = 0, t_all0 = clock64();   // dbg & 16: where the issuer's time goes
+        for (int k = 0; k < my_items; ++k) {
+          // Rows are handled in units of TC_RS_UNIT: all barrier waits of a unit first, then its MMAs back to
+          // back.  A wait costs 70-150 cycles even when the barrier has long completed, and the tensor pipe's
+          // instruction queue is short, so per-row waits left the pipe idle between rows.
+          for (int j0 = 0; j0 < nrows; j0 += TC_RS_UNIT) {
+            const int ju = (nrows - j0 < TC_RS_UNIT) ? nrows - j0 : TC_RS_UNIT;
+            long long tq0 = clock64();
+            // lanes wait in parallel: lane u on the ring row of unit row u, lane 16+u on the accumulator slot
+            // that row opens (a wait costs 70-150 cycles even when the barrier completed long ago)
+            if (lane < ju) {
+              int sl = slot + lane; uint32_t ph = rph;
+              if (sl >= R) { sl -= R; ph ^= 1u; }
+              mbar_wait(smem_u32(&sb->full[sl]), ph, 3);
+            } else if (lane >= 16 && lane - 16 < ju && j0 + lane - 16 <= TH - 1) {
+              const int qn = qg + j0 + lane - 16;  // output row q = j receives its first contribution: fresh slot
+              mbar_wait(smem_u32(&sb->tempty[qn & (ACC - 1)]), (((uint32_t)qn / ACC) & 1u) ^ 1u, 4);
+            }
+            __syncwarp();
+            long long tq1 = clock64();
+            t_full += tq1 - tq0;
+            long long tq2 = clock64();
+            t_tempty += tq2 - tq1;
+            tc_fence_after();
+            for (int u = 0; u < ju; ++u) {
+              const int j = j0 + u;
+              // output rows of this strip fed by input row j: q in [j-(KS-1), j] clipped to the strip
+              const int qa = (j - (KS - 1) > 0) ? j - (KS - 1) : 0;
+              const int qb = (j < TH - 1) ? j : TH - 1;
+              const bool has_new = j <= TH - 1;    // row q = j: overwrite on its first step
+              const int cnt = qb - qa + 1;                       // accumulator blocks written by this row
+              const int sa = (qg + qa) & (ACC - 1);              // slot of the first one
+              const int c0 = (cnt < ACC - sa) ? cnt : ACC - sa;  // blocks before the slot ring wraps
+              const int c1 = cnt - c0;
+              const int boff = qa - (j - (KS - 1));              // first weight block (block b <-> dy = KS-1-b)
+              const uint32_t rb = __shfl_sync(0xffffffffu, (a_base16 + (uint32_t)(slot * Ps)) | (plane_stride16 << 16), 0);
+              const uint32_t wb_t = __shfl_sync(0xffffffffu, w_base16, 0);
+              const uint32_t d0 = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(sa * N), 0);
+              // blocks that already hold partial sums (step 0 accumulates into them) per run
+              const int n0 = has_new ? (c1 ? c0 : c0 - 1) : c0;
+              const int n1 = has_new ? (c1 ? c1 - 1 : 0) : c1;
+              const uint32_t id_c0 = p.idesc_n[c0], id_c1 = p.idesc_n[c1], id_n0 = p.idesc_n[n0], id_n1 = p.idesc_n[n1],
+                             id_1 = p.idesc_n[1];
+              if (leader) {
+                if (c1 > 0)
+                  tc_issue_row<N, KS, NKS, PST16, true>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
+                                                        id_c1, id_n0, id_n1, id_1);
+                else
+                  tc_issue_row<N, KS, NKS, PST16, false>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
+                                                         id_c1, id_n0, id_n1, id_1);
+                if (j >= KS - 1) tc_commit(smem_u32(&sb->tfull[(qg + j - (KS - 1)) & (ACC - 1)]));   // row complete
+                tc_commit(smem_u32(&sb->empty[slot]));                                             // ring row consumed
+              }
+              __syncwarp();
+              if (++slot == R) { slot = 0; rph ^= 1u; }
+            }
+            t_issue += clock64() - tq2;
+          }
+          qg += TH;
+        }
+        if ((p.dbg & 16) && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+          printf("conv_tc rs issuer cta %d: rows %d total %lld cycles: full-wait %lld tempty-wait %lld issue %lld\n", (int)blockIdx.x,
+                 my_items * nrows, clock64() - t_all0, t_full, t_tempty, t_issue);
+      }
+    }
   } else if (warp <= TC_ISSUERS) {
     // =============================================================== MMA issuers
     // All lanes walk the tile sequence (so the per-tile bases are warp-uniform values); one elected
@@ -486,7 +663,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
 #pragma unroll
         for (int k = 0; k < NAV; ++k) av[k] = av_next[k];
       }
-      if (++stage == TC_ACC_STAGES) { stage = 0; sph ^= 1u; }
+      if (++stage == ACC) { stage = 0; sph ^= 1u; }
     }
   }
 
@@ -519,6 +696,13 @@ struct TcState {
   float* ptab_c = nullptr;                    // chunk-planar fp32 copy of ptab
   int n_ent_cc = 0, n_ent_in4 = 0;
   TcGeom g_cc, g_out, g_in4;
+  // row-streaming variant (W == 128): weight images with the KS tap rows stacked along N, own geometry
+  bool rs = false;
+  uint16_t* w_fwd_rs[IODINE_MAX_LAYERS];
+  uint16_t* w_bwd_rs[IODINE_MAX_LAYERS];
+  uint16_t* w_out_rs = nullptr;
+  void* zero_row = nullptr;              // W x 16 zero bytes
+  TcGeom g_cc_rs, g_out_rs;
   bool attr_done = false;
 };
 
@@ -567,7 +751,7 @@ static int make_map(TcMaps* maps, void* base, int W, int H, int planes, int BK, 
 static int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // geometry for (input planes, N, entries, max extra reach of an entry's second K half)
-static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo_pos, TcGeom* g) {
+static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo_pos, TcGeom* g, bool rs = false) {
   const IodineShape& s = p->s;
   const int pad = s.dec_k / 2;
   g->Ps = round_up(s.W + 2 * pad, 8);
@@ -575,6 +759,7 @@ static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo
   g->w_bytes = (uint32_t)n_ent * 2u * (uint32_t)N * 16u;
   g->box_bytes = (uint32_t)(s.W + 2 * pad) * 16u;
   g->m = (127 + 2 * pad + max_lbo_pos + g->Ps - 1) / g->Ps;   // rows mirrored behind the ring end
+  if (rs) g->m = 0;                                            // row-streaming tiles never leave their ring row
   const size_t row_bytes = (size_t)nch_in * g->Ps * 16;
   const size_t budget = (size_t)227 * 1024 - round_up((int)g->w_bytes, 1024) - 1024 - sizeof(TcSmem);
   int rows = (int)(budget / row_bytes);
@@ -619,6 +804,19 @@ int tc_alloc(Plan* p) {
   IOD_REQUIRE(tc_geometry(p, C / 8, C, st->n_ent_cc, 0, &st->g_cc), "tc geometry (C->C) failed");
   IOD_REQUIRE(tc_geometry(p, C / 8, 16, st->n_ent_cc, 0, &st->g_out), "tc geometry (C->4) failed");
   IOD_REQUIRE(tc_geometry(p, 1, C, st->n_ent_in4, Ps, &st->g_in4), "tc geometry (4->C) failed");
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { st->w_fwd_rs[l] = nullptr; st->w_bwd_rs[l] = nullptr; }
+  st->rs = s.W == 128 && s.dec_k == 3 && !getenv("IODINE_TC_NO_RS") &&
+           tc_geometry(p, C / 8, C, st->n_ent_cc, 0, &st->g_cc_rs, true) &&
+           tc_geometry(p, C / 8, 16, st->n_ent_cc, 0, &st->g_out_rs, true);
+  if (st->rs) {
+    for (int l = 1; l < s.dec_layers; ++l) {
+      IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd_rs[l], st->g_cc_rs.w_bytes));
+      IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_bwd_rs[l], st->g_cc_rs.w_bytes));
+    }
+    IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_out_rs, st->g_out_rs.w_bytes));
+    IOD_CHECK_CUDA(cudaMalloc(&st->zero_row, (size_t)s.W * 16));
+    IOD_CHECK_CUDA(cudaMemset(st->zero_row, 0, (size_t)s.W * 16));
+  }
   for (int l = 1; l < s.dec_layers; ++l) {
     IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd[l], st->g_cc.w_bytes));
     IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_bwd[l], st->g_cc.w_bytes));
@@ -632,7 +830,11 @@ int tc_alloc(Plan* p) {
 void tc_free(Plan* p) {
   TcState* st = tc_state(p);
   if (!st) return;
-  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { cudaFree(st->w_fwd[l]); cudaFree(st->w_bwd[l]); }
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) {
+    cudaFree(st->w_fwd[l]); cudaFree(st->w_bwd[l]); cudaFree(st->w_fwd_rs[l]); cudaFree(st->w_bwd_rs[l]);
+  }
+  cudaFree(st->w_out_rs);
+  cudaFree(st->zero_row);
   cudaFree(st->w_out); cudaFree(st->w_in4); cudaFree(st->ptab_c);
   delete st;
   p->tc = nullptr;
@@ -679,6 +881,21 @@ __global__ void tc_pack_cc_kernel(const float* __restrict__ w, uint16_t* __restr
     if (bwd) bwd[i] = to_h(w[(((size_t)k * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)], f16);
   }
 }
+// Row-streaming image: [entry = dx*(C/16) + ks][k-half][n' = b*N + n][8], block b <-> tap row dy = KS-1-b
+// (the oldest of the KS output rows an input row feeds comes first); fwd/bwd element as above.
+__global__ void tc_pack_rs_kernel(const float* __restrict__ w, uint16_t* __restrict__ fwd,
+                                  uint16_t* __restrict__ bwd, int C, int NO, int N, int KS, int f16) {
+  const int nks = C / 16;
+  const int total = KS * nks * 2 * KS * N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, n = (i / 8) % N, b = (i / (8 * N)) % KS, kc = (i / (8 * N * KS)) % 2,
+              ks = (i / (16 * N * KS)) % nks, dx = i / (16 * N * KS * nks);
+    const int dy = KS - 1 - b;
+    const int k = (2 * ks + kc) * 8 + e;
+    if (fwd) fwd[i] = to_h(n < NO ? w[(((size_t)n * C + k) * KS + dy) * KS + dx] : 0.f, f16);
+    if (bwd) bwd[i] = to_h(w[(((size_t)k * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)], f16);
+  }
+}
 // 4->C data-gradient of decoder.conv [4][C][k][k]; entry = tap pair (2q, 2q+1); the odd tail
 // reuses the previous tap with zero weights in its first half.  B[n=ci][k=o] (o < 4 real).
 __global__ void tc_pack_in4_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int C, int KS, int f16) {
@@ -718,6 +935,14 @@ int tc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
   IOD_LAUNCH_CHECK(p);
   tc_pack_in4_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_in4, C, KS, f16);
   IOD_LAUNCH_CHECK(p);
+  if (st->rs) {
+    for (int l = 1; l < s.dec_layers; ++l) {
+      tc_pack_rs_kernel<<<64, 256, 0, st_>>>(w->dec_w[l], st->w_fwd_rs[l], st->w_bwd_rs[l], C, C, C, KS, f16);
+      IOD_LAUNCH_CHECK(p);
+    }
+    tc_pack_rs_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_out_rs, nullptr, C, 4, 16, KS, f16);
+    IOD_LAUNCH_CHECK(p);
+  }
   tc_ptab_planar_kernel<<<256, 256, 0, st_>>>(p->ptab, st->ptab_c, p->HW, C);   // after pack_ptab (same stream)
   IOD_LAUNCH_CHECK(p);
   return 0;
@@ -740,6 +965,7 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->strips = (s.H + g.TH - 1) / g.TH;
   q->items = p->BK * q->strips;
   q->idesc = make_idesc(N, s.precision == IODINE_FP16);
+  for (int c = 0; c < 8; ++c) q->idesc_n[c] = (c >= 1 && c * N <= 256) ? make_idesc(c * N, s.precision == IODINE_FP16) : 0u;
   q->f16 = s.precision == IODINE_FP16;
   {
     static const int dbg = getenv("IODINE_TC_DEBUG") ? atoi(getenv("IODINE_TC_DEBUG")) : 0;
@@ -760,9 +986,9 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
 }
 
 // dispatch on the compile-time shape <N, EPI, KS, NKS>
-template <int N, int EPI, int KS, int NKS, int PS, int PST16>
+template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS = false>
 static int tc_launch_g(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
-  auto kern = conv_tc_kernel<N, EPI, KS, NKS, PS, PST16>;
+  auto kern = conv_tc_kernel<N, EPI, KS, NKS, PS, PST16, RS>;
   static bool attr_done = false;
   if (!attr_done) {
     IOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -787,6 +1013,25 @@ static int tc_launch_k(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_
   if constexpr (KS == 3 && NKS == 0 && N == 32) { if (ps == 72 && pst == 2520) return tc_launch_g<N, EPI, KS, NKS, 72, 2520>(p, q, smem, st_); }
   if (getenv("IODINE_TC_VERBOSE")) fprintf(stderr, "conv_tc: generic kernel for N=%d EPI=%d KS=%d NKS=%d (Ps=%d, plane stride %d)\n", N, EPI, KS, NKS, ps, pst);
   return tc_launch_g<N, EPI, KS, NKS, 0, 0>(p, q, smem, st_);
+}
+
+// row-streaming variant (W == 128, 3x3): C -> C layers and decoder.conv forward
+template <int EPI>
+static int tc_launch_rs(Plan* p, const TcParams& q, size_t smem, bool out4, cudaStream_t st_) {
+  const int C = p->C, pst = (int)q.plane_stride16;
+  if (!out4) {
+    if (C == 64) return pst == 1224 ? tc_launch_g<64, EPI, 3, 4, 136, 1224, true>(p, q, smem, st_)
+                                    : tc_launch_g<64, EPI, 3, 4, 136, 0, true>(p, q, smem, st_);
+    if (C == 32) return tc_launch_g<32, EPI, 3, 2, 136, 0, true>(p, q, smem, st_);
+    if (C == 16) return tc_launch_g<16, EPI, 3, 1, 136, 0, true>(p, q, smem, st_);
+  } else {
+    if (C == 64) return pst == 1632 ? tc_launch_g<16, EPI_OUT4, 3, 4, 136, 1632, true>(p, q, smem, st_)
+                                    : tc_launch_g<16, EPI_OUT4, 3, 4, 136, 0, true>(p, q, smem, st_);
+    if (C == 32) return tc_launch_g<16, EPI_OUT4, 3, 2, 136, 0, true>(p, q, smem, st_);
+    if (C == 16) return tc_launch_g<16, EPI_OUT4, 3, 1, 136, 0, true>(p, q, smem, st_);
+  }
+  set_error("conv_tc (row-streaming): unsupported C=%d", C);
+  return 1;
 }
 
 // C -> C layers (forward / data-gradient): N = C, NKS = C/16
@@ -842,11 +1087,17 @@ int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* a
   IOD_REQUIRE(map != nullptr, "conv_tc: source buffer has no tensor map");
   TcParams q;
   q.maps = *map;
-  fill_common(p, st->g_cc, p->C / 8, p->C, &q);
-  q.wimg = dgrad ? st->w_bwd[layer] : st->w_fwd[layer];
+  fill_common(p, st->rs ? st->g_cc_rs : st->g_cc, p->C / 8, p->C, &q);
+  q.wimg = st->rs ? (dgrad ? st->w_bwd_rs[layer] : st->w_fwd_rs[layer]) : (dgrad ? st->w_bwd[layer] : st->w_fwd[layer]);
   q.bias = dgrad ? nullptr : p->dec[layer].b;
   q.actp = reinterpret_cast<const uint4*>(act_prev);
   q.out = out;
+  q.in = reinterpret_cast<const uint4*>(in);
+  q.zero_row = reinterpret_cast<const uint4*>(st->zero_row);
+  if (st->rs) {
+    if (dgrad) return tc_launch_rs<EPI_DGRAD>(p, q, st->g_cc_rs.smem, false, st_);
+    return tc_launch_rs<EPI_FWD>(p, q, st->g_cc_rs.smem, false, st_);
+  }
   if (dgrad) return tc_launch_cc<EPI_DGRAD>(p, q, st->g_cc.smem, st_);
   return tc_launch_cc<EPI_FWD>(p, q, st->g_cc.smem, st_);
 }
@@ -857,11 +1108,14 @@ int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st_) {
   IOD_REQUIRE(map != nullptr, "conv_tc: source buffer has no tensor map");
   TcParams q;
   q.maps = *map;
-  fill_common(p, st->g_out, p->C / 8, 16, &q);
-  q.wimg = st->w_out;
+  fill_common(p, st->rs ? st->g_out_rs : st->g_out, p->C / 8, 16, &q);
+  q.wimg = st->rs ? st->w_out_rs : st->w_out;
   q.bias = p->out_b;
   q.actp = nullptr;
   q.out = out4;
+  q.in = reinterpret_cast<const uint4*>(in);
+  q.zero_row = reinterpret_cast<const uint4*>(st->zero_row);
+  if (st->rs) return tc_launch_rs<EPI_OUT4>(p, q, st->g_out_rs.smem, true, st_);
   return tc_launch_o4(p, q, st->g_out.smem, st_);
 }
 

@@ -26,8 +26,11 @@
 
 namespace iod {
 
-constexpr int RTC_STAGES = 6;      // A-operand ring (one tap of one tile per stage)
-constexpr int RTC_LAG = 3;         // cp.async groups a producer thread keeps in flight
+// A-operand ring (one tap of one tile per stage) and the number of cp.async groups a producer thread keeps in
+// flight: the gather is latency-bound, so small stages (layer 0: 4 KB) get a deep ring
+__host__ __device__ constexpr int rtc_stages(int nks) { return nks == 1 ? 16 : nks == 2 ? 12 : 8; }
+__host__ __device__ constexpr int rtc_lag(int nks) { return rtc_stages(nks) - 2; }
+constexpr int RTC_MAX_STAGES = 16;
 constexpr int RTC_ACC = 4;         // TMEM accumulator stages
 constexpr int RTC_THREADS = 128 + 32 + 128;
 
@@ -47,8 +50,8 @@ struct RtcParams {
 };
 
 struct RtcSmem {
-  uint64_t full[RTC_STAGES];
-  uint64_t empty[RTC_STAGES];
+  uint64_t full[RTC_MAX_STAGES];
+  uint64_t empty[RTC_MAX_STAGES];
   uint64_t tfull[RTC_ACC];
   uint64_t tempty[RTC_ACC];
   uint64_t wbar;
@@ -66,6 +69,7 @@ template <int N, int NKS>
 __global__ void __launch_bounds__(RTC_THREADS, 1) refine_tc_kernel(const __grid_constant__ RtcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int TMEM_COLS = (RTC_ACC * N < 32) ? 32 : RTC_ACC * N;
+  constexpr int RTC_STAGES = rtc_stages(NKS), RTC_LAG = rtc_lag(NKS);
   constexpr uint32_t STAGE_BYTES = (uint32_t)(2 * NKS) * 2048u;       // cin_planes x (128 positions x 16 B)
   const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
   uint8_t* s_w = smem;
@@ -253,7 +257,7 @@ struct RtcState {
 static RtcState* rtc_state(Plan* p) { return reinterpret_cast<RtcState*>(p->rtc); }
 
 static size_t rtc_smem_bytes(uint32_t w_bytes, int nks) {
-  return (size_t)((w_bytes + 1023u) & ~1023u) + (size_t)RTC_STAGES * (2 * nks) * 2048 + sizeof(RtcSmem) + 64;
+  return (size_t)((w_bytes + 1023u) & ~1023u) + (size_t)rtc_stages(nks) * (2 * nks) * 2048 + sizeof(RtcSmem) + 64;
 }
 
 // 1 if every refine layer fits the tensor-core kernel (otherwise the FFMA path of conv_f32.cu runs)

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p, long long* cycl
 // commits per tile, accumulator-stage rotation, number of issuing warps.  Operand contents are
 // whatever is in shared memory (timing only).
 // ------------------------------------------------------------------------------------------------
-struct TileParams { int tiles; int commits; int rotate; int issuers; int N; };
+struct TileParams { int tiles; int commits; int rotate; int issuers; int N; int rs; };
 
 __device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -195,7 +195,17 @@ __global__ void __launch_bounds__(128, 1) tile_kernel(TileParams p, long long* c
         rb[dy] = __shfl_sync(0xffffffffu, (a_base16 + (uint32_t)pr * Ps) | (ps16 << 16), 0);
         if (++pr == 5) pr = 0;
       }
-      if (lane == 0) {
+      if (lane == 0 && p.rs) {                     // row-streaming pattern: 12 MMAs (dx, ks) on ONE ring row
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const int e = dx * 4 + ks;
+            mma_f16(tmem_base, HI | (rb[0] + (uint32_t)dx + (uint32_t)(2 * ks) * ps16), HI | (wb + (uint32_t)(e * 2 * N)), idesc, 1u);
+          }
+        for (int c = 0; c < p.commits; ++c)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[(t * 2 + c) & 15])) : "memory");
+      } else if (lane == 0) {
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -225,13 +235,29 @@ __global__ void __launch_bounds__(128, 1) tile_kernel(TileParams p, long long* c
 }
 
 template <int N>
+static void run_rows(long long* d_cyc) {
+  CK(cudaFuncSetAttribute(tile_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  std::vector<long long> cyc(148 * 4);
+  for (int commits = 0; commits <= 2; commits += 2) {
+    TileParams p{1200, commits, 0, 1, N, 1};
+    tile_kernel<N><<<148, 128, 220 * 1024>>>(p, d_cyc);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(cyc.data(), d_cyc, cyc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < 148; ++i) mx = cyc[i * 4] > mx ? cyc[i * 4] : mx;
+    printf("rows  N=%d commits/row=%d : %.1f cycles/MMA (%.0f cycles/row of 12 MMAs)\n", N, commits, (double)mx / (1200.0 * 12),
+           (double)mx / 1200.0);
+  }
+}
+
+template <int N>
 static void run_tiles(long long* d_cyc) {
   CK(cudaFuncSetAttribute(tile_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   std::vector<long long> cyc(148 * 4);
   for (int issuers = 1; issuers <= 4; issuers *= 2)
     for (int rotate = 0; rotate <= 1; ++rotate)
       for (int commits = 0; commits <= 2; ++commits) {
-        TileParams p{400, commits, rotate, issuers, N};
+        TileParams p{400, commits, rotate, issuers, N, 0};
         tile_kernel<N><<<148, 128, 220 * 1024>>>(p, d_cyc);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(cyc.data(), d_cyc, cyc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -250,6 +276,13 @@ int main() {
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 163840 + 32768 + 1024));
   long long* d_cyc; float* d_D;
   CK(cudaMalloc(&d_cyc, 148 * 4 * sizeof(long long)));
+  run_rows<192>(d_cyc);
+  run_rows<128>(d_cyc);
+  run_rows<96>(d_cyc);
+  run_rows<64>(d_cyc);
+  run_rows<48>(d_cyc);
+  run_rows<16>(d_cyc);
+  if (getenv("PROBE_ROWS_ONLY")) return 0;
   run_tiles<64>(d_cyc);
   run_tiles<16>(d_cyc);
   if (getenv("PROBE_TILES_ONLY")) return 0;
