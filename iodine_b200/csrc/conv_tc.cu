@@ -586,24 +586,35 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
                            : make_uint4(0u, 0u, 0u, 0u);
     };
 
-    TcTileIter cur;
-    cur.ps = PS;
-    cur.init(p);
-    uint4 av[NAV], av_next[NAV];
-    long long pix = cur.valid(p) ? pix_of(cur) : -1;
-    if constexpr (EPI == EPI_DGRAD) {
-      if (cur.valid(p)) load_prev(cur, pix, av);
-    }
+    // Tiles are walked by ONE iterator that runs three tiles ahead of the tile being written: the loads of
+    // the previous activation (data-gradient epilogue) need ~3 tiles of lead under load -- with one tile of
+    // lead the 16 KB per tile in flight per SM capped that stream below 1 TB/s and the epilogue, not the
+    // tensor pipe, bounded the layer.
+    TcTileIter far;
+    far.ps = PS;
+    far.init(p);
+    const int my_items_e = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int ntotal = (my_items_e > 0 ? my_items_e : 0) * p.NT;
+    long long pix = -1, pix1 = -1, pix2 = -1, pix3 = -1;
+    int cn = 0, cn1 = 0, cn2 = 0, cn3 = 0;
+    uint4 av[NAV], av1[NAV], av2[NAV], av3[NAV];
+    auto fetch = [&](long long& pix_o, int& n_o, uint4* av_o) {
+      if (far.valid(p)) {
+        pix_o = pix_of(far);
+        n_o = far.n;
+        if constexpr (EPI == EPI_DGRAD) load_prev(far, pix_o, av_o);
+        far.next(p);
+      } else {
+        pix_o = -1;
+      }
+    };
+    fetch(pix, cn, av);
+    fetch(pix1, cn1, av1);
+    fetch(pix2, cn2, av2);
     int stage = 0;
     uint32_t sph = 0;
-    while (cur.valid(p)) {
-      // the next tile's previous-activation loads fly while this tile is processed
-      TcTileIter nxt = cur;
-      nxt.next(p);
-      const long long pix_next = nxt.valid(p) ? pix_of(nxt) : -1;
-      if constexpr (EPI == EPI_DGRAD) {
-        if (nxt.valid(p)) load_prev(nxt, pix_next, av_next);
-      }
+    for (int tno = 0; tno < ntotal; ++tno) {
+      fetch(pix3, cn3, av3);
 
       mbar_wait(smem_u32(&sb->tfull[stage]), sph, 5);
       tc_fence_after();
@@ -628,7 +639,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
           o.y = __uint_as_float(acc[1]) + bias_r[1];
           o.z = __uint_as_float(acc[2]) + bias_r[2];
           o.w = __uint_as_float(acc[3]) + bias_r[3];
-          reinterpret_cast<float4*>(p.out)[(size_t)cur.n * plane_sz + (size_t)pix] = o;
+          reinterpret_cast<float4*>(p.out)[(size_t)cn * plane_sz + (size_t)pix] = o;
         } else {
           uint4* outp = reinterpret_cast<uint4*>(p.out);
 #pragma unroll
@@ -653,15 +664,15 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
             o.y = pack_h2(v[2], v[3], F16);
             o.z = pack_h2(v[4], v[5], F16);
             o.w = pack_h2(v[6], v[7], F16);
-            outp[((size_t)cur.n * (N / 8) + k0 + k) * plane_sz + (size_t)pix] = o;
+            outp[((size_t)cn * (N / 8) + k0 + k) * plane_sz + (size_t)pix] = o;
           }
         }
       }
-      cur = nxt;
-      pix = pix_next;
+      pix = pix1; pix1 = pix2; pix2 = pix3;
+      cn = cn1; cn1 = cn2; cn2 = cn3;
       if constexpr (EPI == EPI_DGRAD) {
 #pragma unroll
-        for (int k = 0; k < NAV; ++k) av[k] = av_next[k];
+        for (int k = 0; k < NAV; ++k) { av[k] = av1[k]; av1[k] = av2[k]; av2[k] = av3[k]; }
       }
       if (++stage == ACC) { stage = 0; sph ^= 1u; }
     }
