@@ -66,7 +66,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '25'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -99,6 +99,15 @@ class ClockSampler:
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def profiled_traffic(precision):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get(precision)
+    return None
 
 
 def measured_peaks():
@@ -246,6 +255,31 @@ def run_native(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
 
+    # side measurements (N=1 only): the same step in the other precision modes, 2 timed steps each
+    variants = {}
+    if world == 1 and not args.no_variants and not args.profile_mode:
+        for prec in ('fp32', 'bf16', 'fp16'):
+            if prec == args.precision:
+                continue
+            torch.manual_seed(0)
+            m2 = IODINE(arch, precision=prec).to(dev)
+            m2.max_images_per_call = B
+            e2 = m2.state_for_debug(B)
+            for _ in range(3):
+                e2.encode(x, eps)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(2):
+                e2.encode(x, eps)
+            a1.record()
+            torch.cuda.synchronize()
+            variants[prec] = {'value': B * K * T * 2 / (a0.elapsed_time(a1) * 1e-3), 'unit': UNIT,
+                              'ms_per_step': a0.elapsed_time(a1) / 2}
+            e2.close()
+            del m2, e2
+            torch.cuda.empty_cache()
+
     units_per_step = world * B * K * T
     value = units_per_step * args.steps / (dev_ms * 1e-3)
     e2e_value = units_per_step * host_steps / e2e_s
@@ -279,11 +313,15 @@ def run_native(args):
                     'conv_cc_kernel FFMA' if args.precision == 'fp32' else 'conv_tc tcgen05'),
                 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': (achieved_tf / peak_tf) if achieved_tf else None,
-                'traffic': None, 'peak_source': peak_src,
+                'traffic': profiled_traffic(args.precision), 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': B * K * S * S * arch.DEC.CONV_CHAN * (4 if args.precision == 'fp32' else 2) * 2.5,
+                'hbm_peak_gbs': peak_gbs,
                 'launches_timed': int(conv_n), 'avg_launch_ms': conv_ms / conv_n if conv_n else None,
                 'flop_per_launch': per_launch_flop,
                 'share_of_step': conv_ms / dev_ms if dev_ms else None},
         }
+        if world == 1 and not args.no_variants and not args.profile_mode:
+            line['variants'] = variants
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, med = oracle_port_steps_per_s(arch, args.cpu_batch, 2, 1, threads=cores)
@@ -302,7 +340,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='images per GPU')
-    ap.add_argument('--precision', default=os.environ.get('IODINE_PRECISION', 'fp32'))
+    ap.add_argument('--precision', default=os.environ.get('IODINE_PRECISION', 'fp16'),
+                    help='fp16 (default: tcgen05, meets the 1e-3 parity bar), bf16 (tcgen05), fp32 (exact FFMA path)')
+    ap.add_argument('--no-variants', action='store_true', help='skip the short fp32 / bf16 side measurements')
     ap.add_argument('--cpu-batch', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-mode', action='store_true',
@@ -312,6 +352,7 @@ def main():
         args.warmup = max(args.warmup, 3)
     if args.profile_mode:
         args.no_cpu_baseline = True
+        args.no_variants = True
     if args.impl == 'reference':
         return run_reference_arm(args)
     world = int(os.environ.get('WORLD_SIZE', '1'))
