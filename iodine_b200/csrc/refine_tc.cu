@@ -26,20 +26,22 @@
 
 namespace iod {
 
-// A-operand ring (one tap of one tile per stage) and the number of cp.async groups a producer thread keeps in
-// flight: the gather is latency-bound, so small stages (layer 0: 4 KB) get a deep ring
-__host__ __device__ constexpr int rtc_stages(int nks) { return nks == 1 ? 16 : nks == 2 ? 12 : 8; }
-__host__ __device__ constexpr int rtc_lag(int nks) { return rtc_stages(nks) - 2; }
+// A-operand ring: a stage holds TPS consecutive taps of one tile (all 9 for the 16-channel first layer, so a
+// tile is ONE producer->issuer handshake: a barrier wait costs ~100 cycles even when it succeeds at once),
+// ST stages; a producer thread keeps ST-2 cp.async groups in flight.
 constexpr int RTC_MAX_STAGES = 16;
 constexpr int RTC_ACC = 4;         // TMEM accumulator stages
-constexpr int RTC_THREADS = 128 + 32 + 128;
+// 4 producer warps, 1 issuer warp, then 4 or 8 epilogue warps (two per TMEM lane quadrant, each taking half of the
+// accumulator columns, when N >= 32)
+__host__ __device__ constexpr int rtc_epi_warps(int N) { return N >= 32 ? 8 : 4; }
+__host__ __device__ constexpr int rtc_threads(int N) { return 128 + 32 + 32 * rtc_epi_warps(N); }
 
 struct RtcParams {
   const uint4* in;       // chunk-planar [n][cin_planes][Hin][Win] (uint4 = 8 channels of one pixel)
   uint4* out;            // chunk-planar [n][N/8][Hout][Wout]
   const void* wimg;      // [tap][ks][k-half][n][8] 16-bit
   const float* bias;     // [N]                     (tab == nullptr)
-  const float* tab;      // [Hout*Wout][N] bias + coordinate-channel convolution (layer 0) or nullptr
+  const float* tab;      // [N/8][Hout*Wout][8] bias + coordinate-channel convolution (layer 0) or nullptr
   uint32_t w_bytes;
   int32_t Hin, Win, Hout, Wout, S, pad, KS;
   int32_t cin_planes;
@@ -65,12 +67,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int N, int NKS>
-__global__ void __launch_bounds__(RTC_THREADS, 1) refine_tc_kernel(const __grid_constant__ RtcParams p) {
+template <int N, int NKS, int TPS, int ST>
+__global__ void __launch_bounds__(rtc_threads(N), 1) refine_tc_kernel(const __grid_constant__ RtcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int TMEM_COLS = (RTC_ACC * N < 32) ? 32 : RTC_ACC * N;
-  constexpr int RTC_STAGES = rtc_stages(NKS), RTC_LAG = rtc_lag(NKS);
-  constexpr uint32_t STAGE_BYTES = (uint32_t)(2 * NKS) * 2048u;       // cin_planes x (128 positions x 16 B)
+  constexpr int RTC_STAGES = ST, RTC_LAG = ST - 2;
+  static_assert(ST >= 3 && ST <= RTC_MAX_STAGES, "stage count");
+  constexpr uint32_t TAP_BYTES = (uint32_t)(2 * NKS) * 2048u;         // cin_planes x (128 positions x 16 B)
+  constexpr uint32_t STAGE_BYTES = (uint32_t)TPS * TAP_BYTES;
   const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
   uint8_t* s_w = smem;
   uint8_t* s_a = smem + w_region;
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) refine_tc_kernel(const __grid_
     }
     for (int i = 0; i < RTC_ACC; ++i) {
       mbar_init(smem_u32(&sb->tfull[i]), 1);
-      mbar_init(smem_u32(&sb->tempty[i]), 4);      // one arrive per epilogue warp
+      mbar_init(smem_u32(&sb->tempty[i]), rtc_epi_warps(N));   // one arrive per epilogue warp
     }
     mbar_init(smem_u32(&sb->wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -118,15 +122,19 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) refine_tc_kernel(const __grid_
       const int y = r / p.Wout, x = r - y * p.Wout;
       const uint4* in_n = p.in + (size_t)n * (2 * NKS) * plane_in;
       int dy = 0, dx = 0;
-      for (int tap = 0; tap < ntaps; ++tap) {
+      for (int tap0 = 0; tap0 < ntaps; tap0 += TPS) {
         mbar_wait(smem_u32(&sb->empty[stage]), phase ^ 1u, 11);
-        const int iy = y * p.S + dy - p.pad, ix = x * p.S + dx - p.pad;
-        const bool inb = valid && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-        const uint4* src = inb ? in_n + (size_t)iy * p.Win + ix : p.in;
-        const uint32_t dst = a_base + (uint32_t)stage * STAGE_BYTES;
-        const uint32_t nbytes = inb ? 16u : 0u;    // 0: cp.async writes 16 zero bytes (the zero padding)
 #pragma unroll
-        for (int g = 0; g < 2 * NKS; ++g) cp_async16(dst + (uint32_t)g * 2048u, src + (size_t)g * plane_in, nbytes);
+        for (int t = 0; t < TPS; ++t) {
+          const int iy = y * p.S + dy - p.pad, ix = x * p.S + dx - p.pad;
+          const bool inb = valid && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+          const uint4* src = inb ? in_n + (size_t)iy * p.Win + ix : p.in;
+          const uint32_t dst = a_base + (uint32_t)stage * STAGE_BYTES + (uint32_t)t * TAP_BYTES;
+          const uint32_t nbytes = inb ? 16u : 0u;  // 0: cp.async writes 16 zero bytes (the zero padding)
+#pragma unroll
+          for (int g = 0; g < 2 * NKS; ++g) cp_async16(dst + (uint32_t)g * 2048u, src + (size_t)g * plane_in, nbytes);
+          if (++dx == p.KS) { dx = 0; ++dy; }
+        }
         cp_async_commit();
         ++issued;
         if (issued > RTC_LAG) {                    // the group committed RTC_LAG groups ago has landed
@@ -136,7 +144,6 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) refine_tc_kernel(const __grid_
           if (++arrived_stage == RTC_STAGES) arrived_stage = 0;
         }
         if (++stage == RTC_STAGES) { stage = 0; phase ^= 1u; }
-        if (++dx == p.KS) { dx = 0; ++dy; }
       }
     }
     // drain
@@ -169,15 +176,18 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) refine_tc_kernel(const __grid_
         mbar_wait(smem_u32(&sb->tempty[acc]), aph ^ 1u, 13);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
-        for (int tap = 0; tap < ntaps; ++tap) {
+        for (int tap0 = 0; tap0 < ntaps; tap0 += TPS) {
           mbar_wait(smem_u32(&sb->full[stage]), phase, 14);
           tc_fence_after();
-          const uint32_t a0 = a16 + (uint32_t)stage * (STAGE_BYTES >> 4);
-          const uint32_t b0 = w16 + (uint32_t)(tap * NKS) * (uint32_t)(2 * N);
 #pragma unroll
-          for (int ks = 0; ks < NKS; ++ks)
-            tc_mma_bf16(d_tmem, DESC_HI | (a0 + (uint32_t)ks * 256u), DESC_HI | (b0 + (uint32_t)(ks * 2 * N)), p.idesc,
-                        (tap | ks) ? 1u : 0u);
+          for (int t = 0; t < TPS; ++t) {
+            const uint32_t a0 = a16 + (uint32_t)stage * (STAGE_BYTES >> 4) + (uint32_t)t * (TAP_BYTES >> 4);
+            const uint32_t b0 = w16 + (uint32_t)((tap0 + t) * NKS) * (uint32_t)(2 * N);
+#pragma unroll
+            for (int ks = 0; ks < NKS; ++ks)
+              tc_mma_bf16(d_tmem, DESC_HI | (a0 + (uint32_t)ks * 256u), DESC_HI | (b0 + (uint32_t)(ks * 2 * N)), p.idesc,
+                          ((tap0 + t) | ks) ? 1u : 0u);
+          }
           tc_commit(smem_u32(&sb->empty[stage]));
           if (++stage == RTC_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -188,49 +198,68 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) refine_tc_kernel(const __grid_
     __syncwarp();
   } else {
     // =============================================================== epilogue warps
+    constexpr int EW = rtc_epi_warps(N);
+    constexpr int NC = (EW == 8) ? N / 2 : N;      // accumulator columns per warp
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int col0 = (EW == 8) ? ((warp - 5) / 4) * NC : 0;
     const int F16 = p.f16;
     int acc = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    // bias / table values are requested one tile AHEAD: issued after the accumulator wait (ptxas does not move
+    // loads across the TMEM read) they cost one exposed L2 latency per 8 channels and bounded the layer
+    float4 tb[NC / 4], tb_next[NC / 4];
+    auto locate = [&](int tile, bool& valid, int& n, int& r) {
       const int pos = tile * 128 + quad * 32 + lane;
-      const bool valid = pos < p.total;
-      const int n = valid ? pos / HWo : 0;
-      const int r = valid ? pos - n * HWo : 0;
+      valid = tile < p.tiles && pos < p.total;
+      n = valid ? pos / HWo : 0;
+      r = valid ? pos - n * HWo : 0;
+    };
+    auto load_bias = [&](int r, float4* dst) {
+#pragma unroll
+      for (int k = 0; k < NC / 8; ++k) {
+        const int c = col0 + k * 8;
+        const float4* bp = reinterpret_cast<const float4*>(p.tab ? p.tab + ((size_t)(c >> 3) * HWo + r) * 8 : p.bias + c);
+        dst[2 * k] = __ldg(bp);
+        dst[2 * k + 1] = __ldg(bp + 1);
+      }
+    };
+    bool valid; int n, r;
+    locate(blockIdx.x, valid, n, r);
+    load_bias(r, tb);
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      bool valid_n; int n_n, r_n;
+      locate(tile + gridDim.x, valid_n, n_n, r_n);
+      load_bias(r_n, tb_next);
       mbar_wait(smem_u32(&sb->tfull[acc]), aph, 15);
       tc_fence_after();
+      uint32_t v[NC];
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * N + col0) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        constexpr int NC = (N < 32) ? N : 32;
-        uint32_t v[NC];
-        const uint32_t taddr = tmem_base + (uint32_t)(acc * N + c0) + ((uint32_t)(quad * 32) << 16);
+      for (int q = 0; q < NC / 16; ++q) IOD_TMEM_LD16((v + q * 16), taddr + q * 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[acc]));      // accumulator stage is free again
+      if (valid) {
 #pragma unroll
-        for (int q = 0; q < NC / 16; ++q) IOD_TMEM_LD16((v + q * 16), taddr + q * 16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= N) {                         // last read of this accumulator stage
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[acc]));
-        }
-        if (valid) {
+        for (int k = 0; k < NC / 8; ++k) {
+          float f[8];
+          const int c = col0 + k * 8;
+          const float4 b0 = tb[2 * k], b1 = tb[2 * k + 1];
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int k = 0; k < NC / 8; ++k) {
-            float f[8];
-            const int c = c0 + k * 8;
-            const float4* bp = reinterpret_cast<const float4*>(p.tab ? p.tab + (size_t)r * N + c : p.bias + c);
-            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = elu_fast(__uint_as_float(v[k * 8 + e]) + bb[e]);
-            uint4 o;
-            o.x = pack_h2(f[0], f[1], F16);
-            o.y = pack_h2(f[2], f[3], F16);
-            o.z = pack_h2(f[4], f[5], F16);
-            o.w = pack_h2(f[6], f[7], F16);
-            p.out[((size_t)n * (N / 8) + (c >> 3)) * HWo + r] = o;
-          }
+          for (int e = 0; e < 8; ++e) f[e] = elu_fast(__uint_as_float(v[k * 8 + e]) + bb[e]);
+          uint4 o;
+          o.x = pack_h2(f[0], f[1], F16);
+          o.y = pack_h2(f[2], f[3], F16);
+          o.z = pack_h2(f[4], f[5], F16);
+          o.w = pack_h2(f[6], f[7], F16);
+          p.out[((size_t)n * (N / 8) + (c >> 3)) * HWo + r] = o;
         }
       }
+      valid = valid_n; n = n_n; r = r_n;
+#pragma unroll
+      for (int k = 0; k < NC / 4; ++k) tb[k] = tb_next[k];
       if (++acc == RTC_ACC) { acc = 0; aph ^= 1u; }
     }
   }
@@ -256,8 +285,18 @@ struct RtcState {
 
 static RtcState* rtc_state(Plan* p) { return reinterpret_cast<RtcState*>(p->rtc); }
 
-static size_t rtc_smem_bytes(uint32_t w_bytes, int nks) {
-  return (size_t)((w_bytes + 1023u) & ~1023u) + (size_t)rtc_stages(nks) * (2 * nks) * 2048 + sizeof(RtcSmem) + 64;
+// (taps per stage, stages) of the instantiation that serves (Cout, kernel size, K-steps per tap); 0 = none
+static bool rtc_cfg(int Cr, int KS, int nks, int* tps, int* st) {
+  if (KS == 3 && nks == 1) { *tps = 9; *st = 4; return true; }
+  if (KS == 3 && nks == 2) { *tps = 3; *st = 6; return Cr == 32; }
+  if (KS == 3 && nks == 4) { *tps = 1; *st = 8; return Cr == 64; }
+  if (KS == 5 && nks == 1) { *tps = 5; *st = 6; return true; }
+  if (KS == 5 && nks == 2) { *tps = 1; *st = 12; return Cr == 32; }
+  return false;
+}
+
+static size_t rtc_smem_bytes(uint32_t w_bytes, int nks, int tps, int st) {
+  return (size_t)((w_bytes + 1023u) & ~1023u) + (size_t)st * tps * (2 * nks) * 2048 + sizeof(RtcSmem) + 64;
 }
 
 // 1 if every refine layer fits the tensor-core kernel (otherwise the FFMA path of conv_f32.cu runs)
@@ -268,7 +307,9 @@ int rtc_supported(const Plan* p) {
   for (int l = 0; l < s.ref_layers; ++l) {
     const int cin = l == 0 ? 16 : Cr;
     const uint32_t wb = (uint32_t)kk * (cin / 16) * 2u * (uint32_t)Cr * 16u;
-    if (rtc_smem_bytes(wb, cin / 16) > (size_t)227 * 1024) return 0;
+    int tps = 0, st = 0;
+    if (!rtc_cfg(Cr, s.ref_k, cin / 16, &tps, &st)) return 0;
+    if (rtc_smem_bytes(wb, cin / 16, tps, st) > (size_t)227 * 1024) return 0;
   }
   return 1;
 }
@@ -318,7 +359,7 @@ __global__ void rtc_pack_kernel(const float* __restrict__ w, uint16_t* __restric
   }
 }
 
-// tab0[y][x][co] = bias[co] + zero-padded strided conv of the two coordinate planes (input channels 15, 16 of
+// tab0[co/8][y][x][co%8] = bias[co] + zero-padded strided conv of the two coordinate planes (input channels 15, 16 of
 // the refinement input: x = linspace(-1,1,W) along W, y along H; iodine.py:334-339)
 __global__ void rtc_tab0_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ tab,
                                 int Cr, int KS, int S, int H, int W, int Ho, int Wo) {
@@ -338,7 +379,7 @@ __global__ void rtc_tab0_kernel(const float* __restrict__ w, const float* __rest
         s += w[(((size_t)co * 17 + 15) * KS + dy) * KS + dx] * cxv + w[(((size_t)co * 17 + 16) * KS + dy) * KS + dx] * cyv;
       }
     }
-    tab[i] = s;
+    tab[((size_t)(co >> 3) * (Ho * Wo) + (size_t)y * Wo + x) * 8 + (co & 7)] = s;
   }
 }
 
@@ -358,16 +399,16 @@ int rtc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
   return 0;
 }
 
-template <int N, int NKS>
+template <int N, int NKS, int TPS, int ST>
 static int rtc_launch_t(Plan* p, const RtcParams& q, cudaStream_t st_) {
-  auto kern = refine_tc_kernel<N, NKS>;
+  auto kern = refine_tc_kernel<N, NKS, TPS, ST>;
   static bool attr_done = false;
   if (!attr_done) {
     IOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
   const int grid = q.tiles < p->num_sms ? q.tiles : p->num_sms;
-  kern<<<grid, RTC_THREADS, rtc_smem_bytes(q.w_bytes, NKS), st_>>>(q);
+  kern<<<grid, rtc_threads(N), rtc_smem_bytes(q.w_bytes, NKS, TPS, ST), st_>>>(q);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -415,8 +456,11 @@ int rtc_launch_refine_convs(Plan* p, cudaStream_t st_) {
     const int nks = st->cin[l] / 16;
     int rc = 1;
     set_error("refine_tc: unsupported ref_chan=%d / K-steps %d", Cr, nks);
-#define RTC_CASE(n, k) if (Cr == n && nks == k) rc = rtc_launch_t<n, k>(p, q, st_);
-    RTC_CASE(64, 1) RTC_CASE(64, 4) RTC_CASE(32, 1) RTC_CASE(32, 2) RTC_CASE(16, 1)
+#define RTC_CASE(n, ksz, k, tps, stg) if (Cr == n && s.ref_k == ksz && nks == k) rc = rtc_launch_t<n, k, tps, stg>(p, q, st_);
+    RTC_CASE(64, 3, 1, 9, 4) RTC_CASE(32, 3, 1, 9, 4) RTC_CASE(16, 3, 1, 9, 4)
+    RTC_CASE(64, 3, 4, 1, 8) RTC_CASE(32, 3, 2, 3, 6)
+    RTC_CASE(64, 5, 1, 5, 6) RTC_CASE(32, 5, 1, 5, 6) RTC_CASE(16, 5, 1, 5, 6)
+    RTC_CASE(32, 5, 2, 1, 12)
 #undef RTC_CASE
     if (rc) return 1;
     cur = p->r16[l & 1];

@@ -39,6 +39,9 @@ def _nrm(a, b):
     ('clevr6', dict(iters=1, slots=2), 1),        # C=64, W=128: row-aligned tiles
     ('tiny', dict(img_size=24, dec_chan=32), 3),  # odd width
     ('tiny', dict(dec_layers=1), 2),              # no C->C layer: only the 4-channel ends
+    ('tiny', dict(img_size=128, dec_chan=32, dec_layers=3, slots=2, iters=1), 1),   # row-streaming, N = 3*32
+    ('tiny', dict(img_size=128, dec_chan=16, dec_layers=3, slots=2, iters=1), 1),   # row-streaming, N = 3*16
+    ('tiny', dict(img_size=128, dec_chan=64, dec_layers=2, slots=3, iters=1), 2),   # row-streaming, odd item counts
 ])
 @pytest.mark.parametrize('prec', ['bf16', 'fp16'])
 def test_decoder_buffers_against_fp32_path(name, over, B, prec):
