@@ -153,6 +153,14 @@ IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, co
                             float* pred_host, float* mask_host, float* mean_host,
                             float* z_host, float* elbo_terms_host, void* stream);
 
+/* Evaluator tail: lib/eval/ari_eval.py:32-39 (argmax over the K predicted masks) +
+ * lib/utils/ari.py:36-54 (contingency table) + lib/utils/ari.py:6-33 (ARI), per image, on the device.
+ *   mask[B,K,H,W] fp32 (IODINE.reconstruct's mask); gt_masks[B,G,H,W] uint8 (the reference's mask.byte(), padded
+ *   to G masks per image); n_gt[B] valid ground-truth masks per image;
+ *   table_out[B,G,K] uint64 contingency tables; ari_out[B] f64 (nullable).  K, G <= 16. */
+IODINE_API int iodine_ari(const float* mask, const uint8_t* gt_masks, const int32_t* n_gt, int32_t B, int32_t K,
+                          int32_t G, int32_t H, int32_t W, uint64_t* table_out, double* ari_out, void* stream);
+
 /* Test hook: copy a named internal buffer of the last step to dst (device memory).
  * names: "out4" [BK,H,W,4], "seed4" [BK,H,W,4], "dz" [BK,L], "act<i>" [BK,H,W,C] (fp32
  * view of decoder layer i's post-activation), "pool" [BK,Cr], "stats" [BK,4,2] (f64),

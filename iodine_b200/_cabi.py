@@ -18,7 +18,7 @@ EXPORTS = [
     'iodine_plan_workspace_bytes', 'iodine_plan_set_workspace', 'iodine_plan_set_weights',
     'iodine_init_state', 'iodine_refine_step', 'iodine_elbo', 'iodine_encode', 'iodine_decode',
     'iodine_reconstruct', 'iodine_reconstruct_host', 'iodine_debug_read',
-    'iodine_plan_launch_count', 'iodine_plan_profile', 'iodine_plan_profile_read',
+    'iodine_plan_launch_count', 'iodine_plan_profile', 'iodine_plan_profile_read', 'iodine_ari',
 ]
 
 
@@ -81,6 +81,7 @@ def load():
         'iodine_plan_launch_count': [vp, C.POINTER(C.c_uint64)],
         'iodine_plan_profile': [vp, i32],
         'iodine_plan_profile_read': [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
+        'iodine_ari': [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
