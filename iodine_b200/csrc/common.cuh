@@ -82,6 +82,18 @@ struct Plan {
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
   size_t prof_used = 0;
 
+  // ---- CUDA-graph replay of encode() (plan.cu): the ~125 launches of one call are captured once per
+  //      (x, eps, outputs) pointer tuple and replayed on a plan-owned stream
+  struct EncodeGraph {
+    cudaGraphExec_t exec = nullptr;
+    const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const void* seen[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pointers of the previous eager call
+    uint64_t kernels = 0;                                                   // kernel launches inside the graph
+  } graph;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t gev_in = nullptr, gev_out = nullptr;
+  bool graphs = true;
+
   // ---- weights (plan-owned device memory, allocated at create)
   float* wsum = nullptr;      // [n_class][C][L]   layer-1 tap sums per border class
   float* ptab = nullptr;      // [H][W][C]         layer-1 coord-conv + bias table

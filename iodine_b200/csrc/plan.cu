@@ -198,6 +198,57 @@ static int do_encode(Plan* p, const float* x, const float* eps, float* z_out, fl
   return 0;
 }
 
+// encode() through a CUDA graph.  The first call with a given pointer tuple runs eagerly, the second captures
+// (on a plan-owned stream: the caller's may be the legacy default stream, which cannot be captured) and every
+// later one replays.  Profiling brackets (events) and IODINE_NO_GRAPH=1 keep the eager path.
+static int do_encode_g(Plan* p, const float* x, const float* eps, float* z_out, float* terms, float* post_out,
+                       cudaStream_t st) {
+  if (!p->graphs || p->profiling) return do_encode(p, x, eps, z_out, terms, post_out, st);
+  const void* key[5] = {x, eps, z_out, terms, post_out};
+  Plan::EncodeGraph& g = p->graph;
+  const bool hit = g.exec && !memcmp(g.key, key, sizeof(key));
+  if (!hit) {
+    const bool warm = !memcmp(g.seen, key, sizeof(key));
+    memcpy(g.seen, key, sizeof(key));
+    if (!warm) return do_encode(p, x, eps, z_out, terms, post_out, st);
+    // capture
+    if (!p->gstream) {
+      IOD_CHECK_CUDA(cudaStreamCreateWithFlags(&p->gstream, cudaStreamNonBlocking));
+      IOD_CHECK_CUDA(cudaEventCreateWithFlags(&p->gev_in, cudaEventDisableTiming));
+      IOD_CHECK_CUDA(cudaEventCreateWithFlags(&p->gev_out, cudaEventDisableTiming));
+    }
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    const uint64_t n0 = p->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(p->gstream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      p->graphs = false;
+      return do_encode(p, x, eps, z_out, terms, post_out, st);
+    }
+    const int rc = do_encode(p, x, eps, z_out, terms, post_out, p->gstream);
+    const cudaError_t ce = cudaStreamEndCapture(p->gstream, &graph);
+    const uint64_t nk = p->launches - n0;
+    p->launches = n0;
+    if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      g.exec = nullptr;
+      p->graphs = false;                        // this driver cannot capture the sequence: stay eager
+      return do_encode(p, x, eps, z_out, terms, post_out, st);
+    }
+    cudaGraphDestroy(graph);
+    memcpy(g.key, key, sizeof(key));
+    g.kernels = nk;
+  }
+  IOD_CHECK_CUDA(cudaEventRecord(p->gev_in, st));
+  IOD_CHECK_CUDA(cudaStreamWaitEvent(p->gstream, p->gev_in, 0));
+  IOD_CHECK_CUDA(cudaGraphLaunch(g.exec, p->gstream));
+  IOD_CHECK_CUDA(cudaEventRecord(p->gev_out, p->gstream));
+  IOD_CHECK_CUDA(cudaStreamWaitEvent(st, p->gev_out, 0));
+  p->launches += g.kernels;
+  return 0;
+}
+
 static int do_decode(Plan* p, const float* z, float* pred, float* mask, float* mean, cudaStream_t st) {
   if (decoder_forward(p, nullptr, nullptr, nullptr, z, st)) return 1;
   return launch_recombine(p, pred, mask, mean, st);
@@ -233,6 +284,7 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
 
   Plan* p = new Plan();
   p->s = s;
+  p->graphs = getenv("IODINE_NO_GRAPH") == nullptr;
   IOD_CHECK_CUDA(cudaGetDevice(&p->device));
   IOD_CHECK_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
   p->BK = s.B * s.K; p->HW = s.H * s.W; p->M = s.mlp_units; p->C = s.dec_chan; p->Cr = s.ref_chan;
@@ -286,6 +338,8 @@ IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
   tc_free(p);
   rtc_free(p);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+  if (p->graph.exec) cudaGraphExecDestroy(p->graph.exec);
+  if (p->gstream) { cudaStreamDestroy(p->gstream); cudaEventDestroy(p->gev_in); cudaEventDestroy(p->gev_out); }
   delete p;
   return 0;
 }
@@ -302,6 +356,7 @@ IODINE_API int iodine_plan_set_workspace(IodinePlan* plan, void* workspace, size
   IOD_REQUIRE(bytes >= p->ws_need, "workspace too small: %zu < %zu", bytes, p->ws_need);
   IOD_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
   p->ws = workspace; p->ws_bytes = bytes;
+  if (p->graph.exec) { cudaGraphExecDestroy(p->graph.exec); p->graph.exec = nullptr; }
   carve(p, (char*)workspace);
   if (tc_mode(p) && tc_on_workspace(p)) return 1;
   return 0;
@@ -354,7 +409,7 @@ IODINE_API int iodine_encode(IodinePlan* plan, const float* x, const float* eps,
   Plan* p = reinterpret_cast<Plan*>(plan);
   if (check_ready(p)) return 1;
   IOD_REQUIRE(x && eps && z_out, "null tensor argument");
-  return do_encode(p, x, eps, z_out, elbo_terms_out, post_out, (cudaStream_t)stream);
+  return do_encode_g(p, x, eps, z_out, elbo_terms_out, post_out, (cudaStream_t)stream);
 }
 
 IODINE_API int iodine_decode(IodinePlan* plan, const float* z, float* pred_out, float* mask_out, float* mean_out,
@@ -372,7 +427,7 @@ IODINE_API int iodine_reconstruct(IodinePlan* plan, const float* x, const float*
   if (check_ready(p)) return 1;
   IOD_REQUIRE(x && eps, "null tensor argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (do_encode(p, x, eps, p->st_z, elbo_terms_out, nullptr, st)) return 1;
+  if (do_encode_g(p, x, eps, p->st_z, elbo_terms_out, nullptr, st)) return 1;
   if (z_out)
     IOD_CHECK_CUDA(cudaMemcpyAsync(z_out, p->st_z, (size_t)p->BK * p->s.L * sizeof(float),
                                    cudaMemcpyDeviceToDevice, st));
@@ -390,7 +445,7 @@ IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, co
   const size_t HW = p->HW, BK = p->BK;
   IOD_CHECK_CUDA(cudaMemcpyAsync(p->hx, x_host, (size_t)s.B * 3 * HW * sizeof(float), cudaMemcpyHostToDevice, st));
   IOD_CHECK_CUDA(cudaMemcpyAsync(p->heps, eps_host, (size_t)(s.T + 1) * BK * s.L * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (do_encode(p, p->hx, p->heps, p->st_z, p->st_terms, nullptr, st)) return 1;
+  if (do_encode_g(p, p->hx, p->heps, p->st_z, p->st_terms, nullptr, st)) return 1;
   if (do_decode(p, p->st_z, pred_host ? p->hpred : nullptr, mask_host ? p->hmask : nullptr,
                 mean_host ? p->hmean : nullptr, st))
     return 1;

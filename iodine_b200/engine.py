@@ -64,6 +64,14 @@ class RefinementEngine:
             _cabi.check(self.lib.iodine_plan_set_workspace(self._plan, C.c_void_p(base), need.value))
         self._weights_key = None
         self._keep = None
+        # persistent I/O buffers of encode()/reconstruct(): stable device pointers let the library replay the
+        # whole call as one CUDA graph (plan.cu: do_encode_g); user tensors are copied in / cloned out
+        B, K, L, T = self.B, self.K, self.L, self.T
+        self._x_in = self._new(B, 3, self.H, self.W)
+        self._eps_in = self._new(T + 1, B, K, L)
+        self._z = self._new(B, K, L)
+        self._terms = self._new(max(T, 1), 2)
+        self._post = self._new(2, B, K, L)
 
     def close(self):
         if self._plan:
@@ -150,15 +158,20 @@ class RefinementEngine:
                                              _ptr(self._f32(mu)), _ptr(self._f32(lv)), _ptr(terms), _stream()))
         return terms
 
-    def encode(self, x, eps):
+    def _stage_inputs(self, x, eps):
         B, K, L, T = self.B, self.K, self.L, self.T
-        x = self._f32(x, (B, 3, self.H, self.W))
-        eps = self._f32(eps, (T + 1, B, K, L))
-        z, terms, post = self._new(B, K, L), self._new(max(T, 1), 2), self._new(2, B, K, L)
+        assert tuple(x.shape) == (B, 3, self.H, self.W), 'expected %s, got %s' % ((B, 3, self.H, self.W), tuple(x.shape))
+        assert tuple(eps.shape) == (T + 1, B, K, L), 'eps must be [T+1,B,K,L]'
+        self._x_in.copy_(x)
+        self._eps_in.copy_(eps)
+
+    def encode(self, x, eps):
+        T = self.T
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.iodine_encode(self._plan, _ptr(x), _ptr(eps), _ptr(z), _ptr(terms),
-                                               _ptr(post), _stream()))
-        return z, terms[:T], post
+            self._stage_inputs(x, eps)
+            _cabi.check(self.lib.iodine_encode(self._plan, _ptr(self._x_in), _ptr(self._eps_in), _ptr(self._z),
+                                               _ptr(self._terms), _ptr(self._post), _stream()))
+            return self._z.clone(), self._terms[:T].clone(), self._post.clone()
 
     def decode(self, z):
         B, K = self.B, self.K
@@ -170,16 +183,14 @@ class RefinementEngine:
         return pred, mask, mean
 
     def reconstruct(self, x, eps):
-        B, K, L, T = self.B, self.K, self.L, self.T
-        x = self._f32(x, (B, 3, self.H, self.W))
-        eps = self._f32(eps, (T + 1, B, K, L))
+        B, K, T = self.B, self.K, self.T
         pred, mask, mean = (self._new(B, 3, self.H, self.W), self._new(B, K, 1, self.H, self.W),
                             self._new(B, K, 3, self.H, self.W))
-        z, terms = self._new(B, K, L), self._new(max(T, 1), 2)
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.iodine_reconstruct(self._plan, _ptr(x), _ptr(eps), _ptr(pred), _ptr(mask),
-                                                    _ptr(mean), _ptr(z), _ptr(terms), _stream()))
-        return pred, mask, mean, z, terms[:T]
+            self._stage_inputs(x, eps)
+            _cabi.check(self.lib.iodine_reconstruct(self._plan, _ptr(self._x_in), _ptr(self._eps_in), _ptr(pred),
+                                                    _ptr(mask), _ptr(mean), _ptr(self._z), _ptr(self._terms), _stream()))
+            return pred, mask, mean, self._z.clone(), self._terms[:T].clone()
 
     def reconstruct_host(self, x_host, eps_host, out=None):
         """HOST (ideally pinned) buffers in and out; synchronises.  ``out`` may carry
