@@ -74,7 +74,8 @@ struct alignas(64) TcParams {
   int32_t TH;                     // image rows per work item (divides H: every item is TH rows)
   int32_t NT;                     // tiles per work item
   int32_t strips;                 // ceil(H / TH)
-  int32_t items;                  // BK * strips
+  int32_t items;                  // BK * strips (row-streaming: * rs_segs)
+  int32_t rs_segs;                // row-streaming: 128-column segments per image row (an item is one of them)
   uint32_t idesc;
   uint32_t idesc_n[8];            // row-streaming: instruction descriptor for c accumulator blocks (N = c * Cout)
   uint32_t w_bytes;               // weight image bytes (multiple of 16)
@@ -200,11 +201,14 @@ __device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, ui
 struct TcTileIter {
   int item, t, ntiles, n, y0, th;
   int row, rem, seg;
+  int xoff = 0;                                  // row-streaming: first image column of the item's 128-column segment
   int ps = 0;                                    // compile-time ring pitch of a specialised kernel (0: p.Ps)
   __device__ __forceinline__ void load_item(const TcParams& p) {
     if (item < p.items) {
-      n = item / p.strips;                       // one division per work item (>= 8 tiles)
-      y0 = (item - n * p.strips) * p.TH;
+      int rest = item;
+      if (p.rs_segs > 1) { rest = item / p.rs_segs; xoff = (item - rest * p.rs_segs) * 128; }
+      n = rest / p.strips;                       // one division per work item (>= 8 tiles)
+      y0 = (rest - n * p.strips) * p.TH;
       th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
       ntiles = tc_num_tiles(p, th);
     }
@@ -299,26 +303,39 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       }
       const bool prod_leader = elect_one_sync();
       const int c_lo = (p.nch_in * pw) / 2, c_hi = (p.nch_in * (pw + 1)) / 2;     // this producer's planes
-      const uint32_t row_bytes = (uint32_t)Ps * 16u, run_bytes = (uint32_t)p.W * 16u;
-      const uint32_t a_base = smem_u32(s_a) + (uint32_t)pad * 16u;               // interior starts after the left halo
+      const uint32_t row_bytes = (uint32_t)Ps * 16u;
+      const uint32_t a_base = smem_u32(s_a);
       const size_t plane_px = (size_t)p.H * p.W;
+      const int segs = p.rs_segs > 1 ? p.rs_segs : 1;
       int slot = 0;
       uint32_t phase = 0;
       if (prod_leader) {
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-          const int n = item / p.strips, y0 = (item - n * p.strips) * p.TH;
+          const int rest = item / segs, seg = item - rest * segs;
+          const int n = rest / p.strips, y0 = (rest - n * p.strips) * p.TH;
           const int nrows = p.TH + 2 * pad;
+          // columns copied per row: the segment plus the neighbouring pixel on every side that lies inside the
+          // image; a side on the image border keeps ring halo zeros (W > 128: re-zeroed per row, the slot may
+          // have held a row of another segment)
+          const int left = (seg > 0) ? pad : 0, right = (seg < segs - 1) ? pad : 0;
+          const uint32_t run_bytes = (uint32_t)(128 + left + right) * 16u;
+          const uint32_t dst_off = (uint32_t)(pad - left) * 16u;
+          const bool zl = segs > 1 && !left, zr = segs > 1 && !right;
+          const uint32_t per_plane = run_bytes + (zl ? (uint32_t)pad * 16u : 0u) + (zr ? (uint32_t)pad * 16u : 0u);
           for (int j = 0; j < nrows; ++j) {
             const uint32_t fb = smem_u32(&sb->full[slot]);
             mbar_wait(smem_u32(&sb->empty[slot]), phase ^ 1u, 1);
-            mbar_expect_tx(fb, run_bytes * (uint32_t)(c_hi - c_lo));             // (arrives even with no plane)
+            mbar_expect_tx(fb, per_plane * (uint32_t)(c_hi - c_lo));              // (arrives even with no plane)
             const int y = y0 - pad + j;
             const bool inside = y >= 0 && y < p.H;
-            const uint4* src = inside ? p.in + ((size_t)n * p.nch_in + c_lo) * plane_px + (size_t)y * p.W : p.zero_row;
+            const uint4* src = inside ? p.in + ((size_t)n * p.nch_in + c_lo) * plane_px + (size_t)y * p.W + (seg * 128 - left)
+                                      : p.zero_row;
             const size_t sstep = inside ? plane_px : 0;
             uint32_t dst = a_base + (uint32_t)slot * row_bytes + (uint32_t)c_lo * plane_bytes;
             for (int c = c_lo; c < c_hi; ++c) {
-              bulk_load_1d(dst, src, run_bytes, fb);
+              bulk_load_1d(dst + dst_off, src, run_bytes, fb);
+              if (zl) bulk_load_1d(dst, p.zero_row, (uint32_t)pad * 16u, fb);
+              if (zr) bulk_load_1d(dst + (uint32_t)(pad + 128) * 16u, p.zero_row, (uint32_t)pad * 16u, fb);
               src += sstep;
               dst += plane_bytes;
             }
@@ -576,6 +593,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     auto pix_of = [&](const TcTileIter& it) -> long long {
       int r = it.row, c = it.rem + quad * 32 + lane;
       while (c >= Ps) { c -= Ps; ++r; }
+      c += it.xoff;
       if (c >= W || r >= it.th) return -1;
       return (long long)(it.y0 + r) * W + c;
     };
@@ -765,8 +783,8 @@ static int round_up(int v, int a) { return (v + a - 1) / a * a; }
 static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo_pos, TcGeom* g, bool rs = false) {
   const IodineShape& s = p->s;
   const int pad = s.dec_k / 2;
-  g->Ps = round_up(s.W + 2 * pad, 8);
-  g->segs = (s.W % 128 == 0) ? s.W / 128 : 0;
+  g->Ps = round_up((rs ? 128 : s.W) + 2 * pad, 8);            // row-streaming: the ring holds one 128-column segment
+  g->segs = rs ? 1 : (s.W % 128 == 0) ? s.W / 128 : 0;
   g->w_bytes = (uint32_t)n_ent * 2u * (uint32_t)N * 16u;
   g->box_bytes = (uint32_t)(s.W + 2 * pad) * 16u;
   g->m = (127 + 2 * pad + max_lbo_pos + g->Ps - 1) / g->Ps;   // rows mirrored behind the ring end
@@ -795,7 +813,8 @@ int tc_supported(const Plan* p) {
   TcGeom g;
   if (C % 16 != 0) { set_error("16-bit modes: DEC.CONV_CHAN=%d must be a multiple of 16", C); return 0; }
   const int n_cc = kk * (C / 16);
-  if (!tc_geometry(p, C / 8, C, n_cc, 0, &g)) {
+  const bool rs_ok = s.W % 128 == 0 && s.dec_k == 3 && !getenv("IODINE_TC_NO_RS") && tc_geometry(p, C / 8, C, n_cc, 0, &g, true);
+  if (!rs_ok && !tc_geometry(p, C / 8, C, n_cc, 0, &g)) {
     set_error("16-bit modes: decoder shape (C=%d, k=%d, W=%d) does not fit the tensor-core kernel's shared memory",
               C, s.dec_k, s.W);
     return 0;
@@ -812,21 +831,26 @@ int tc_alloc(Plan* p) {
   st->n_ent_cc = kk * (C / 16);
   st->n_ent_in4 = (kk + 1) / 2;
   const int Ps = round_up(s.W + 2 * pad, 8);
-  IOD_REQUIRE(tc_geometry(p, C / 8, C, st->n_ent_cc, 0, &st->g_cc), "tc geometry (C->C) failed");
-  IOD_REQUIRE(tc_geometry(p, C / 8, 16, st->n_ent_cc, 0, &st->g_out), "tc geometry (C->4) failed");
-  IOD_REQUIRE(tc_geometry(p, 1, C, st->n_ent_in4, Ps, &st->g_in4), "tc geometry (4->C) failed");
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { st->w_fwd_rs[l] = nullptr; st->w_bwd_rs[l] = nullptr; }
-  st->rs = s.W == 128 && s.dec_k == 3 && !getenv("IODINE_TC_NO_RS") &&
+  st->rs = s.W % 128 == 0 && s.dec_k == 3 && !getenv("IODINE_TC_NO_RS") &&
            tc_geometry(p, C / 8, C, st->n_ent_cc, 0, &st->g_cc_rs, true) &&
            tc_geometry(p, C / 8, 16, st->n_ent_cc, 0, &st->g_out_rs, true);
+  if (!st->rs) {
+    IOD_REQUIRE(tc_geometry(p, C / 8, C, st->n_ent_cc, 0, &st->g_cc), "tc geometry (C->C) failed");
+    IOD_REQUIRE(tc_geometry(p, C / 8, 16, st->n_ent_cc, 0, &st->g_out), "tc geometry (C->4) failed");
+  } else {
+    st->g_cc = st->g_cc_rs;                    // (sizes the weight images; the generic C->C kernels are not launched)
+    st->g_out = st->g_out_rs;
+  }
+  IOD_REQUIRE(tc_geometry(p, 1, C, st->n_ent_in4, Ps, &st->g_in4), "tc geometry (4->C) failed");
   if (st->rs) {
     for (int l = 1; l < s.dec_layers; ++l) {
       IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd_rs[l], st->g_cc_rs.w_bytes));
       IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_bwd_rs[l], st->g_cc_rs.w_bytes));
     }
     IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_out_rs, st->g_out_rs.w_bytes));
-    IOD_CHECK_CUDA(cudaMalloc(&st->zero_row, (size_t)s.W * 16));
-    IOD_CHECK_CUDA(cudaMemset(st->zero_row, 0, (size_t)s.W * 16));
+    IOD_CHECK_CUDA(cudaMalloc(&st->zero_row, 4096));
+    IOD_CHECK_CUDA(cudaMemset(st->zero_row, 0, 4096));
   }
   for (int l = 1; l < s.dec_layers; ++l) {
     IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd[l], st->g_cc.w_bytes));
@@ -974,6 +998,7 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->H = s.H; q->W = s.W; q->pad = s.dec_k / 2;
   q->Ps = g.Ps; q->R = g.R; q->m = g.m; q->segs = g.segs; q->TH = g.TH;
   q->strips = (s.H + g.TH - 1) / g.TH;
+  q->rs_segs = 0;
   q->items = p->BK * q->strips;
   q->idesc = make_idesc(N, s.precision == IODINE_FP16);
   for (int c = 0; c < 8; ++c) q->idesc_n[c] = (c >= 1 && c * N <= 256) ? make_idesc(c * N, s.precision == IODINE_FP16) : 0u;
@@ -1099,6 +1124,7 @@ int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* a
   TcParams q;
   q.maps = *map;
   fill_common(p, st->rs ? st->g_cc_rs : st->g_cc, p->C / 8, p->C, &q);
+  if (st->rs) { q.rs_segs = p->s.W / 128; q.items *= q.rs_segs; }
   q.wimg = st->rs ? (dgrad ? st->w_bwd_rs[layer] : st->w_fwd_rs[layer]) : (dgrad ? st->w_bwd[layer] : st->w_fwd[layer]);
   q.bias = dgrad ? nullptr : p->dec[layer].b;
   q.actp = reinterpret_cast<const uint4*>(act_prev);
@@ -1120,6 +1146,7 @@ int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st_) {
   TcParams q;
   q.maps = *map;
   fill_common(p, st->rs ? st->g_out_rs : st->g_out, p->C / 8, 16, &q);
+  if (st->rs) { q.rs_segs = p->s.W / 128; q.items *= q.rs_segs; }
   q.wimg = st->rs ? st->w_out_rs : st->w_out;
   q.bias = p->out_b;
   q.actp = nullptr;

@@ -42,6 +42,8 @@ def _nrm(a, b):
     ('tiny', dict(img_size=128, dec_chan=32, dec_layers=3, slots=2, iters=1), 1),   # row-streaming, N = 3*32
     ('tiny', dict(img_size=128, dec_chan=16, dec_layers=3, slots=2, iters=1), 1),   # row-streaming, N = 3*16
     ('tiny', dict(img_size=128, dec_chan=64, dec_layers=2, slots=3, iters=1), 2),   # row-streaming, odd item counts
+    ('tiny', dict(img_size=256, dec_chan=16, dec_layers=3, slots=2, iters=1), 1),   # row-streaming, two 128-column segments
+    ('tiny', dict(img_size=256, dec_chan=64, dec_layers=2, slots=1, iters=1), 1),   # BASELINE config #5 geometry (W=256, C=64)
 ])
 @pytest.mark.parametrize('prec', ['bf16', 'fp16'])
 def test_decoder_buffers_against_fp32_path(name, over, B, prec):
