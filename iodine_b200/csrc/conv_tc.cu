@@ -76,6 +76,8 @@ struct alignas(64) TcParams {
   int32_t strips;                 // ceil(H / TH)
   int32_t items;                  // BK * strips (row-streaming: * rs_segs)
   int32_t rs_segs;                // row-streaming: 128-column segments per image row (an item is one of them)
+  int32_t rev;                    // walk the work items from the last to the first: consecutive layers alternate
+                                  // direction so that a layer starts on what the previous one wrote last (still in L2)
   uint32_t idesc;
   uint32_t idesc_n[8];            // row-streaming: instruction descriptor for c accumulator blocks (N = c * Cout)
   uint32_t w_bytes;               // weight image bytes (multiple of 16)
@@ -205,8 +207,9 @@ struct TcTileIter {
   int ps = 0;                                    // compile-time ring pitch of a specialised kernel (0: p.Ps)
   __device__ __forceinline__ void load_item(const TcParams& p) {
     if (item < p.items) {
-      int rest = item;
-      if (p.rs_segs > 1) { rest = item / p.rs_segs; xoff = (item - rest * p.rs_segs) * 128; }
+      const int im = p.rev ? p.items - 1 - item : item;
+      int rest = im;
+      if (p.rs_segs > 1) { rest = im / p.rs_segs; xoff = (im - rest * p.rs_segs) * 128; }
       n = rest / p.strips;                       // one division per work item (>= 8 tiles)
       y0 = (rest - n * p.strips) * p.TH;
       th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
@@ -311,7 +314,8 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       uint32_t phase = 0;
       if (prod_leader) {
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-          const int rest = item / segs, seg = item - rest * segs;
+          const int im = p.rev ? p.items - 1 - item : item;
+          const int rest = im / segs, seg = im - rest * segs;
           const int n = rest / p.strips, y0 = (rest - n * p.strips) * p.TH;
           const int nrows = p.TH + 2 * pad;
           // columns copied per row: the segment plus the neighbouring pixel on every side that lies inside the
@@ -370,7 +374,8 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     long long tp_wait = 0, tp_all0 = clock64();
     int tp_rows = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int n = item / p.strips, y0 = (item - n * p.strips) * p.TH;
+      const int im = p.rev ? p.items - 1 - item : item;
+      const int n = im / p.strips, y0 = (im - n * p.strips) * p.TH;
       const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
       const int nrows = th + 2 * pad;
       for (int j = 0; j < nrows; ++j) {
@@ -999,6 +1004,7 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->Ps = g.Ps; q->R = g.R; q->m = g.m; q->segs = g.segs; q->TH = g.TH;
   q->strips = (s.H + g.TH - 1) / g.TH;
   q->rs_segs = 0;
+  q->rev = 0;
   q->items = p->BK * q->strips;
   q->idesc = make_idesc(N, s.precision == IODINE_FP16);
   for (int c = 0; c < 8; ++c) q->idesc_n[c] = (c >= 1 && c * N <= 256) ? make_idesc(c * N, s.precision == IODINE_FP16) : 0u;
@@ -1125,6 +1131,9 @@ int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* a
   q.maps = *map;
   fill_common(p, st->rs ? st->g_cc_rs : st->g_cc, p->C / 8, p->C, &q);
   if (st->rs) { q.rs_segs = p->s.W / 128; q.items *= q.rs_segs; }
+  // traversal direction: read a buffer in the opposite direction to the one it was written in (the collapsed
+  // first layer and the 4->C data-gradient write ascending), so that the freshest ~100 MB are still L2 hits
+  if (!getenv("IODINE_TC_NO_REV")) q.rev = dgrad ? ((p->s.dec_layers - 1 - layer) % 2 == 0) : (layer % 2 == 1);
   q.wimg = st->rs ? (dgrad ? st->w_bwd_rs[layer] : st->w_fwd_rs[layer]) : (dgrad ? st->w_bwd[layer] : st->w_fwd[layer]);
   q.bias = dgrad ? nullptr : p->dec[layer].b;
   q.actp = reinterpret_cast<const uint4*>(act_prev);
@@ -1147,6 +1156,7 @@ int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st_) {
   q.maps = *map;
   fill_common(p, st->rs ? st->g_out_rs : st->g_out, p->C / 8, 16, &q);
   if (st->rs) { q.rs_segs = p->s.W / 128; q.items *= q.rs_segs; }
+  if (!getenv("IODINE_TC_NO_REV")) q.rev = ((p->s.dec_layers - 1) % 2 == 0);   // opposite to the last forward layer (or to layer 1)
   q.wimg = st->rs ? st->w_out_rs : st->w_out;
   q.bias = p->out_b;
   q.actp = nullptr;
