@@ -39,7 +39,7 @@ UNIT = 'refinement-steps/s'
 
 
 def clevr6_arch():
-    from oracle.arch import arch_by_name   # plain data (SimpleNamespace), no oracle compute
+    from iodine_b200.config import arch_by_name
     return arch_by_name('clevr6')
 
 
@@ -337,9 +337,9 @@ def run_native(args):
             line['variants'] = variants
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, med = oracle_port_steps_per_s(arch, args.cpu_batch, 2, 1, threads=cores)
+            v, med = oracle_port_steps_per_s(arch, args.cpu_batch, 6, 1, threads=cores)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                    'sample': 'reconstruct() of B=%d images (%d units), median of 2, %.1f s each'
+                                    'sample': 'reconstruct() of B=%d images (%d units), median of 6 calls, %.1f s each'
                                               % (args.cpu_batch, args.cpu_batch * K * T, med)}
         print(json.dumps(line), flush=True)
     if world > 1:
