@@ -105,6 +105,16 @@ __global__ void __launch_bounds__(rtc_threads(N), 1) refine_tc_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = sb->tmem_base;
   const int HWo = p.Hout * p.Wout;
+  // Tile order.  With a per-position bias table (layer 0) consecutive tiles of a CTA should share their table
+  // slice so that it stays in L1: position-block major (all slot-images of positions [128 rb, 128 rb + 128) before
+  // the next block).  Otherwise tiles are consecutive runs of the flattened (slot-image, y, x) space.
+  const int n_img = p.total / HWo;
+  const bool rb_major = p.tab != nullptr && (HWo % 128) == 0;
+  auto tile_pos0 = [&](int tile) -> int {
+    if (!rb_major) return tile * 128;
+    const int rb = tile / n_img;
+    return (tile - rb * n_img) * HWo + rb * 128;
+  };
 
   if (warp < 4) {
     // =============================================================== producers (gather)
@@ -115,7 +125,7 @@ __global__ void __launch_bounds__(rtc_threads(N), 1) refine_tc_kernel(const __gr
     uint32_t phase = 0;
     int issued = 0, arrived_stage = 0;             // groups committed; stage of the oldest un-arrived group
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      const int pos = tile * 128 + tid;
+      const int pos = tile_pos0(tile) + tid;
       const bool valid = pos < p.total;
       const int n = valid ? pos / HWo : 0;
       const int r = valid ? pos - n * HWo : 0;
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(rtc_threads(N), 1) refine_tc_kernel(const __gr
     // loads across the TMEM read) they cost one exposed L2 latency per 8 channels and bounded the layer
     float4 tb[NC / 4], tb_next[NC / 4];
     auto locate = [&](int tile, bool& valid, int& n, int& r) {
-      const int pos = tile * 128 + quad * 32 + lane;
+      const int pos = tile_pos0(tile) + quad * 32 + lane;
       valid = tile < p.tiles && pos < p.total;
       n = valid ? pos / HWo : 0;
       r = valid ? pos - n * HWo : 0;
