@@ -38,9 +38,9 @@ METRIC = 'refinement-steps/sec (BxKxT) CLEVR6 128x128 K=7 T=5'
 UNIT = 'refinement-steps/s'
 
 
-def clevr6_arch():
+def clevr6_arch(**over):
     from iodine_b200.config import arch_by_name
-    return arch_by_name('clevr6')
+    return arch_by_name('clevr6', **over)
 
 
 def flops_per_unit(arch):
@@ -182,7 +182,14 @@ def run_native(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    arch = clevr6_arch()
+    over = {}
+    if args.slots:
+        over['slots'] = args.slots
+    if args.iters:
+        over['iters'] = args.iters
+    if args.img_size:
+        over['img_size'] = args.img_size
+    arch = clevr6_arch(**over)
     B, K, T, L, S = args.batch, arch.SLOTS, arch.ITERS, arch.DIM_LATENT, arch.IMG_SIZE
     torch.manual_seed(0)
     model = IODINE(arch, precision=args.precision).to(dev)
@@ -309,8 +316,8 @@ def run_native(args):
             'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32' if args.precision == 'fp32' else '%s operands / f32 accumulate' % args.precision,
             'data': 'synthetic',
-            'config': {'workload': 'CLEVR6 128x128 K=7 T=5 B=%d per GPU (configs[1]); step = one '
-                                   'IODINE.encode() over the batch' % B,
+            'config': {'workload': 'CLEVR6 %dx%d K=%d T=%d B=%d per GPU (%s); step = one '
+                                   'IODINE.encode() over the batch' % (S, S, K, T, B, 'configs[1]' if (S, K, T, B) == (128, 7, 5, 32) else 'non-default shape'),
                        'units_per_step': units_per_step, 'precision': args.precision,
                        'l2': 'activations (%.2f GB/layer) exceed the 126 MB L2; no flush needed'
                              % (B * K * S * S * arch.DEC.CONV_CHAN * (4 if args.precision == 'fp32' else 2) / 1e9),
@@ -356,6 +363,9 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('IODINE_PRECISION', 'fp16'),
                     help='fp16 (default: tcgen05, meets the 1e-3 parity bar), bf16 (tcgen05), fp32 (exact FFMA path)')
     ap.add_argument('--no-variants', action='store_true', help='skip the short fp32 / bf16 side measurements')
+    ap.add_argument('--slots', type=int, default=0, help='override K (BASELINE config #4: 11)')
+    ap.add_argument('--iters', type=int, default=0, help='override T (BASELINE config #4: 7)')
+    ap.add_argument('--img-size', type=int, default=0, help='override the image size (BASELINE config #5: 256)')
     ap.add_argument('--cpu-batch', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-mode', action='store_true',
