@@ -155,7 +155,7 @@ class IODINE(nn.Module):
         dev = self._device()
         free, _ = torch.cuda.mem_get_info(dev)
         a = self.arch
-        eb = 2 if self.precision == 'bf16' else 4
+        eb = 2 if self.precision in ('bf16', 'fp16') else 4
         per_img = self.K * a.IMG_SIZE * a.IMG_SIZE * (
             (a.DEC.CONV_LAYERS + 2) * a.DEC.CONV_CHAN * eb + (8 + 12 + 20 + 4) * 4
             + a.REF.CONV_CHAN * 4 // 2)
@@ -251,12 +251,31 @@ class IODINE(nn.Module):
         B = B or self.z.shape[0]
         return (t[:, 0] - t[:, 1]) / B
 
-    def forward(self, x):
-        """Training objective (reference iodine.py:115-158).  Back-propagation through the
-        refinement loop is not part of the native inference path."""
-        raise NotImplementedError(
-            'IODINE.forward (training loss with BPTT through the refinement loop) is not '
-            'implemented by the native engine yet; encode/decode/reconstruct/elbo are.')
+    @torch.no_grad()
+    def forward(self, x, eps=None):
+        """Training objective VALUE (reference iodine.py:115-158): ``-sum_i (i+1)/(T+1) * elbo_i`` over the T
+        in-loop ELBOs and the final one (151-153, 158), as a 0-dim tensor.
+
+        The value comes from the native inference kernels; it carries NO autograd graph -- back-propagation
+        through the refinement loop (decoder / refiner weight gradients, LSTM backward) is SURVEY.md 8f rank 1 and
+        not implemented, so ``loss.backward()`` raises torch's usual "does not require grad" error instead of
+        silently training nothing."""
+        x = self._require_cuda(x)
+        B, T = x.shape[0], self.n_iters
+        eps = self._noise(B, eps)
+        self.encode(x, eps=eps)                                   # T in-loop ELBOs + final posterior
+        elbos = list(self.elbo_per_step(B))
+        final = 0
+        for b0, b1 in self._spans(B):
+            final = final + self._engine(b1 - b0).elbo_terms(x[b0:b1], eps[T, b0:b1], self.posterior.mean[b0:b1],
+                                                            self.posterior.logvar[b0:b1])
+        elbos.append((final[0] - final[1]) / B)
+        loss = 0
+        for i, e in enumerate(elbos):
+            loss = loss + (i + 1) / len(elbos) * e
+        logger.update(init_mean=self.posterior.init_mean.detach().mean(),
+                      init_logvar=self.posterior.init_logvar.detach().mean())
+        return -loss
 
     # ------------------------------------------------------------------ side channel (A9)
     def _log_scalars(self, B):

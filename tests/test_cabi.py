@@ -57,5 +57,5 @@ def test_no_cpu_fallback():
     m = IODINE(A.arch_by_name('tiny'))
     with pytest.raises(_cabi.IodineError):
         m.reconstruct(torch.rand(1, 3, 16, 16))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_cabi.IodineError):
         m(torch.rand(1, 3, 16, 16))

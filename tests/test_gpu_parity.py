@@ -190,3 +190,23 @@ def test_full_size_properties_clevr6_b32():
     assert rel_err(model.elbo_terms, e32) < 1e-5
     # the golden B=1 vector is image 0 of the same generator stream? (no: different seeds) ->
     # compare against the committed clevr6 golden separately in test_reconstruct_against_golden
+
+
+@pytest.mark.parametrize('name', ['tiny_b2_sharp', 'test5x5_b2_sharp'])
+def test_forward_loss_value_against_oracle(name):
+    """IODINE.forward (iodine.py:115-158): -sum_i (i+1)/(T+1) elbo_i over T in-loop ELBOs + the final one."""
+    g, arch, B, sd, model = golden_state_dict(name)
+    model.to(DEV)
+    x, eps = t(g['x']), t(g['eps'])
+    loss = model(x.to(DEV), eps=eps.to(DEV))
+    assert loss.dim() == 0 and not loss.requires_grad
+    tr = S.encode_trace(sd, arch, x, eps)
+    elbos = [s['elbo'] for s in tr['steps']]
+    mean, logits, _, _ = S.decoder_forward(sd, tr['z'], arch.IMG_SIZE)       # final elbo(x): z = sample(eps[T])
+    ll = S.mixture(x, mean, logits, arch.SIGMA)['ll_sum'] / B
+    kl = S.kl_elementwise(tr['post_mean'], tr['post_logvar']).sum() / B
+    elbos.append(ll - kl)
+    want = -sum((i + 1) / len(elbos) * e for i, e in enumerate(elbos))
+    assert abs(loss.item() - want.item()) < TOL_INT * abs(want.item())
+    for i in range(arch.ITERS):                                               # in-loop ELBOs vs the reference's own
+        assert abs(elbos[i].item() - float(g['s%d_elbo' % i])) < 2e-5 * abs(float(g['s%d_elbo' % i]))

@@ -1,0 +1,73 @@
+"""CPU: the host mirror keeps the reference's Python boundary: state_dict keys / shapes, seeded
+default init, checkpoint loading incl. the DataParallel ``module.`` prefix, ``make_model(cfg)``."""
+import io
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import arch as A
+from oracle import ref_loader as R
+
+from helpers import seeded_model
+from iodine_b200.modeling import IODINE, make_model
+
+
+def _cfg(arch, device='cpu', parallel=False, precision=None):
+    m = SimpleNamespace(NAME='IODINE', DEVICE=device, PARALLEL=parallel)
+    if precision:
+        m.PRECISION = precision
+    return SimpleNamespace(MODEL=m, ARCH=arch)
+
+
+def test_state_dict_keys_match_survey_listing():
+    m = IODINE(A.arch_by_name('clevr6'))
+    sd = m.state_dict()
+    assert sum(v.numel() for v in sd.values()) == 1109956          # SURVEY.md 8b [measured on the reference]
+    assert tuple(sd['refine.mlc.layers.0.weight'].shape) == (64, 17, 3, 3)
+    assert tuple(sd['decoder.mlc.layers.0.weight'].shape) == (64, 66, 3, 3)
+    assert tuple(sd['decoder.conv.weight'].shape) == (4, 64, 3, 3)
+    assert tuple(sd['refine.lstm.weight_ih'].shape) == (1024, 512)
+    assert tuple(sd['posterior.init_mean'].shape) == (64,)
+
+
+@pytest.mark.skipif(not R.reference_available(), reason='reference tree not mounted')
+@pytest.mark.parametrize('name', ['tiny', 'dsprites', 'test5x5'])
+def test_same_keys_shapes_and_seeded_init_as_live_reference(name):
+    arch = A.arch_by_name(name)
+    ref = R.build_reference_model(arch, seed=0, sharpen=1.0)
+    ours = seeded_model(arch)
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+        assert torch.equal(a[k], b[k]), k          # same creation order -> bit-identical default init
+
+
+@pytest.mark.skipif(not R.reference_available(), reason='reference tree not mounted')
+def test_reference_checkpoint_loads_with_and_without_module_prefix():
+    arch = A.arch_by_name('tiny')
+    ref = R.build_reference_model(arch, seed=3, sharpen=2.0)
+    buf = io.BytesIO()
+    torch.save({'model': ref.state_dict(), 'epoch': 7}, buf)                 # lib/utils/checkpoint.py:43-54
+    buf.seek(0)
+    ck = torch.load(buf)
+    plain = make_model(_cfg(arch))
+    plain.load_state_dict(ck['model'])                                       # checkpoint.py:68
+    assert torch.equal(plain.decoder.conv.weight, ref.decoder.conv.weight)
+    dp = make_model(_cfg(arch, parallel=True))                               # MODEL.PARALLEL: keys carry 'module.'
+    dp.load_state_dict({'module.' + k: v for k, v in ck['model'].items()})
+    assert torch.equal(dp.module.refine.lstm.weight_hh, ref.refine.lstm.weight_hh)
+    assert dp.module.sigma == arch.SIGMA                                     # lib/engine/train.py:97
+
+
+def test_make_model_contract():
+    arch = A.arch_by_name('tiny')
+    m = make_model(_cfg(arch, precision='fp16'))
+    assert isinstance(m, IODINE) and m.precision == 'fp16'
+    with pytest.raises(ValueError):
+        make_model(SimpleNamespace(MODEL=SimpleNamespace(NAME='VAE', DEVICE='cpu', PARALLEL=False), ARCH=arch))
+    bad = A.arch_by_name('tiny')
+    bad.ENCODING = bad.ENCODING[:-1]
+    with pytest.raises(NotImplementedError):
+        IODINE(bad)
