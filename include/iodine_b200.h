@@ -153,6 +153,13 @@ IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, co
                             float* pred_host, float* mask_host, float* mean_host,
                             float* z_host, float* elbo_terms_host, void* stream);
 
+/* The same sequence WITHOUT the final synchronisation: everything is enqueued on `stream` and the host buffers
+ * are valid once the caller has synchronised it.  Two plans on two streams double-buffer an evaluation loop:
+ * the copies of one batch overlap the kernels of the other (bench.py's e2e leg). */
+IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_host, const float* eps_host,
+                                  float* pred_host, float* mask_host, float* mean_host,
+                                  float* z_host, float* elbo_terms_host, void* stream);
+
 /* Evaluator tail: lib/eval/ari_eval.py:32-39 (argmax over the K predicted masks) +
  * lib/utils/ari.py:36-54 (contingency table) + lib/utils/ari.py:6-33 (ARI), per image, on the device.
  *   mask[B,K,H,W] fp32 (IODINE.reconstruct's mask); gt_masks[B,G,H,W] uint8 (the reference's mask.byte(), padded

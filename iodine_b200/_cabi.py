@@ -17,7 +17,7 @@ EXPORTS = [
     'iodine_abi_version', 'iodine_last_error', 'iodine_plan_create', 'iodine_plan_destroy',
     'iodine_plan_workspace_bytes', 'iodine_plan_set_workspace', 'iodine_plan_set_weights',
     'iodine_init_state', 'iodine_refine_step', 'iodine_elbo', 'iodine_encode', 'iodine_decode',
-    'iodine_reconstruct', 'iodine_reconstruct_host', 'iodine_debug_read',
+    'iodine_reconstruct', 'iodine_reconstruct_host', 'iodine_reconstruct_host_async', 'iodine_debug_read',
     'iodine_plan_launch_count', 'iodine_plan_profile', 'iodine_plan_profile_read', 'iodine_ari',
 ]
 
@@ -77,6 +77,7 @@ def load():
         'iodine_decode': [vp] * 6,
         'iodine_reconstruct': [vp] * 9,
         'iodine_reconstruct_host': [vp] * 9,
+        'iodine_reconstruct_host_async': [vp] * 9,
         'iodine_debug_read': [vp, C.c_char_p, vp, sz, C.POINTER(sz), vp],
         'iodine_plan_launch_count': [vp, C.POINTER(C.c_uint64)],
         'iodine_plan_profile': [vp, i32],

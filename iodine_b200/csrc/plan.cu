@@ -434,9 +434,9 @@ IODINE_API int iodine_reconstruct(IodinePlan* plan, const float* x, const float*
   return do_decode(p, p->st_z, pred_out, mask_out, mean_out, st);
 }
 
-IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, const float* eps_host,
-                            float* pred_host, float* mask_host, float* mean_host, float* z_host,
-                            float* elbo_terms_host, void* stream) {
+IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_host, const float* eps_host,
+                                  float* pred_host, float* mask_host, float* mean_host, float* z_host,
+                                  float* elbo_terms_host, void* stream) {
   Plan* p = reinterpret_cast<Plan*>(plan);
   if (check_ready(p)) return 1;
   IOD_REQUIRE(x_host && eps_host, "null tensor argument");
@@ -454,7 +454,15 @@ IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, co
   if (mean_host) IOD_CHECK_CUDA(cudaMemcpyAsync(mean_host, p->hmean, BK * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (z_host) IOD_CHECK_CUDA(cudaMemcpyAsync(z_host, p->st_z, BK * s.L * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (elbo_terms_host) IOD_CHECK_CUDA(cudaMemcpyAsync(elbo_terms_host, p->st_terms, (size_t)s.T * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  IOD_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+IODINE_API int iodine_reconstruct_host(IodinePlan* plan, const float* x_host, const float* eps_host,
+                            float* pred_host, float* mask_host, float* mean_host, float* z_host,
+                            float* elbo_terms_host, void* stream) {
+  if (iodine_reconstruct_host_async(plan, x_host, eps_host, pred_host, mask_host, mean_host, z_host, elbo_terms_host, stream))
+    return 1;
+  IOD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
 

@@ -192,8 +192,9 @@ class RefinementEngine:
                                                     _ptr(mask), _ptr(mean), _ptr(self._z), _ptr(self._terms), _stream()))
             return pred, mask, mean, self._z.clone(), self._terms[:T].clone()
 
-    def reconstruct_host(self, x_host, eps_host, out=None):
-        """HOST (ideally pinned) buffers in and out; synchronises.  ``out`` may carry
+    def reconstruct_host(self, x_host, eps_host, out=None, sync=True):
+        """HOST (ideally pinned) buffers in and out; synchronises unless ``sync=False`` (then the outputs are valid
+        after the caller synchronises the current stream -- used to double-buffer two engines on two streams).  ``out`` may carry
         pre-allocated pinned tensors 'pred','mask','mean','z','terms'."""
         B, K, L, T = self.B, self.K, self.L, self.T
         assert x_host.device.type == 'cpu' and eps_host.device.type == 'cpu'
@@ -205,7 +206,8 @@ class RefinementEngine:
             out = dict(pred=mk(B, 3, self.H, self.W), mask=mk(B, K, 1, self.H, self.W),
                        mean=mk(B, K, 3, self.H, self.W), z=mk(B, K, L), terms=mk(max(T, 1), 2))
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.iodine_reconstruct_host(
+            fn = self.lib.iodine_reconstruct_host if sync else self.lib.iodine_reconstruct_host_async
+            _cabi.check(fn(
                 self._plan, _ptr(x_host), _ptr(eps_host), _ptr(out['pred']), _ptr(out['mask']),
                 _ptr(out['mean']), _ptr(out['z']), _ptr(out['terms']), _stream()))
         return out

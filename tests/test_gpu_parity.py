@@ -166,6 +166,33 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     assert rel_err(out['z'], g['final_z']) < TOL_OUT
 
 
+def test_async_host_entry_point_double_buffered_on_two_streams():
+    """iodine_reconstruct_host_async: two plans on two streams, results valid after each stream's sync; replays
+    (CUDA-graph path: 3rd+ call with the same plan-owned pointers) agree with the eager calls."""
+    g, arch, B, sd, model = golden_state_dict('tiny_b2_sharp')
+    model_b = seeded_model(arch, float(g['sharpen']))
+    engs = [_engine(model, B), _engine(model_b, B)]
+    streams = [torch.cuda.Stream(device=DEV), torch.cuda.Stream(device=DEV)]
+    x, eps = t(g['x']).pin_memory(), t(g['eps']).pin_memory()
+    outs = [None, None]
+    first = None
+    for i in range(6):
+        j = i & 1
+        if outs[j] is not None:
+            streams[j].synchronize()
+            if first is None:
+                first = {k: v.clone() for k, v in outs[j].items()}
+            for k in first:
+                assert rel_err(outs[j][k], first[k]) < 1e-5, (i, k)    # eager == graph replay (fp32 atomics: not bitwise)
+        with torch.cuda.stream(streams[j]):
+            outs[j] = engs[j].reconstruct_host(x, eps, outs[j], sync=False)
+    for j in (0, 1):
+        streams[j].synchronize()
+        assert rel_err(outs[j]['pred'], g['final_pred']) < TOL_OUT
+        assert rel_err(outs[j]['mask'], g['final_mask']) < TOL_OUT
+        assert rel_err(outs[j]['z'], g['final_z']) < TOL_OUT
+
+
 def test_full_size_properties_clevr6_b32():
     """BASELINE config #2 (CLEVR6 128x128, K=7, T=5, B=32): properties that need no oracle."""
     arch = A.arch_by_name('clevr6')
