@@ -172,7 +172,17 @@ def run_reference_arm(args):
 
 
 # =========================================================================== native arm
+def _quiet_stdout():
+    """Route everything libraries print on fd 1 (NCCL's version banner, ...) to stderr; returns a writer for the
+    real stdout, which then carries nothing but the JSON line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, 'w')
+
+
 def run_native(args):
+    out_stream = _quiet_stdout()
     import torch.distributed as dist
     from iodine_b200.modeling.iodine import IODINE
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -390,7 +400,8 @@ def run_native(args):
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': 'reconstruct() of B=%d images (%d units), median of 6 calls, %.1f s each'
                                               % (args.cpu_batch, args.cpu_batch * K * T, med)}
-        print(json.dumps(line), flush=True)
+        out_stream.write(json.dumps(line) + '\n')
+        out_stream.flush()
     if world > 1:
         dist.destroy_process_group()
 
