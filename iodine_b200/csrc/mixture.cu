@@ -122,72 +122,89 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
       mgsum += lg[k] * gm[k];
     }
   }
-  __shared__ float sred[NW][8];
-  for (int k = 0; k < K; ++k) {
-    float a_mean = 0.f, a_mean2 = 0.f, a_gm = 0.f, a_gm2 = 0.f, a_loo = 0.f, a_loo2 = 0.f;
-    // (runtime k indexes compile-time-unrolled registers through a select chain)
-    float mk = 0.f, m_r = 0.f, m_g = 0.f, m_b = 0.f, gmk = 0.f, lgr = 0.f;
+  // Layer-norm sums.  Every slot contributes six sums over the block's pixels (grad_means: sum, sum^2 over the
+  // three channels; grad_mask; leave-one-out) and the image two (pixel likelihood).  Slots are handled in batches
+  // of MIX_KB = 5 (30 sums, + the 2 likelihood sums in the first batch = 32): a TRANSPOSED warp reduction brings
+  // the 32 per-lane partials down to one total per lane in 31 shuffles (lane l ends up with the total of sum l)
+  // instead of 5 shuffles per sum -- the kernel was bound by the shuffle unit (220 shuffles per pixel at K = 7).
+  constexpr int MIX_KB = 5;
+  constexpr int NBATCH = (KMAX + MIX_KB - 1) / MIX_KB;
+  __shared__ double s_stat[NBATCH][32];
+  for (int i = threadIdx.x; i < NBATCH * 32; i += blockDim.x) (&s_stat[0][0])[i] = 0.0;
+  __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < KMAX; ++kk)
-      if (kk == k) { mk = lg[kk]; m_r = mr[kk]; m_g = mg[kk]; m_b = mb[kk]; gmk = gm[kk]; lgr = logit_raw[kk]; }
-    if (live) {
-      const float dr = xr - m_r, dg = xg - m_g, db = xb - m_b;
-      const float llr = -dr * dr * inv_2s2 + ll_const, llg = -dg * dg * inv_2s2 + ll_const,
-                  llb = -db * db * inv_2s2 + ll_const;
-      const float me = mk + 1e-12f;
-      const float er = expf(llr - s_r), eg = expf(llg - s_g), eb = expf(llb - s_b);
-      // dJ/dmean_kc = r_kc (x_c - mean_kc)/sigma^2 with r_kc = (mask+1e-12) * exp(ll - s)
-      const float gr = me * er * dr * inv_s2, gg = me * eg * dg * inv_s2, gb = me * eb * db * inv_s2;
-      const float Lk = expf(llr + llg + llb);
-      const float mpost = Lk / kl_tot;                                   // (292) 0/0 -> NaN as ref
-      const float loo = (mkl_tot - mk * Lk) / (1.f - mk + 1e-5f);        // (326-328)
-      const size_t sp = ((size_t)(b * K + k)) * HW + pix;
-      float4* ax = reinterpret_cast<float4*>(auxs) + sp * 3;
-      ax[0] = make_float4(m_r, m_g, m_b, mk);
-      ax[1] = make_float4(lgr, mpost, gr, gg);
-      ax[2] = make_float4(gb, gmk, loo, 0.f);
-      // chain to the decoder's raw outputs: sigmoid' and softmax'
-      const float4 sd = make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g),
-                                    gb * m_b * (1.f - m_b), mk * (gmk - mgsum));
-      if (seed_half) {   // one 8-channel 16-bit plane for the tensor-core data-gradient (conv_tc.cu)
-        reinterpret_cast<uint4*>(seed4)[sp] = make_uint4(pack_h2(sd.x, sd.y, seed_half == 2),
-                                                         pack_h2(sd.z, sd.w, seed_half == 2), 0u, 0u);
-      } else {
-        reinterpret_cast<float4*>(seed4)[sp] = sd;
+  for (int bt = 0; bt < NBATCH; ++bt) {
+    if (bt * MIX_KB < K) {                          // block-uniform
+      float vb[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) vb[i] = 0.f;
+      if (bt == 0) { vb[30] = likv; vb[31] = likv * likv; }
+#pragma unroll
+      for (int kk = 0; kk < MIX_KB; ++kk) {
+        const int k = bt * MIX_KB + kk;             // compile-time
+        if (k < KMAX && k < K && live) {
+          const float mk = lg[k], m_r = mr[k], m_g = mg[k], m_b = mb[k], gmk = gm[k], lgr = logit_raw[k];
+          const float dr = xr - m_r, dg = xg - m_g, db = xb - m_b;
+          const float llr = -dr * dr * inv_2s2 + ll_const, llg = -dg * dg * inv_2s2 + ll_const,
+                      llb = -db * db * inv_2s2 + ll_const;
+          const float me = mk + 1e-12f;
+          const float er = expf(llr - s_r), eg = expf(llg - s_g), eb = expf(llb - s_b);
+          // dJ/dmean_kc = r_kc (x_c - mean_kc)/sigma^2 with r_kc = (mask+1e-12) * exp(ll - s)
+          const float gr = me * er * dr * inv_s2, gg = me * eg * dg * inv_s2, gb = me * eb * db * inv_s2;
+          const float Lk = expf(llr + llg + llb);
+          const float mpost = Lk / kl_tot;                                   // (292) 0/0 -> NaN as ref
+          const float loo = (mkl_tot - mk * Lk) / (1.f - mk + 1e-5f);        // (326-328)
+          const size_t sp = ((size_t)(b * K + k)) * HW + pix;
+          float4* ax = reinterpret_cast<float4*>(auxs) + sp * 3;
+          ax[0] = make_float4(m_r, m_g, m_b, mk);
+          ax[1] = make_float4(lgr, mpost, gr, gg);
+          ax[2] = make_float4(gb, gmk, loo, 0.f);
+          // chain to the decoder's raw outputs: sigmoid' and softmax'
+          const float4 sd = make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g),
+                                        gb * m_b * (1.f - m_b), mk * (gmk - mgsum));
+          if (seed_half) {   // one 8-channel 16-bit plane for the tensor-core data-gradient (conv_tc.cu)
+            reinterpret_cast<uint4*>(seed4)[sp] = make_uint4(pack_h2(sd.x, sd.y, seed_half == 2),
+                                                             pack_h2(sd.z, sd.w, seed_half == 2), 0u, 0u);
+          } else {
+            reinterpret_cast<float4*>(seed4)[sp] = sd;
+          }
+          vb[6 * kk + 0] = gr + gg + gb;
+          vb[6 * kk + 1] = gr * gr + gg * gg + gb * gb;
+          vb[6 * kk + 2] = gmk;
+          vb[6 * kk + 3] = gmk * gmk;
+          vb[6 * kk + 4] = loo;
+          vb[6 * kk + 5] = loo * loo;
+        }
       }
-      a_mean = gr + gg + gb; a_mean2 = gr * gr + gg * gg + gb * gb;
-      a_gm = gmk; a_gm2 = gmk * gmk;
-      a_loo = loo; a_loo2 = loo * loo;
-    }
-    a_mean = warp_sum(a_mean); a_mean2 = warp_sum(a_mean2);
-    a_gm = warp_sum(a_gm); a_gm2 = warp_sum(a_gm2);
-    a_loo = warp_sum(a_loo); a_loo2 = warp_sum(a_loo2);
-    __syncthreads();
-    if (lane == 0) {
-      sred[warp][0] = a_mean; sred[warp][1] = a_mean2; sred[warp][2] = a_gm;
-      sred[warp][3] = a_gm2; sred[warp][4] = a_loo; sred[warp][5] = a_loo2;
-    }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-      double t = 0.0;
-      for (int w = 0; w < NW; ++w) t += (double)sred[w][threadIdx.x];
-      // stats[n][group][2]: group 0 grad_means, 1 grad_mask, 2 likelihood, 3 leave-one-out
-      const int grp = threadIdx.x >> 1, which = threadIdx.x & 1;
-      const int g = (grp == 2) ? 3 : grp;
-      atomicAdd(&stats[((size_t)(b * K + k) * 4 + g) * 2 + which], t);
+      // transposed reduction: after the round with mask m, lanes with bit m clear hold the lower half of the
+      // surviving sums and lanes with it set the upper half; lane l finishes with the total of sum l
+#pragma unroll
+      for (int m = 16, n = 32; m >= 1; m >>= 1, n >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+          const float send = up ? vb[i] : vb[i + n / 2];
+          const float keep = up ? vb[i + n / 2] : vb[i];
+          vb[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+      atomicAdd(&s_stat[bt][lane], (double)vb[0]);
     }
   }
-  // likelihood statistics are per image; every slot of the image gets the same numbers
-  {
-    float a = warp_sum(likv), a2 = warp_sum(likv * likv);
-    __syncthreads();
-    if (lane == 0) { sred[warp][0] = a; sred[warp][1] = a2; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-      double t = 0.0;
-      for (int w = 0; w < NW; ++w) t += (double)sred[w][threadIdx.x];
-      for (int k = 0; k < K; ++k)
-        atomicAdd(&stats[((size_t)(b * K + k) * 4 + 2) * 2 + threadIdx.x], t);
+  __syncthreads();
+  // block totals -> global f64 sums.  stats[n][group][2]: group 0 grad_means, 1 grad_mask, 2 likelihood, 3 loo
+  for (int i = threadIdx.x; i < NBATCH * 32; i += blockDim.x) {
+    const int bt = i >> 5, l = i & 31;
+    const double v = s_stat[bt][l];
+    if (l < 30) {
+      const int k = bt * MIX_KB + l / 6, j = l % 6;
+      if (k < K) {
+        const int grp = j >> 1, g = (grp == 2) ? 3 : grp;
+        atomicAdd(&stats[((size_t)(b * K + k) * 4 + g) * 2 + (j & 1)], v);
+      }
+    } else if (bt == 0) {
+      // likelihood statistics are per image; every slot of the image gets the same numbers
+      for (int k = 0; k < K; ++k) atomicAdd(&stats[((size_t)(b * K + k) * 4 + 2) * 2 + (l - 30)], v);
     }
   }
 }
