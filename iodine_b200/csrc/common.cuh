@@ -96,6 +96,7 @@ struct Plan {
 
   // ---- weights (plan-owned device memory, allocated at create)
   float* wsum = nullptr;      // [n_class][C][L]   layer-1 tap sums per border class
+  float* wsumT = nullptr;     // [n_class][L][C]   the same, transposed (coalesced over C for the forward GEMV)
   float* ptab = nullptr;      // [H][W][C]         layer-1 coord-conv + bias table
   ConvPack dec[IODINE_MAX_LAYERS];   // layers 1..n-1 (index = layer), C->C
   float* out_w = nullptr;     // [tap][ci][4]      decoder.conv forward

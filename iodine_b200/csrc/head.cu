@@ -58,8 +58,8 @@ __global__ void pack_refine_kernel(const float* __restrict__ w, float* __restric
 
 // Layer-1 collapse.  For border class (cy,cx) the valid taps are those that stay inside the
 // image; wsum[cls][co][ci] = sum of W1[co][ci][dy][dx] over them (ci < L).
-__global__ void pack_wsum_kernel(const float* __restrict__ w1, float* __restrict__ wsum, int C, int L,
-                                 int KS) {
+__global__ void pack_wsum_kernel(const float* __restrict__ w1, float* __restrict__ wsum, float* __restrict__ wsumT,
+                                 int C, int L, int KS) {
   const int P = KS / 2, CI = L + 2;
   const int total = KS * KS * C * L;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -71,6 +71,7 @@ __global__ void pack_wsum_kernel(const float* __restrict__ w1, float* __restrict
     for (int dy = dy_lo; dy <= dy_hi; ++dy)
       for (int dx = dx_lo; dx <= dx_hi; ++dx) s += w1[(((size_t)co * CI + ci) * KS + dy) * KS + dx];
     wsum[i] = s;
+    wsumT[((size_t)cls * L + ci) * C + co] = s;
   }
 }
 
@@ -115,7 +116,7 @@ int launch_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st) {
   const int C = p->C, L = s.L, KS = s.dec_k, Cr = p->Cr, M = p->M;
   const int ck = (KS == 3) ? 16 : 8;
   IOD_REQUIRE(w->dec_w[0] && w->dec_b[0], "set_weights: decoder layer 0 missing");
-  pack_wsum_kernel<<<64, 256, 0, st>>>(w->dec_w[0], p->wsum, C, L, KS);
+  pack_wsum_kernel<<<64, 256, 0, st>>>(w->dec_w[0], p->wsum, p->wsumT, C, L, KS);
   IOD_LAUNCH_CHECK(p);
   pack_ptab_kernel<<<256, 256, 0, st>>>(w->dec_w[0], w->dec_b[0], p->ptab, C, L, KS, s.H, s.W);
   IOD_LAUNCH_CHECK(p);
@@ -159,12 +160,13 @@ int launch_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st) {
 // =====================================================================================
 // sample + first decoder layer
 // =====================================================================================
-// z = mu + exp(logvar/2) * eps (or z given), u[n][cls][co] = sum_ci wsum[cls][co][ci] z[n][ci]
-__global__ void __launch_bounds__(128)
+// z = mu + exp(logvar/2) * eps (or z given), u[n][cls][co] = sum_ci wsumT[cls][ci][co] z[n][ci]
+// (thread = one (class, channel) output; consecutive threads read consecutive channels of the transposed weights)
+__global__ void __launch_bounds__(256)
 sample_u_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
                 const float* __restrict__ eps, const float* __restrict__ z_in,
-                const float* __restrict__ wsum, float* __restrict__ z_out, float* __restrict__ u,
-                int L, int NCC /* n_class*C */) {
+                const float* __restrict__ wsumT, float* __restrict__ z_out, float* __restrict__ u,
+                int L, int C, int NCC /* n_class*C */) {
   extern __shared__ float sz[];
   const int n = blockIdx.x;
   for (int i = threadIdx.x; i < L; i += blockDim.x) {
@@ -176,10 +178,16 @@ sample_u_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
   }
   __syncthreads();
   for (int o = threadIdx.x; o < NCC; o += blockDim.x) {
-    const float* wr = wsum + (size_t)o * L;
-    float s = 0.f;
-    for (int i = 0; i < L; ++i) s = fmaf(wr[i], sz[i], s);
-    u[(size_t)n * NCC + o] = s;
+    const int cls = o / C, co = o - cls * C;
+    const float* wr = wsumT + (size_t)cls * L * C + co;
+    float s0 = 0.f, s1 = 0.f;
+    int i = 0;
+    for (; i + 1 < L; i += 2) {
+      s0 = fmaf(__ldg(wr + (size_t)i * C), sz[i], s0);
+      s1 = fmaf(__ldg(wr + (size_t)(i + 1) * C), sz[i + 1], s1);
+    }
+    if (i < L) s0 = fmaf(__ldg(wr + (size_t)i * C), sz[i], s0);
+    u[(size_t)n * NCC + o] = s0 + s1;
   }
 }
 
@@ -217,8 +225,8 @@ int launch_sample_l1(Plan* p, const float* mu, const float* logvar, const float*
                      const float* z_in, float* act0, cudaStream_t st) {
   const IodineShape& s = p->s;
   const int ncc = p->n_class * p->C;
-  sample_u_kernel<<<p->BK, 128, s.L * sizeof(float), st>>>(mu, logvar, eps, z_in, p->wsum, p->z, p->u,
-                                                           s.L, ncc);
+  sample_u_kernel<<<p->BK, 256, s.L * sizeof(float), st>>>(mu, logvar, eps, z_in, p->wsumT, p->z, p->u,
+                                                           s.L, p->C, ncc);
   IOD_LAUNCH_CHECK(p);
   const int per = p->HW * (p->C / 4);
   dim3 grid((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256, p->BK);
@@ -432,12 +440,19 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __
 }
 
 // Gaussian.update (iodine.py:642-643): mu += delta[:, :L], logvar += delta[:, L:]
+// (delta arrives as `parts` split-K partial sums [parts][N][2L])
 __global__ void update_kernel(const float* __restrict__ delta, float* __restrict__ mu,
-                              float* __restrict__ logvar, int N, int L) {
+                              float* __restrict__ logvar, int N, int L, int parts) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * L; i += gridDim.x * blockDim.x) {
     const int n = i / L, j = i % L;
-    mu[i] += delta[(size_t)n * 2 * L + j];
-    logvar[i] += delta[(size_t)n * 2 * L + L + j];
+    float dm = 0.f, dl = 0.f;
+    for (int q = 0; q < parts; ++q) {
+      const float* d = delta + ((size_t)q * N + n) * 2 * L;
+      dm += d[j];
+      dl += d[L + j];
+    }
+    mu[i] += dm;
+    logvar[i] += dl;
   }
 }
 
@@ -460,12 +475,13 @@ int launch_head(Plan* p, float* mu, float* logvar, float* h, float* c, cudaStrea
   lstm_pointwise_kernel<<<(N * M + 255) / 256, 256, 0, st>>>(p->gates, h, c, N, M, LSTM_KSPLIT);
   IOD_LAUNCH_CHECK(p);
   {  // both heads read the CELL state (iodine.py:488-492); delta reuses the gates buffer
-    dim3 grid((2 * L + 63) / 64, (N + 15) / 16);
+    const int hk = ((M + LSTM_KSPLIT - 1) / LSTM_KSPLIT + 15) / 16 * 16;
+    dim3 grid((2 * L + 63) / 64, (N + 15) / 16, LSTM_KSPLIT);
     linear_kernel<0, 1><<<grid, 256, 0, st>>>(c, M, M, p->head_w, p->head_b, nullptr, 0, 0, nullptr, nullptr,
-                                              p->gates, 2 * L, N, 2 * L, M, 0);
+                                              p->gates, 2 * L, N, 2 * L, hk, (size_t)N * 2 * L);
     IOD_LAUNCH_CHECK(p);
   }
-  update_kernel<<<(N * L + 255) / 256, 256, 0, st>>>(p->gates, mu, logvar, N, L);
+  update_kernel<<<(N * L + 255) / 256, 256, 0, st>>>(p->gates, mu, logvar, N, L, LSTM_KSPLIT);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

@@ -301,7 +301,7 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
   }
   const size_t C = p->C, L = s.L, M = p->M, Cr = p->Cr, kk = (size_t)s.dec_k * s.dec_k,
                rkk = (size_t)s.ref_k * s.ref_k;
-  if (alloc_f(&p->wsum, kk * C * L) || alloc_f(&p->ptab, (size_t)p->HW * C)) return 1;
+  if (alloc_f(&p->wsum, kk * C * L) || alloc_f(&p->wsumT, kk * C * L) || alloc_f(&p->ptab, (size_t)p->HW * C)) return 1;
   for (int l = 1; l < s.dec_layers; ++l)
     if (alloc_f(&p->dec[l].w, kk * C * C) || alloc_f(&p->dec[l].wt, kk * C * C) || alloc_f(&p->dec[l].b, C)) return 1;
   if (alloc_f(&p->out_w, kk * C * 4) || alloc_f(&p->out_wt, kk * C * 4) || alloc_f(&p->out_b, 4)) return 1;
@@ -326,7 +326,7 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
 IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
   Plan* p = reinterpret_cast<Plan*>(plan);
   if (!p) return 0;
-  cudaFree(p->wsum); cudaFree(p->ptab);
+  cudaFree(p->wsum); cudaFree(p->wsumT); cudaFree(p->ptab);
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) {
     cudaFree(p->dec[l].w); cudaFree(p->dec[l].wt); cudaFree(p->dec[l].b);
     if (l < p->s.ref_layers) { cudaFree(p->ref_wp[l]); cudaFree(p->ref_b[l]); }

@@ -104,7 +104,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, u
       : "r"(addr))
 
 // ELU with the hardware exponential: |error| <= ~2e-7 absolute, far below bf16 rounding.
-__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+// Branch-free form with the flush-to-zero ex2 (the non-ftz __expf carries extra scaling instructions for
+// subnormals, and the ELU-heavy kernels are instruction-issue bound): max(v,0) + (2^(min(v,0) log2 e) - 1).
+__device__ __forceinline__ float elu_fast(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
+  return fmaxf(v, 0.f) + (e - 1.f);
+}
 
 
 }  // namespace iod
