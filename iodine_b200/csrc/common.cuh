@@ -150,7 +150,7 @@ struct Plan {
 };
 
 // split-K factor of the LSTM gate GEMM (head.cu); the gates buffer holds that many partial sums
-constexpr int LSTM_KSPLIT = 4;
+constexpr int LSTM_KSPLIT = 8;
 
 // tensor-core modes keep the decoder activations as 16-bit values (bf16 or fp16), chunk-planar
 inline bool tc_mode(const Plan* p) { return p->s.precision == IODINE_BF16 || p->s.precision == IODINE_FP16; }
