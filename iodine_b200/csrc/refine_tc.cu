@@ -299,7 +299,7 @@ static RtcState* rtc_state(Plan* p) { return reinterpret_cast<RtcState*>(p->rtc)
 static bool rtc_cfg(int Cr, int KS, int nks, int* tps, int* st) {
   if (KS == 3 && nks == 1) { *tps = 9; *st = 4; return true; }
   if (KS == 3 && nks == 2) { *tps = 3; *st = 6; return Cr == 32; }
-  if (KS == 3 && nks == 4) { *tps = 1; *st = 8; return Cr == 64; }
+  if (KS == 3 && nks == 4) { *tps = 3; *st = 3; return Cr == 64; }
   if (KS == 5 && nks == 1) { *tps = 5; *st = 6; return true; }
   if (KS == 5 && nks == 2) { *tps = 1; *st = 12; return Cr == 32; }
   return false;
@@ -468,7 +468,7 @@ int rtc_launch_refine_convs(Plan* p, cudaStream_t st_) {
     set_error("refine_tc: unsupported ref_chan=%d / K-steps %d", Cr, nks);
 #define RTC_CASE(n, ksz, k, tps, stg) if (Cr == n && s.ref_k == ksz && nks == k) rc = rtc_launch_t<n, k, tps, stg>(p, q, st_);
     RTC_CASE(64, 3, 1, 9, 4) RTC_CASE(32, 3, 1, 9, 4) RTC_CASE(16, 3, 1, 9, 4)
-    RTC_CASE(64, 3, 4, 1, 8) RTC_CASE(32, 3, 2, 3, 6)
+    RTC_CASE(64, 3, 4, 3, 3) RTC_CASE(32, 3, 2, 3, 6)
     RTC_CASE(64, 5, 1, 5, 6) RTC_CASE(32, 5, 1, 5, 6) RTC_CASE(16, 5, 1, 5, 6)
     RTC_CASE(32, 5, 2, 1, 12)
 #undef RTC_CASE
