@@ -63,7 +63,8 @@ struct TcMaps {                   // one source buffer: rows are fetched as runs
 struct alignas(64) TcParams {
   TcMaps maps;
   int32_t f16;                    // 1: IEEE half operands, 0: bfloat16
-  int32_t dbg;                    // IODINE_TC_DEBUG bit mask (timing experiments only; results are wrong when set)
+  int32_t dbg;                    // IODINE_TC_DEBUG bit mask (timing experiments only; results are wrong when set):
+                                  // 1 no TMEM reads, 2 no epilogue stores, 4 no TMA (generic producer), 8 no activation loads
   int32_t nch_in;                 // input planes
   int32_t nch_out;                // output planes (N/8) for the bf16 epilogues
   int32_t H, W;
@@ -371,8 +372,6 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     const bool prod_leader = elect_one_sync();
     int slot = 0;
     uint32_t phase = 0;
-    long long tp_wait = 0, tp_all0 = clock64();
-    int tp_rows = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int im = p.rev ? p.items - 1 - item : item;
       const int n = im / p.strips, y0 = (im - n * p.strips) * p.TH;
@@ -381,11 +380,8 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       for (int j = 0; j < nrows; ++j) {
         const uint32_t fb = smem_u32(&sb->full[slot]);
         const bool mirrored = slot < p.m;
-        ++tp_rows;
         if (prod_leader) {
-          const long long tw0 = clock64();
           mbar_wait(smem_u32(&sb->empty[slot]), phase ^ 1u, 1);
-          tp_wait += clock64() - tw0;
           if (p.dbg & 4) {
             mbar_arrive(fb);
           } else {
@@ -408,8 +404,6 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       }
     }
     __syncwarp();
-    if ((p.dbg & 16) && prod_leader && blockIdx.x == 0)
-      printf("conv_tc producer cta 0: rows %d total %lld cycles, waiting for free ring rows %lld\n", tp_rows, clock64() - tp_all0, tp_wait);
   } else if (RS && warp == 1) {
     // =============================================================== MMA issuer, row-streaming
     // One thread: input rows are consumed strictly in order, each exactly once.
@@ -423,14 +417,12 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         const int my_items = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         int slot = 0; uint32_t rph = 0;            // ring slot / phase of the next input row
         int qg = 0;                                // output rows (tiles) of all previous items of this CTA
-        long long t_full = 0, t_tempty = 0, t_issue = 0, t_all0 = clock64();   // dbg & 16: where the issuer's time goes
         for (int k = 0; k < my_items; ++k) {
           // Rows are handled in units of TC_RS_UNIT: all barrier waits of a unit first, then its MMAs back to
           // back.  A wait costs 70-150 cycles even when the barrier has long completed, and the tensor pipe's
           // instruction queue is short, so per-row waits left the pipe idle between rows.
           for (int j0 = 0; j0 < nrows; j0 += TC_RS_UNIT) {
             const int ju = (nrows - j0 < TC_RS_UNIT) ? nrows - j0 : TC_RS_UNIT;
-            long long tq0 = clock64();
             // lanes wait in parallel: lane u on the ring row of unit row u, lane 16+u on the accumulator slot
             // that row opens (a wait costs 70-150 cycles even when the barrier completed long ago)
             if (lane < ju) {
@@ -442,10 +434,6 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
               mbar_wait(smem_u32(&sb->tempty[qn & (ACC - 1)]), (((uint32_t)qn / ACC) & 1u) ^ 1u, 4);
             }
             __syncwarp();
-            long long tq1 = clock64();
-            t_full += tq1 - tq0;
-            long long tq2 = clock64();
-            t_tempty += tq2 - tq1;
             tc_fence_after();
             for (int u = 0; u < ju; ++u) {
               const int j = j0 + u;
@@ -479,13 +467,9 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
               __syncwarp();
               if (++slot == R) { slot = 0; rph ^= 1u; }
             }
-            t_issue += clock64() - tq2;
           }
           qg += TH;
         }
-        if ((p.dbg & 16) && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-          printf("conv_tc rs issuer cta %d: rows %d total %lld cycles: full-wait %lld tempty-wait %lld issue %lld\n", (int)blockIdx.x,
-                 my_items * nrows, clock64() - t_all0, t_full, t_tempty, t_issue);
       }
     }
   } else if (warp <= TC_ISSUERS) {
