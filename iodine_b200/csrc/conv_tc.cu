@@ -253,7 +253,6 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int pad = KS / 2;
   const int Ps = PS ? PS : p.Ps, R = p.R;
-  const int Q = R * Ps;
   const int F16 = p.f16;
 
   // ---- one-time setup: zero the ring (no stale NaN patterns under discarded positions),
