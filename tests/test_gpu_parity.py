@@ -237,3 +237,21 @@ def test_forward_loss_value_against_oracle(name):
     assert abs(loss.item() - want.item()) < TOL_INT * abs(want.item())
     for i in range(arch.ITERS):                                               # in-loop ELBOs vs the reference's own
         assert abs(elbos[i].item() - float(g['s%d_elbo' % i])) < 2e-5 * abs(float(g['s%d_elbo' % i]))
+
+
+@pytest.mark.parametrize('slots,prec', [(11, 'fp32'), (16, 'fp32'), (11, 'fp16')])
+def test_many_slots_against_oracle(slots, prec):
+    """K > 8 takes the 16-slot instantiation of the mixture kernel (BASELINE configs #4 / #5: K = 11 / 16)."""
+    arch = A.arch_by_name('tiny', slots=slots, iters=2)
+    B = 2
+    model = seeded_model(arch, 3.0, precision=prec).to(DEV)
+    sd = S.state_dict_to(seeded_model(arch, 3.0).state_dict(), torch.float32)
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(B, 3, arch.IMG_SIZE, arch.IMG_SIZE, generator=g)
+    eps = torch.randn(arch.ITERS + 1, B, slots, arch.DIM_LATENT, generator=g)
+    pred, mask, mean = model.reconstruct(x.to(DEV), eps=eps.to(DEV))
+    tr = S.encode_trace(sd, arch, x, eps)
+    assert rel_err(pred, tr['pred']) < TOL_OUT
+    assert rel_err(mask, tr['mask']) < TOL_OUT
+    want = torch.stack([s['elbo'] for s in tr['steps']])
+    assert rel_err(model.elbo_per_step(B), want) < TOL_OUT
