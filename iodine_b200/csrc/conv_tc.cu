@@ -77,6 +77,12 @@ struct alignas(64) TcParams {
   int32_t strips;                 // ceil(H / TH)
   int32_t items;                  // BK * strips (row-streaming: * rs_segs)
   int32_t rs_segs;                // row-streaming: 128-column segments per image row (an item is one of them)
+  // row-streaming work list: every CTA owns ONE contiguous range of the flattened (slot-image, segment, row)
+  // space, cut only at image boundaries -- items of up to H rows instead of TH-row strips: rows per CTA are
+  // balanced to +-1 (strips: 25 vs 24 per CTA at B = 32) and a CTA restarts the row stream 2-3 times per launch
+  // instead of 25 (each restart = KS-1 halo rows re-read and 2(KS-1) short, issue-bound MMA passes)
+  const int4* itab;               // {slot-image n, first row y0, rows th, first column xoff}
+  const int32_t* coff;            // [grid + 1] item range of CTA c
   int32_t rev;                    // walk the work items from the last to the first: consecutive layers alternate
                                   // direction so that a layer starts on what the previous one wrote last (still in L2)
   uint32_t idesc;
@@ -206,7 +212,17 @@ struct TcTileIter {
   int row, rem, seg;
   int xoff = 0;                                  // row-streaming: first image column of the item's 128-column segment
   int ps = 0;                                    // compile-time ring pitch of a specialised kernel (0: p.Ps)
+  int it_end = 0;                                // table mode (row-streaming): item = index into p.itab
   __device__ __forceinline__ void load_item(const TcParams& p) {
+    if (p.itab) {
+      if (item < it_end) {
+        const int4 d = __ldg(p.itab + item);
+        n = d.x; y0 = d.y; th = d.z; xoff = d.w;
+        ntiles = th;                               // one 128-column tile per row
+      }
+      t = 0; row = 0; rem = 0; seg = 0;
+      return;
+    }
     if (item < p.items) {
       const int im = p.rev ? p.items - 1 - item : item;
       int rest = im;
@@ -218,11 +234,16 @@ struct TcTileIter {
     }
     t = 0; row = 0; rem = 0; seg = 0;
   }
-  __device__ __forceinline__ void init(const TcParams& p) { item = blockIdx.x; load_item(p); }
-  __device__ __forceinline__ bool valid(const TcParams& p) const { return item < p.items; }
+  __device__ __forceinline__ void init(const TcParams& p) {
+    if (p.itab) { item = __ldg(p.coff + blockIdx.x); it_end = __ldg(p.coff + blockIdx.x + 1); }
+    else item = blockIdx.x;
+    load_item(p);
+  }
+  __device__ __forceinline__ bool valid(const TcParams& p) const { return p.itab ? item < it_end : item < p.items; }
   __device__ __forceinline__ bool last_of_item() const { return t + 1 >= ntiles; }
   __device__ __forceinline__ void next(const TcParams& p) {
-    if (++t >= ntiles) { item += gridDim.x; load_item(p); return; }
+    if (++t >= ntiles) { item += p.itab ? 1 : (int)gridDim.x; load_item(p); return; }
+    if (p.itab) { ++row; return; }
     const int Ps = ps ? ps : p.Ps;
     if (p.segs) {
       if (++seg == p.segs) { seg = 0; rem = 0; ++row; } else rem += 128;
@@ -313,11 +334,10 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       int slot = 0;
       uint32_t phase = 0;
       if (prod_leader) {
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-          const int im = p.rev ? p.items - 1 - item : item;
-          const int rest = im / segs, seg = im - rest * segs;
-          const int n = rest / p.strips, y0 = (rest - n * p.strips) * p.TH;
-          const int nrows = p.TH + 2 * pad;
+        for (int item = __ldg(p.coff + blockIdx.x), it_end = __ldg(p.coff + blockIdx.x + 1); item < it_end; ++item) {
+          const int4 d = __ldg(p.itab + item);
+          const int n = d.x, y0 = d.y, seg = d.w >> 7;
+          const int nrows = d.z + 2 * pad;
           // columns copied per row: the segment plus the neighbouring pixel on every side that lies inside the
           // image; a side on the image border keeps ring halo zeros (W > 128: re-zeroed per row, the slot may
           // have held a row of another segment)
@@ -412,11 +432,11 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         mbar_wait(smem_u32(&sb->wbar), 0, 2);
         const uint32_t a_base16 = smem_u32(s_a) >> 4;
         const uint32_t w_base16 = smem_u32(s_w) >> 4;
-        const int TH = p.TH, nrows = TH + 2 * pad;
-        const int my_items = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         int slot = 0; uint32_t rph = 0;            // ring slot / phase of the next input row
         int qg = 0;                                // output rows (tiles) of all previous items of this CTA
-        for (int k = 0; k < my_items; ++k) {
+        for (int item = __ldg(p.coff + blockIdx.x), it_end = __ldg(p.coff + blockIdx.x + 1); item < it_end; ++item) {
+          const int TH = __ldg(p.itab + item).z;   // rows of this item (1 .. H)
+          const int nrows = TH + 2 * pad;
           // Rows are handled in units of TC_RS_UNIT: all barrier waits of a unit first, then its MMAs back to
           // back.  A wait costs 70-150 cycles even when the barrier has long completed, and the tensor pipe's
           // instruction queue is short, so per-row waits left the pipe idle between rows.
@@ -599,8 +619,14 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     TcTileIter far;
     far.ps = PS;
     far.init(p);
-    const int my_items_e = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int ntotal = (my_items_e > 0 ? my_items_e : 0) * p.NT;
+    int ntotal;                                    // tiles this CTA writes
+    if (p.itab) {
+      ntotal = 0;
+      for (int i = __ldg(p.coff + blockIdx.x); i < __ldg(p.coff + blockIdx.x + 1); ++i) ntotal += __ldg(p.itab + i).z;
+    } else {
+      const int my_items_e = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      ntotal = (my_items_e > 0 ? my_items_e : 0) * p.NT;
+    }
     long long pix = -1, pix1 = -1, pix2 = -1, pix3 = -1;
     int cn = 0, cn1 = 0, cn2 = 0, cn3 = 0;
     uint4 av[NAV], av1[NAV], av2[NAV], av3[NAV];
@@ -719,6 +745,9 @@ struct TcState {
   uint16_t* w_bwd_rs[IODINE_MAX_LAYERS];
   uint16_t* w_out_rs = nullptr;
   void* zero_row = nullptr;              // W x 16 zero bytes
+  int4* itab = nullptr;                  // row-streaming work list (device)
+  int32_t* coff = nullptr;
+  int rs_grid = 0;
   TcGeom g_cc_rs, g_out_rs;
   bool attr_done = false;
 };
@@ -839,6 +868,32 @@ int tc_alloc(Plan* p) {
     IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_out_rs, st->g_out_rs.w_bytes));
     IOD_CHECK_CUDA(cudaMalloc(&st->zero_row, 4096));
     IOD_CHECK_CUDA(cudaMemset(st->zero_row, 0, 4096));
+    // work list: CTA c owns units [c U / G, (c+1) U / G) of the flattened (slot-image, segment, row) space
+    {
+      const int segs = s.W / 128;
+      const long long U = (long long)p->BK * segs * s.H;
+      const int G = (int)(U < p->num_sms ? U : p->num_sms);
+      std::vector<int4> items;
+      std::vector<int32_t> off(G + 1);
+      for (int c = 0; c < G; ++c) {
+        off[c] = (int32_t)items.size();
+        long long u0 = U * c / G;
+        const long long u1 = U * (c + 1) / G;
+        while (u0 < u1) {
+          const long long col = u0 / s.H;
+          const int y0 = (int)(u0 - col * s.H);
+          const int th = (int)((s.H - y0 < u1 - u0) ? (s.H - y0) : (u1 - u0));
+          items.push_back(make_int4((int)(col / segs), y0, th, (int)(col % segs) * 128));
+          u0 += th;
+        }
+      }
+      off[G] = (int32_t)items.size();
+      st->rs_grid = G;
+      IOD_CHECK_CUDA(cudaMalloc((void**)&st->itab, items.size() * sizeof(int4)));
+      IOD_CHECK_CUDA(cudaMalloc((void**)&st->coff, off.size() * sizeof(int32_t)));
+      IOD_CHECK_CUDA(cudaMemcpy(st->itab, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      IOD_CHECK_CUDA(cudaMemcpy(st->coff, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
   }
   for (int l = 1; l < s.dec_layers; ++l) {
     IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd[l], st->g_cc.w_bytes));
@@ -858,6 +913,8 @@ void tc_free(Plan* p) {
   }
   cudaFree(st->w_out_rs);
   cudaFree(st->zero_row);
+  cudaFree(st->itab);
+  cudaFree(st->coff);
   cudaFree(st->w_out); cudaFree(st->w_in4); cudaFree(st->ptab_c);
   delete st;
   p->tc = nullptr;
@@ -988,6 +1045,8 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->strips = (s.H + g.TH - 1) / g.TH;
   q->rs_segs = 0;
   q->rev = 0;
+  q->itab = nullptr;
+  q->coff = nullptr;
   q->items = p->BK * q->strips;
   q->idesc = make_idesc(N, s.precision == IODINE_FP16);
   for (int c = 0; c < 8; ++c) q->idesc_n[c] = (c >= 1 && c * N <= 256) ? make_idesc(c * N, s.precision == IODINE_FP16) : 0u;
@@ -1113,7 +1172,7 @@ int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* a
   TcParams q;
   q.maps = *map;
   fill_common(p, st->rs ? st->g_cc_rs : st->g_cc, p->C / 8, p->C, &q);
-  if (st->rs) { q.rs_segs = p->s.W / 128; q.items *= q.rs_segs; }
+  if (st->rs) { q.rs_segs = p->s.W / 128; q.items = st->rs_grid; q.itab = st->itab; q.coff = st->coff; }
   // traversal direction: read a buffer in the opposite direction to the one it was written in (the collapsed
   // first layer and the 4->C data-gradient write ascending), so that the freshest ~100 MB are still L2 hits
   if (!getenv("IODINE_TC_NO_REV")) q.rev = dgrad ? ((p->s.dec_layers - 1 - layer) % 2 == 0) : (layer % 2 == 1);
@@ -1138,7 +1197,7 @@ int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st_) {
   TcParams q;
   q.maps = *map;
   fill_common(p, st->rs ? st->g_out_rs : st->g_out, p->C / 8, 16, &q);
-  if (st->rs) { q.rs_segs = p->s.W / 128; q.items *= q.rs_segs; }
+  if (st->rs) { q.rs_segs = p->s.W / 128; q.items = st->rs_grid; q.itab = st->itab; q.coff = st->coff; }
   if (!getenv("IODINE_TC_NO_REV")) q.rev = ((p->s.dec_layers - 1) % 2 == 0);   // opposite to the last forward layer (or to layer 1)
   q.wimg = st->rs ? st->w_out_rs : st->w_out;
   q.bias = p->out_b;
