@@ -210,6 +210,13 @@ def run_native(args):
     eps_host = torch.randn(T + 1, B, K, L, generator=torch.Generator().manual_seed(123 + rank)).pin_memory()
     x, eps = x_host.to(dev), eps_host.to(dev)
     eng = model.state_for_debug(B)
+    comms = []
+    if world > 1:
+        # the path's only exchange -- the [T,2] ELBO partial sums -- is one ncclAllReduce issued by the library on
+        # the stream of the call (iodine_plan_set_comm); one communicator per plan / stream
+        from iodine_b200.parallel import NcclComm
+        comms.append(NcclComm())
+        eng.set_comm(comms[0], rank, world)
     pin = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
     host_out = dict(pred=pin(B, 3, S, S), mask=pin(B, K, 1, S, S), mean=pin(B, K, 3, S, S),
                     z=pin(B, K, L), terms=pin(T, 2))
@@ -221,17 +228,11 @@ def run_native(args):
             torch.cuda.synchronize()
 
     def step_device():
-        z, terms, _ = eng.encode(x, eps)
-        if world > 1:                      # the path's only exchange: ELBO partial sums
-            dist.all_reduce(terms)
+        z, terms, _ = eng.encode(x, eps)     # world > 1: terms come back all-reduced (in-stream NCCL)
         return terms
 
     def step_host():
-        out = eng.reconstruct_host(x_host, eps_host, host_out)   # synchronises
-        if world > 1:
-            t = out['terms'].to(dev)
-            dist.all_reduce(t)
-        return out
+        return eng.reconstruct_host(x_host, eps_host, host_out)   # synchronises; terms all-reduced before the D2H copy
 
     def max_over_ranks(v):
         if world == 1:
@@ -282,6 +283,9 @@ def run_native(args):
     model_b.load_state_dict(model.state_dict())
     model_b.max_images_per_call = B
     engs = [eng, model_b.state_for_debug(B)]
+    if world > 1:
+        comms.append(NcclComm())
+        engs[1].set_comm(comms[1], rank, world)
     streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
     xs = [x_host, x_host.clone().pin_memory()]
     epss = [eps_host, eps_host.clone().pin_memory()]
@@ -302,9 +306,6 @@ def run_native(args):
             if pending[j]:
                 streams[j].synchronize()
                 consumed[0] += float(outs[j]['terms'][0, 0])
-        if world > 1:
-            tt = outs[0]['terms'].to(dev)
-            dist.all_reduce(tt)
 
     host_steps = 1 if args.profile_mode else args.steps
     if not args.profile_mode:

@@ -160,6 +160,17 @@ IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_ho
                                   float* pred_host, float* mask_host, float* mean_host,
                                   float* z_host, float* elbo_terms_host, void* stream);
 
+/* Multi-GPU (replaces torch.nn.DataParallel, lib/modeling/build.py:11-12, and the replica-mean of
+ * lib/engine/train.py:61).  The path shards by whole images, one process and one plan per GPU; every K-way reduction
+ * is inside one image, so the ONLY cross-rank quantity is the [T,2] table of batch sums behind the ELBO means
+ * (iodine.py:193, 220).  After this call iodine_encode / iodine_reconstruct / iodine_reconstruct_host[_async]
+ * sum that table over the communicator with one ncclAllReduce on the caller's stream (stream-ordered, no host
+ * synchronisation) before they return it; nothing else crosses ranks.  All ranks must make the same calls, with
+ * elbo_terms_out given on all of them or on none.  iodine_refine_step / iodine_elbo stay rank-local.
+ *   nccl_comm: an ncclComm_t of the calling process (NULL uninstalls); NCCL is resolved from the process at run
+ *   time (dlopen of libnccl.so.2), the library does not link against it. */
+IODINE_API int iodine_plan_set_comm(IodinePlan* plan, void* nccl_comm, int32_t rank, int32_t nranks);
+
 /* Evaluator tail: lib/eval/ari_eval.py:32-39 (argmax over the K predicted masks) +
  * lib/utils/ari.py:36-54 (contingency table) + lib/utils/ari.py:6-33 (ARI), per image, on the device.
  *   mask[B,K,H,W] fp32 (IODINE.reconstruct's mask); gt_masks[B,G,H,W] uint8 (the reference's mask.byte(), padded

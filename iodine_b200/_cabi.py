@@ -19,6 +19,7 @@ EXPORTS = [
     'iodine_init_state', 'iodine_refine_step', 'iodine_elbo', 'iodine_encode', 'iodine_decode',
     'iodine_reconstruct', 'iodine_reconstruct_host', 'iodine_reconstruct_host_async', 'iodine_debug_read',
     'iodine_plan_launch_count', 'iodine_plan_profile', 'iodine_plan_profile_read', 'iodine_ari',
+    'iodine_plan_set_comm',
 ]
 
 
@@ -83,6 +84,7 @@ def load():
         'iodine_plan_profile': [vp, i32],
         'iodine_plan_profile_read': [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
         'iodine_ari': [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+        'iodine_plan_set_comm': [vp, vp, i32, i32],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

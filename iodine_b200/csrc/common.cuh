@@ -78,6 +78,8 @@ struct Plan {
   int ref_w[IODINE_MAX_LAYERS + 1];
   uint64_t launches = 0;
   bool weights_set = false;
+  void* comm = nullptr;       // ncclComm_t installed by iodine_plan_set_comm (nullptr: single rank)
+  int comm_rank = 0, comm_nranks = 1;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
   size_t prof_used = 0;

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <dlfcn.h>
 
 #include "common.cuh"
 
@@ -249,6 +250,50 @@ static int do_encode_g(Plan* p, const float* x, const float* eps, float* z_out, 
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cross-rank exchange: the path shards by whole images, so the only quantity that
+// crosses ranks is the [T,2] table of (sum_b log-likelihood, sum_b KL) behind the ELBO means of
+// iodine.py:193,220.  It is summed with ONE ncclAllReduce on the caller's stream after the loop.
+// NCCL is resolved at run time from the process (the host application -- torch here -- already
+// carries libnccl.so.2), so the library has no link-time dependency on it and single-rank users
+// never load it.  Prototype and enum values: nccl.h (ncclFloat32 = 7, ncclSum = 0, ncclSuccess = 0).
+// ------------------------------------------------------------------------------------------------
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+static nccl_allreduce_fn g_nccl_allreduce = nullptr;
+static nccl_errstr_fn g_nccl_errstr = nullptr;
+
+static int resolve_nccl() {
+  if (g_nccl_allreduce) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the copy the host process already uses
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    set_error("iodine_plan_set_comm: cannot load libnccl.so.2 (%s)", dlerror());
+    return 1;
+  }
+  g_nccl_allreduce = reinterpret_cast<nccl_allreduce_fn>(dlsym(h, "ncclAllReduce"));
+  g_nccl_errstr = reinterpret_cast<nccl_errstr_fn>(dlsym(h, "ncclGetErrorString"));
+  if (!g_nccl_allreduce) {
+    set_error("iodine_plan_set_comm: libnccl has no ncclAllReduce");
+    return 1;
+  }
+  return 0;
+}
+
+// sum the per-step table over the communicator (no-op for a single rank or a null table)
+static int reduce_terms(Plan* p, float* terms, cudaStream_t st) {
+  if (!p->comm || !terms) return 0;
+  const int rc = g_nccl_allreduce(terms, terms, (size_t)p->s.T * 2, /*ncclFloat32*/ 7, /*ncclSum*/ 0, p->comm, st);
+  if (rc != 0) {
+    set_error("ncclAllReduce of the ELBO table failed on rank %d/%d: %s", p->comm_rank, p->comm_nranks,
+              g_nccl_errstr ? g_nccl_errstr(rc) : "?");
+    return 1;
+  }
+  return 0;
+}
+
 static int do_decode(Plan* p, const float* z, float* pred, float* mask, float* mean, cudaStream_t st) {
   if (decoder_forward(p, nullptr, nullptr, nullptr, z, st)) return 1;
   return launch_recombine(p, pred, mask, mean, st);
@@ -409,7 +454,21 @@ IODINE_API int iodine_encode(IodinePlan* plan, const float* x, const float* eps,
   Plan* p = reinterpret_cast<Plan*>(plan);
   if (check_ready(p)) return 1;
   IOD_REQUIRE(x && eps && z_out, "null tensor argument");
-  return do_encode_g(p, x, eps, z_out, elbo_terms_out, post_out, (cudaStream_t)stream);
+  if (do_encode_g(p, x, eps, z_out, elbo_terms_out, post_out, (cudaStream_t)stream)) return 1;
+  return reduce_terms(p, elbo_terms_out, (cudaStream_t)stream);
+}
+
+IODINE_API int iodine_plan_set_comm(IodinePlan* plan, void* nccl_comm, int32_t rank, int32_t nranks) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  IOD_REQUIRE(p, "null plan");
+  if (!nccl_comm) {
+    p->comm = nullptr; p->comm_rank = 0; p->comm_nranks = 1;
+    return 0;
+  }
+  IOD_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "iodine_plan_set_comm: rank %d outside [0, %d)", rank, nranks);
+  if (resolve_nccl()) return 1;
+  p->comm = nccl_comm; p->comm_rank = rank; p->comm_nranks = nranks;
+  return 0;
 }
 
 IODINE_API int iodine_decode(IodinePlan* plan, const float* z, float* pred_out, float* mask_out, float* mean_out,
@@ -428,6 +487,7 @@ IODINE_API int iodine_reconstruct(IodinePlan* plan, const float* x, const float*
   IOD_REQUIRE(x && eps, "null tensor argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (do_encode_g(p, x, eps, p->st_z, elbo_terms_out, nullptr, st)) return 1;
+  if (reduce_terms(p, elbo_terms_out, st)) return 1;
   if (z_out)
     IOD_CHECK_CUDA(cudaMemcpyAsync(z_out, p->st_z, (size_t)p->BK * p->s.L * sizeof(float),
                                    cudaMemcpyDeviceToDevice, st));
@@ -446,6 +506,7 @@ IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_ho
   IOD_CHECK_CUDA(cudaMemcpyAsync(p->hx, x_host, (size_t)s.B * 3 * HW * sizeof(float), cudaMemcpyHostToDevice, st));
   IOD_CHECK_CUDA(cudaMemcpyAsync(p->heps, eps_host, (size_t)(s.T + 1) * BK * s.L * sizeof(float), cudaMemcpyHostToDevice, st));
   if (do_encode_g(p, p->hx, p->heps, p->st_z, p->st_terms, nullptr, st)) return 1;
+  if (reduce_terms(p, p->st_terms, st)) return 1;
   if (do_decode(p, p->st_z, pred_host ? p->hpred : nullptr, mask_host ? p->hmask : nullptr,
                 mean_host ? p->hmean : nullptr, st))
     return 1;

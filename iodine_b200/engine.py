@@ -221,6 +221,14 @@ class RefinementEngine:
                                                    C.byref(need), _stream()))
         return buf.view(dtype)
 
+    def set_comm(self, comm, rank=0, nranks=1):
+        """Install (or, with ``comm=None``, remove) an NCCL communicator: afterwards encode()/reconstruct()
+        return the per-step ``[T,2]`` sums all-reduced over its ranks (``iodine_plan_set_comm``).
+        ``comm`` is an ``iodine_b200.parallel.NcclComm`` or a raw ``ncclComm_t`` address."""
+        handle = getattr(comm, 'handle', comm)
+        self._comm_keep = comm                      # the communicator must outlive the plan's use of it
+        _cabi.check(self.lib.iodine_plan_set_comm(self._plan, C.c_void_p(handle or None), int(rank), int(nranks)))
+
     def launch_count(self):
         n = C.c_uint64()
         _cabi.check(self.lib.iodine_plan_launch_count(self._plan, C.byref(n)))

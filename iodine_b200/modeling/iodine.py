@@ -118,6 +118,7 @@ class IODINE(nn.Module):
         self.mask = None
         self.elbo_terms = None      # [T,2]: (sum_b log-lik, sum_b KL) per refinement step
         self._engines = {}
+        self._comm = None           # (NcclComm, rank, nranks) installed by set_comm()
         self._weights_sig = {}
         self.max_images_per_call = None   # None = automatic (fit the workspace in free HBM)
 
@@ -142,12 +143,23 @@ class IODINE(nn.Module):
                 self._engines.pop(old).close()
                 self._weights_sig.pop(old, None)
             eng = RefinementEngine(self.arch, B, dev, self.precision)
+            if self._comm is not None:
+                eng.set_comm(*self._comm)
             self._engines[key] = eng
         sig = self._sig()
         if self._weights_sig.get(key) != sig:
             eng.set_weights(self.state_dict())
             self._weights_sig[key] = sig
         return eng
+
+    def set_comm(self, comm, rank=0, nranks=1):
+        """Multi-GPU (replaces DataParallel, lib/modeling/build.py:11-12): with an ``iodine_b200.parallel.NcclComm``
+        installed, ``elbo_terms`` of encode()/reconstruct() are the sums over ALL ranks' images -- one in-stream
+        ncclAllReduce per engine call (``iodine_plan_set_comm``).  Every rank must then make the same number of
+        engine calls (``SlotShard`` checks this).  ``comm=None`` removes it."""
+        self._comm = None if comm is None else (comm, int(rank), int(nranks))
+        for eng in self._engines.values():
+            eng.set_comm(comm, rank, nranks)
 
     def _chunk(self, B):
         if self.max_images_per_call:

@@ -17,6 +17,8 @@ Equal shards reproduce DataParallel's "mean of replica means" exactly; unequal s
 multiple of the world size) still give the exact GLOBAL mean here, which is the better-defined
 quantity (DataParallel's differs in that case).
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -34,6 +36,55 @@ def shard_table(B, world):
     return [shard_bounds(B, world, r) for r in range(world)]
 
 
+class NcclComm:
+    """An ``ncclComm_t`` of this process for ``iodine_plan_set_comm`` (include/iodine_b200.h): the library then sums
+    the ``[T,2]`` ELBO table with one ``ncclAllReduce`` on the stream of the call -- no host round trip, and no torch
+    on the data path.  torch does not expose the communicators behind ``torch.distributed``, so this creates one
+    with the same NCCL library the process already loaded (torch's ``libnccl.so.2``): rank 0 draws the unique id,
+    ``torch.distributed`` (any backend) carries its 128 bytes to the other ranks, every rank joins with
+    ``ncclCommInitRank`` on its current CUDA device.  A C/C++ host does the same with its own bootstrap.
+    """
+
+    class _UniqueId(C.Structure):                  # ncclUniqueId: 128 opaque bytes (nccl.h)
+        _fields_ = [('internal', C.c_byte * 128)]
+
+    def __init__(self, rank=None, world=None, group=None):
+        distributed = dist.is_available() and dist.is_initialized()
+        self.rank = (dist.get_rank(group) if distributed else 0) if rank is None else int(rank)
+        self.world = (dist.get_world_size(group) if distributed else 1) if world is None else int(world)
+        if not torch.cuda.is_available():
+            raise RuntimeError('NcclComm needs a CUDA device (NCCL communicators are per GPU)')
+        torch.cuda.current_device()                # make sure the CUDA context of this rank's device exists
+        try:
+            self._nccl = C.CDLL('libnccl.so.2')
+        except OSError as e:
+            raise RuntimeError('cannot load libnccl.so.2: %s' % e)
+        self._nccl.ncclGetErrorString.restype = C.c_char_p
+        uid = NcclComm._UniqueId()
+        if self.rank == 0:
+            self._ok(self._nccl.ncclGetUniqueId(C.byref(uid)), 'ncclGetUniqueId')
+        if self.world > 1:
+            if not distributed:
+                raise RuntimeError('NcclComm with world > 1 needs torch.distributed to carry the unique id')
+            box = [bytes(uid.internal) if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group else 0, group=group)
+            C.memmove(C.byref(uid), box[0], 128)
+        comm = C.c_void_p()
+        self._nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, NcclComm._UniqueId, C.c_int]
+        self._ok(self._nccl.ncclCommInitRank(C.byref(comm), self.world, uid, self.rank), 'ncclCommInitRank')
+        self.handle = comm.value
+
+    def _ok(self, rc, what):
+        if rc != 0:
+            raise RuntimeError('%s failed: %s' % (what, self._nccl.ncclGetErrorString(rc).decode()))
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self._nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+            self._nccl.ncclCommDestroy(C.c_void_p(self.handle))
+            self.handle = None
+
+
 class SlotShard:
     """Wraps an ``IODINE``-like model (anything with ``reconstruct(x, eps=)`` / ``encode(x, eps=)``
     that leaves the per-step ``[T,2]`` sums in ``.elbo_terms``) for one-process-per-GPU use.
@@ -43,7 +94,10 @@ class SlotShard:
     only its shard (e.g. a DistributedSampler-fed loader).
     """
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, native_comm='auto'):
+        """``native_comm``: let the library all-reduce the ``[T,2]`` table itself on the stream of the call
+        (``iodine_plan_set_comm`` + ``NcclComm``) instead of a ``torch.distributed`` all-reduce afterwards.
+        ``'auto'`` = when the process group runs on NCCL and the model offers ``set_comm``."""
         self.model = model
         self.group = group
         self.distributed = dist.is_available() and dist.is_initialized()
@@ -51,6 +105,15 @@ class SlotShard:
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.global_batch = None
         self.elbo_terms = None          # [T,2] global sums after the all-reduce
+        if native_comm == 'auto':
+            native_comm = (self.world > 1 and hasattr(model, 'set_comm')
+                           and 'nccl' in str(dist.get_backend(group)).lower())
+        self.native = bool(native_comm) and self.world > 1
+        self._comm = None
+        self._calls_checked = set()
+        if self.native:
+            self._comm = NcclComm(group=group)
+            model.set_comm(self._comm, self.rank, self.world)
 
     # ------------------------------------------------------------------ plumbing
     def _local(self, x, eps, local):
@@ -68,10 +131,24 @@ class SlotShard:
                              'world size (K-split mode is not implemented)' % (self.rank, self.world, B))
         return x[b0:b1], (None if eps is None else eps[:, b0:b1])
 
+    def _check_calls(self, n_local):
+        """native mode: the library all-reduces once per engine call, so every rank must make the same number of
+        calls (the model chunks a shard that does not fit HBM); checked once per local batch size."""
+        if not self.native or n_local in self._calls_checked or not hasattr(self.model, '_spans'):
+            return
+        n = len(self.model._spans(n_local))
+        t = torch.tensor([n, -n], dtype=torch.int64, device=self.model._device())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        if int(t[0]) != -int(t[1]):
+            raise RuntimeError('ranks would split their shards into different numbers of engine calls (%d..%d); set '
+                               'model.max_images_per_call so that they agree, or use native_comm=False'
+                               % (-int(t[1]), int(t[0])))
+        self._calls_checked.add(n_local)
+
     def _reduce_terms(self):
         t = self.model.elbo_terms
         t = t.clone() if isinstance(t, torch.Tensor) else torch.as_tensor(t)
-        if self.world > 1:
+        if self.world > 1 and not self.native:
             dist.all_reduce(t, group=self.group)     # the path's single exchange: [T,2] sums
         self.elbo_terms = t
         return t
@@ -96,6 +173,7 @@ class SlotShard:
     # ------------------------------------------------------------------ API (mirrors IODINE)
     def encode(self, x, eps=None, local=False, gather=False):
         xl, el = self._local(x, eps, local)
+        self._check_calls(xl.shape[0])
         z = self.model.encode(xl, eps=el)
         self._reduce_terms()
         return self._gather(z) if gather else z
@@ -103,6 +181,7 @@ class SlotShard:
     def reconstruct(self, x, eps=None, local=False, gather=False):
         """Returns this rank's (pred, mask, mean) -- or the global ones with ``gather=True``."""
         xl, el = self._local(x, eps, local)
+        self._check_calls(xl.shape[0])
         pred, mask, mean = self.model.reconstruct(xl, eps=el)
         self._reduce_terms()
         if gather:
