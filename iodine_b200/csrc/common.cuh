@@ -211,6 +211,7 @@ int tc_export_seed(Plan* p, const void* seed8, float* dst, cudaStream_t st);
 // sums of the last data-gradient (its inverse)
 int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st);
 int tc_launch_class_sum(Plan* p, const void* g, cudaStream_t st);
+int tc_dsum_fused(const Plan* p);   // 1: tc_launch_conv(..., G) of the last data-gradient layer produces the class sums itself
 
 // ------------------------------------------------------------------ refine_tc.cu (tcgen05 refinement encoder)
 int rtc_supported(const Plan* p);

@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include <type_traits>
 #include "tc_ptx.cuh"
 
 namespace iod {
@@ -53,7 +54,9 @@ constexpr int TC_ACC_STAGES = 4;
 constexpr int TC_RS_UNIT = 5;        // input rows per issue unit of the row-streaming variant (<= 16, < ring rows)
 constexpr int TC_RS_SLOTS = 8;       // accumulator slots of the row-streaming variant (one per output row in flight)
 
-enum TcEpi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_OUT4 = 2 };
+// EPI_DSUM: data-gradient whose output is not stored but reduced over the border classes of the collapsed first
+// layer straight from the accumulators (row-streaming kernels only; replaces EPI_DGRAD + tc_class_sum_kernel)
+enum TcEpi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_OUT4 = 2, EPI_DSUM = 3 };
 
 struct TcMaps {                   // one source buffer: rows are fetched as runs of 128 pixels
   CUtensorMap full;               // 4-D {2W (8-byte elements), H, planes, BK}, box 256 elements
@@ -97,7 +100,10 @@ struct alignas(64) TcParams {
   const uint4* in;                // row-streaming: chunk-planar source activation (1-D bulk row copies)
   const uint4* zero_row;          // row-streaming: W x 16 zero bytes (rows outside the image)
   const float* bias;              // [N] (EPI_FWD, EPI_OUT4)
-  const uint4* actp;              // chunk-planar previous activation (EPI_DGRAD)
+  const uint4* actp;              // chunk-planar previous activation (EPI_DGRAD, EPI_DSUM)
+  float* G;                       // [n][3*3][N] class sums (EPI_DSUM), accumulated with atomics
+  int32_t apf;                    // row-streaming data-gradients: producers prefetch the saved activation into L2
+  int32_t lead;                   // row-streaming producers: at most this many ring rows ahead of the consumer (0: ring depth)
   void* out;                      // chunk-planar bf16 (uint4 per position-plane) or fp32 out4
 };
 
@@ -254,6 +260,29 @@ struct TcTileIter {
   }
 };
 
+// Transposed warp reduction: every lane holds NV values (NV = 32 or 16); afterwards lane (j << log2(32/NV)) -- and
+// the lanes that differ from it in the low log2(32/NV) bits -- holds in v[0] the sum over all 32 lanes of value j.
+// In the round with lane mask M, lanes with that bit clear keep the lower half of the surviving values and send the
+// upper half (and vice versa): 31 shuffles for NV = 32 instead of 5 per value.
+template <int NV, int M>
+__device__ __forceinline__ void tc_transposed_sum(float* v, int lane) {
+  if constexpr (M >= 1) {
+    if constexpr (NV > 1) {
+      const bool up = (lane & M) != 0;
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        const float send = up ? v[i] : v[i + NV / 2];
+        const float keep = up ? v[i + NV / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+      }
+      tc_transposed_sum<NV / 2, M / 2>(v, lane);
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], M);
+      tc_transposed_sum<1, M / 2>(v, lane);
+    }
+  }
+}
+
 // PS / PST16: ring pitch and plane stride as compile-time constants (0 = read them from the parameters).
 // RS: row-streaming variant (W == 128, one tile per output row): see tc_issue_row.
 template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS>
@@ -333,6 +362,12 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       const int segs = p.rs_segs > 1 ? p.rs_segs : 1;
       int slot = 0;
       uint32_t phase = 0;
+      // run-ahead cap: before row g is requested, row g - lead must have been consumed.  Everything the ring lets
+      // the producers request sits in the memory system's queues in front of the epilogue's own loads (saved
+      // activation), so a full ring (9 rows x 16 KB per SM) costs those loads microseconds of queueing.
+      const int lead = (p.lead > 0 && p.lead < R) ? p.lead : 0;
+      int g_row = 0, slot2 = 0;
+      uint32_t phase2 = 0;
       if (prod_leader) {
         for (int item = __ldg(p.coff + blockIdx.x), it_end = __ldg(p.coff + blockIdx.x + 1); item < it_end; ++item) {
           const int4 d = __ldg(p.itab + item);
@@ -349,6 +384,11 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
           for (int j = 0; j < nrows; ++j) {
             const uint32_t fb = smem_u32(&sb->full[slot]);
             mbar_wait(smem_u32(&sb->empty[slot]), phase ^ 1u, 1);
+            if (lead && g_row >= lead) {
+              mbar_wait(smem_u32(&sb->empty[slot2]), phase2, 1);
+              if (++slot2 == R) { slot2 = 0; phase2 ^= 1u; }
+            }
+            ++g_row;
             mbar_expect_tx(fb, per_plane * (uint32_t)(c_hi - c_lo));              // (arrives even with no plane)
             const int y = y0 - pad + j;
             const bool inside = y >= 0 && y < p.H;
@@ -362,6 +402,17 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
               if (zr) bulk_load_1d(dst + (uint32_t)(pad + 128) * 16u, p.zero_row, (uint32_t)pad * 16u, fb);
               src += sstep;
               dst += plane_bytes;
+            }
+            // The epilogue multiplies output row y by ELU' of the saved activation: it loads that row with plain
+            // loads about a ring depth + a TMEM queue later.  Those loads queue behind everything the producers
+            // have requested (microseconds under load), which three tiles of register prefetch do not cover --
+            // pull the row into L2 now.
+            if (p.apf && inside && j >= pad && j < nrows - pad) {
+              const uint4* ap = p.actp + ((size_t)n * p.nch_out + c_lo) * plane_px + (size_t)y * p.W + seg * 128;
+              for (int c = c_lo; c < c_hi; ++c) {
+                bulk_prefetch_l2(ap, 128u * 16u);
+                ap += plane_px;
+              }
             }
             if (++slot == R) { slot = 0; phase ^= 1u; }
           }
@@ -591,12 +642,14 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     const int k0 = col0 / 8;                       // first output plane
     const int H = p.H, W = p.W;
     const size_t plane_sz = (size_t)H * W;
+    constexpr bool DG = (EPI == EPI_DGRAD || EPI == EPI_DSUM);   // epilogues that read the saved activation
+    static_assert(EPI != EPI_DSUM || (RS && KS == 3), "EPI_DSUM is a row-streaming 3x3 epilogue");
     constexpr int NB = (EPI == EPI_FWD) ? NC : 4;
     float bias_r[NB];
 #pragma unroll
-    for (int i = 0; i < NB; ++i) bias_r[i] = (EPI == EPI_DGRAD) ? 0.f : __ldg(p.bias + col0 + i);
+    for (int i = 0; i < NB; ++i) bias_r[i] = DG ? 0.f : __ldg(p.bias + col0 + i);
 
-    constexpr int NAV = (EPI == EPI_DGRAD) ? NC / 8 : 1;
+    constexpr int NAV = DG ? NC / 8 : 1;
     // position of this thread's output pixel in tile `it`, or -1
     auto pix_of = [&](const TcTileIter& it) -> long long {
       int r = it.row, c = it.rem + quad * 32 + lane;
@@ -627,14 +680,17 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       const int my_items_e = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       ntotal = (my_items_e > 0 ? my_items_e : 0) * p.NT;
     }
+    // EPI_DSUM keeps NC running sums per thread and trades one tile of lead for the registers (it writes nothing,
+    // so the saved-activation stream has the memory system almost to itself)
+    constexpr bool PF3 = (EPI != EPI_DSUM);
     long long pix = -1, pix1 = -1, pix2 = -1, pix3 = -1;
     int cn = 0, cn1 = 0, cn2 = 0, cn3 = 0;
-    uint4 av[NAV], av1[NAV], av2[NAV], av3[NAV];
+    uint4 av[NAV], av1[NAV], av2[NAV], av3[PF3 ? NAV : 1];
     auto fetch = [&](long long& pix_o, int& n_o, uint4* av_o) {
       if (far.valid(p)) {
         pix_o = pix_of(far);
         n_o = far.n;
-        if constexpr (EPI == EPI_DGRAD) load_prev(far, pix_o, av_o);
+        if constexpr (DG) load_prev(far, pix_o, av_o);
         far.next(p);
       } else {
         pix_o = -1;
@@ -642,11 +698,49 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     };
     fetch(pix, cn, av);
     fetch(pix1, cn1, av1);
-    fetch(pix2, cn2, av2);
+    if constexpr (PF3) fetch(pix2, cn2, av2);
     int stage = 0;
     uint32_t sph = 0;
+    // EPI_DSUM state: every thread keeps running sums of its own pixel column over the rows of the current
+    // (slot-image, row class, segment) -- NC registers, one FFMA per value and tile -- and the warp reduces them
+    // only when that triple changes (a few times per image): the thread of image column 0 / W-1 then holds exactly
+    // the border-column class, the transposed warp sum the whole row class.
+    constexpr int DS_SH = (NC == 32) ? 0 : (NC == 16) ? 1 : 2;
+    constexpr int DS_NV = (EPI == EPI_DSUM) ? NC : 1;
+    float ds_sum[DS_NV];
+#pragma unroll
+    for (int j = 0; j < DS_NV; ++j) ds_sum[j] = 0.f;
+    int ds_n = -1, ds_rc = 0, ds_pix = 0;
+    auto ds_flush = [&]() {
+      if constexpr (EPI == EPI_DSUM) {
+        if (ds_n >= 0) {                                            // warp-uniform
+          const int xcol = ds_pix % W;
+          const uint32_t bl = __ballot_sync(0xffffffffu, xcol == 0 || xcol == W - 1);
+          float col = 0.f;
+          int side = 0;
+          if (bl) {
+            const int src = __ffs(bl) - 1;
+            side = (__shfl_sync(0xffffffffu, xcol, src) == 0) ? 0 : 2;
+#pragma unroll
+            for (int j = 0; j < DS_NV; ++j) {
+              const float tv = __shfl_sync(0xffffffffu, ds_sum[j], src);
+              if (lane == (j << DS_SH)) col = tv;
+            }
+          }
+          tc_transposed_sum<DS_NV, 16>(ds_sum, lane);               // lane (j << DS_SH): row-class sum of channel j
+          if ((lane & ((1 << DS_SH) - 1)) == 0) {
+            float* g = p.G + ((size_t)ds_n * 9 + ds_rc * 3) * N + col0 + (lane >> DS_SH);
+            atomicAdd(g + N, ds_sum[0] - col);                      // interior columns
+            if (bl) atomicAdd(g + side * N, col);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < DS_NV; ++j) ds_sum[j] = 0.f;
+      }
+    };
     for (int tno = 0; tno < ntotal; ++tno) {
-      fetch(pix3, cn3, av3);
+      if constexpr (PF3) fetch(pix3, cn3, av3);
+      else fetch(pix2, cn2, av2);
 
       mbar_wait(smem_u32(&sb->tfull[stage]), sph, 5);
       tc_fence_after();
@@ -664,6 +758,35 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[stage]));   // accumulator stage is free again
 
+      if constexpr (EPI == EPI_DSUM) {
+        // Row-streaming tiles are one full 128-pixel run of one image row: all 32 lanes hold a pixel of that row
+        // (this thread's column is the same for every row of an item), the warp channels col0 .. col0+NC-1.
+        const int pi = (int)pix;
+        const int rc = (pi < W) ? 0 : (pi >= (H - 1) * W) ? 2 : 1;    // border class of the row (3x3: pad 1)
+        if (cn != ds_n || rc != ds_rc || pi != ds_pix + W) {          // warp-uniform
+          ds_flush();
+          ds_n = cn; ds_rc = rc;
+        }
+        ds_pix = pi;
+        auto accumulate = [&](auto h16) {
+          constexpr bool H16 = decltype(h16)::value;
+#pragma unroll
+          for (int k = 0; k < NC / 8; ++k) {
+            const uint32_t aw[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 a;
+              if constexpr (H16) a = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
+              else a = make_float2(__uint_as_float(aw[e] << 16), __uint_as_float(aw[e] & 0xffff0000u));
+              // ELU'(x) from a = ELU(x): 1 for a > 0, a + 1 otherwise = min(a, 0) + 1
+              ds_sum[k * 8 + 2 * e] = fmaf(__uint_as_float(acc[k * 8 + 2 * e]), fminf(a.x, 0.f) + 1.f, ds_sum[k * 8 + 2 * e]);
+              ds_sum[k * 8 + 2 * e + 1] = fmaf(__uint_as_float(acc[k * 8 + 2 * e + 1]), fminf(a.y, 0.f) + 1.f, ds_sum[k * 8 + 2 * e + 1]);
+            }
+          }
+        };
+        if (F16) accumulate(std::true_type{});
+        else accumulate(std::false_type{});
+      } else
       if (pix >= 0 && !(p.dbg & 2)) {
         if constexpr (EPI == EPI_OUT4) {
           float4 o;
@@ -700,14 +823,19 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
           }
         }
       }
-      pix = pix1; pix1 = pix2; pix2 = pix3;
-      cn = cn1; cn1 = cn2; cn2 = cn3;
-      if constexpr (EPI == EPI_DGRAD) {
+      pix = pix1; pix1 = pix2;
+      cn = cn1; cn1 = cn2;
+      if constexpr (PF3) { pix2 = pix3; cn2 = cn3; }
+      if constexpr (DG) {
 #pragma unroll
-        for (int k = 0; k < NAV; ++k) { av[k] = av1[k]; av1[k] = av2[k]; av2[k] = av3[k]; }
+        for (int k = 0; k < NAV; ++k) {
+          av[k] = av1[k]; av1[k] = av2[k];
+          if constexpr (PF3) av2[k] = av3[k];
+        }
       }
       if (++stage == ACC) { stage = 0; sph ^= 1u; }
     }
+    ds_flush();
   }
 
   // ---- teardown
@@ -1047,6 +1175,9 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->rev = 0;
   q->itab = nullptr;
   q->coff = nullptr;
+  q->G = nullptr;
+  q->apf = 0;
+  q->lead = getenv("IODINE_TC_LEAD") ? atoi(getenv("IODINE_TC_LEAD")) : 0;
   q->items = p->BK * q->strips;
   q->idesc = make_idesc(N, s.precision == IODINE_FP16);
   for (int c = 0; c < 8; ++c) q->idesc_n[c] = (c >= 1 && c * N <= 256) ? make_idesc(c * N, s.precision == IODINE_FP16) : 0u;
@@ -1163,16 +1294,24 @@ static const TcMaps* find_map(Plan* p, const void* buf) {
   return nullptr;
 }
 
+// 1 when the last data-gradient can reduce its output over the border classes itself (EPI_DSUM)
+int tc_dsum_fused(const Plan* p) {
+  const TcState* st = reinterpret_cast<const TcState*>(p->tc);
+  return st && st->rs && p->s.dec_k == 3 && !getenv("IODINE_TC_NO_DSUM");
+}
+
 int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* act_prev, void* out, float* G,
                    cudaStream_t st_) {
-  (void)G;
   TcState* st = tc_state(p);
   const TcMaps* map = find_map(p, in);
   IOD_REQUIRE(map != nullptr, "conv_tc: source buffer has no tensor map");
+  IOD_REQUIRE(!G || (dgrad && tc_dsum_fused(p)), "conv_tc: fused class sums need the row-streaming data-gradient");
   TcParams q;
   q.maps = *map;
   fill_common(p, st->rs ? st->g_cc_rs : st->g_cc, p->C / 8, p->C, &q);
   if (st->rs) { q.rs_segs = p->s.W / 128; q.items = st->rs_grid; q.itab = st->itab; q.coff = st->coff; }
+  q.G = G;
+  q.apf = (dgrad && st->rs && !getenv("IODINE_TC_NO_APF")) ? 1 : 0;
   // traversal direction: read a buffer in the opposite direction to the one it was written in (the collapsed
   // first layer and the 4->C data-gradient write ascending), so that the freshest ~100 MB are still L2 hits
   if (!getenv("IODINE_TC_NO_REV")) q.rev = dgrad ? ((p->s.dec_layers - 1 - layer) % 2 == 0) : (layer % 2 == 1);
@@ -1183,6 +1322,7 @@ int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* a
   q.in = reinterpret_cast<const uint4*>(in);
   q.zero_row = reinterpret_cast<const uint4*>(st->zero_row);
   if (st->rs) {
+    if (dgrad && G) return tc_launch_rs<EPI_DSUM>(p, q, st->g_cc_rs.smem, false, st_);
     if (dgrad) return tc_launch_rs<EPI_DGRAD>(p, q, st->g_cc_rs.smem, false, st_);
     return tc_launch_rs<EPI_FWD>(p, q, st->g_cc_rs.smem, false, st_);
   }

@@ -131,11 +131,14 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
     if (launch_dgrad_in4(p, p->seed4, (const float*)p->act[n - 1], (float*)p->gbuf[0], st)) return 1;
   }
   int cur = 0;
+  bool summed = false;                 // class sums already produced by the last data-gradient's epilogue
   for (int l = n - 1; l >= 1; --l) {
     const bool last = (l == 1);
     prof_mark(p, st);
     if (tc_mode(p)) {
-      if (tc_launch_conv(p, l, true, p->gbuf[cur], p->act[l - 1], p->gbuf[cur ^ 1], nullptr, st)) return 1;
+      const bool fuse = last && tc_dsum_fused(p);
+      if (tc_launch_conv(p, l, true, p->gbuf[cur], p->act[l - 1], p->gbuf[cur ^ 1], fuse ? p->G : nullptr, st)) return 1;
+      summed = fuse;
     } else {
       if (launch_conv_cc(p, (const float*)p->gbuf[cur], p->dec[l].wt, nullptr,
                          (const float*)p->act[l - 1], last ? nullptr : (float*)p->gbuf[cur ^ 1],
@@ -147,7 +150,7 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
   }
   // the tensor-core path stores dJ/d(pre-activation 1) and reduces it over the border classes
   // of the collapsed first layer in a separate bandwidth-bound pass
-  if (tc_mode(p)) return tc_launch_class_sum(p, p->gbuf[cur], st);
+  if (tc_mode(p) && !summed) return tc_launch_class_sum(p, p->gbuf[cur], st);
   return 0;
 }
 

@@ -61,6 +61,10 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
       : "memory");
 }
+// pull `bytes` (multiple of 16) of global memory into L2 ahead of a later ordinary load; no destination, no barrier
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
   asm volatile(
