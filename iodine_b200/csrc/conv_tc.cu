@@ -680,12 +680,13 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       const int my_items_e = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       ntotal = (my_items_e > 0 ? my_items_e : 0) * p.NT;
     }
-    // EPI_DSUM keeps NC running sums per thread and trades one tile of lead for the registers (it writes nothing,
-    // so the saved-activation stream has the memory system almost to itself)
+    // EPI_DSUM keeps NC running sums per thread; it pays for those registers with the prefetch queue (one tile of
+    // lead instead of three -- the producers pull its saved-activation rows into L2 long before, see `apf`), so
+    // that nothing spills: the register cap of this 11-warp block is 168.
     constexpr bool PF3 = (EPI != EPI_DSUM);
     long long pix = -1, pix1 = -1, pix2 = -1, pix3 = -1;
     int cn = 0, cn1 = 0, cn2 = 0, cn3 = 0;
-    uint4 av[NAV], av1[NAV], av2[NAV], av3[PF3 ? NAV : 1];
+    uint4 av[NAV], av1[NAV], av2[PF3 ? NAV : 1], av3[PF3 ? NAV : 1];
     auto fetch = [&](long long& pix_o, int& n_o, uint4* av_o) {
       if (far.valid(p)) {
         pix_o = pix_of(far);
@@ -697,8 +698,10 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       }
     };
     fetch(pix, cn, av);
-    fetch(pix1, cn1, av1);
-    if constexpr (PF3) fetch(pix2, cn2, av2);
+    if constexpr (PF3) {
+      fetch(pix1, cn1, av1);
+      fetch(pix2, cn2, av2);
+    }
     int stage = 0;
     uint32_t sph = 0;
     // EPI_DSUM state: every thread keeps running sums of its own pixel column over the rows of the current
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     };
     for (int tno = 0; tno < ntotal; ++tno) {
       if constexpr (PF3) fetch(pix3, cn3, av3);
-      else fetch(pix2, cn2, av2);
+      else fetch(pix1, cn1, av1);
 
       mbar_wait(smem_u32(&sb->tfull[stage]), sph, 5);
       tc_fence_after();
@@ -823,14 +826,14 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
           }
         }
       }
-      pix = pix1; pix1 = pix2;
-      cn = cn1; cn1 = cn2;
-      if constexpr (PF3) { pix2 = pix3; cn2 = cn3; }
+      pix = pix1;
+      cn = cn1;
+      if constexpr (PF3) { pix1 = pix2; pix2 = pix3; cn1 = cn2; cn2 = cn3; }
       if constexpr (DG) {
 #pragma unroll
         for (int k = 0; k < NAV; ++k) {
-          av[k] = av1[k]; av1[k] = av2[k];
-          if constexpr (PF3) av2[k] = av3[k];
+          av[k] = av1[k];
+          if constexpr (PF3) { av1[k] = av2[k]; av2[k] = av3[k]; }
         }
       }
       if (++stage == ACC) { stage = 0; sph ^= 1u; }
