@@ -110,6 +110,14 @@ def profiled_traffic(precision):
     return None
 
 
+def conv_tensor_units(arch, precision):
+    n_cc = arch.DEC.CONV_LAYERS - 1
+    if n_cc < 1:
+        return 0.0
+    fused = precision == 'fp32' or (arch.DEC.KERNEL_SIZE == 3 and arch.IMG_SIZE % 128 == 0)
+    return (2.0 * n_cc + 3.0 * (n_cc - 1) + (2.0 if fused else 3.0)) / (2.0 * n_cc)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -386,7 +394,12 @@ def run_native(args):
                 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': (achieved_tf / peak_tf) if achieved_tf else None,
                 'traffic': profiled_traffic(args.precision), 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': B * K * S * S * arch.DEC.CONV_CHAN * (4 if args.precision == 'fp32' else 2) * 2.5,
+                # activation tensors moved per launch, averaged over the launches timed: forward reads one and writes
+                # one; a data-gradient also reads the saved activation; the LAST data-gradient reduces its output to
+                # the class sums of the collapsed first layer instead of writing it (fp32 path always; 16-bit path when
+                # the row-streaming kernels apply: 3x3, W a multiple of 128)
+                'algorithmic_bytes_per_launch': B * K * S * S * arch.DEC.CONV_CHAN * (4 if args.precision == 'fp32' else 2)
+                * conv_tensor_units(arch, args.precision),
                 'hbm_peak_gbs': peak_gbs,
                 'launches_timed': int(conv_n), 'avg_launch_ms': conv_ms / conv_n if conv_n else None,
                 'flop_per_launch': per_launch_flop,
