@@ -948,7 +948,7 @@ static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo
   g->plane_stride16 = (uint32_t)(R + g->m) * g->Ps;
   if (g->plane_stride16 >= 16384u) return false;              // LBO field is 14 bits
   // rows per work item: balance the grid (items >> SMs) against halo re-reads
-  int TH = (rs && getenv("IODINE_TC_TH")) ? atoi(getenv("IODINE_TC_TH")) : 8;   // largest divisor of H that is <= 8 (tunable for experiments)
+  int TH = 8;                                                  // largest divisor of H that is <= 8 (generic kernels; row-streaming uses the work list)
   while (s.H % TH != 0) --TH;
   g->TH = TH;
   g->smem = (size_t)round_up((int)g->w_bytes, 1024) + (size_t)nch_in * g->plane_stride16 * 16 + sizeof(TcSmem) + 64;
