@@ -22,3 +22,26 @@ class Logger:
 
 
 logger = Logger()
+
+
+class VAEGetter:
+    """``getter.get_tensorboard_data()`` of the reference (vis_logger.py:61-94): everything in the logger, tensors
+    detached and moved to the host, ready for ``TensorBoard.update(**data)``."""
+
+    def __init__(self, logger=logger):
+        self.logger = logger
+
+    def get_tensorboard_data(self):
+        import torch
+        things = self.logger.things
+        for k, v in things.items():
+            if isinstance(v, torch.Tensor):
+                things[k] = v.detach().cpu()
+        return things
+
+
+def make_getter(cfg):
+    """vis_logger.py:53-57: ``cfg.GETTER == 'VAE'`` is the only getter the reference defines (IODINE uses it too)."""
+    if cfg.GETTER == 'VAE':
+        return VAEGetter()
+    return None
