@@ -130,3 +130,19 @@ def run_reference_reconstruct(model, x, eps):
         pred, mask, mean = model.reconstruct(x)
     model.zero_grad(set_to_none=True)
     return pred.detach(), mask.detach(), mean.detach()
+
+
+def run_reference_training_step(model, x, eps):
+    """``loss = model(x)`` (IODINE.forward, iodine.py:115-158) followed by what ``lib/engine/train.py:60-64`` does
+    with it: ``loss.mean()``, ``optimizer.zero_grad()`` -- which discards the parameter gradients the in-loop
+    ``(B * elbo).backward(retain_graph=True)`` calls have accumulated -- and ``loss.backward()``.
+    Returns (loss value, {state_dict key: gradient})."""
+    with injected_noise(eps):
+        loss = model(x)
+    loss = loss.mean()
+    model.zero_grad(set_to_none=True)
+    loss.backward()
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
+             for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    return loss.detach().clone(), grads

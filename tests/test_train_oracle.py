@@ -1,0 +1,53 @@
+"""CPU: the explicit training gradients of oracle/train_restatement.py (the specification of the
+weight-gradient kernels) against the UNMODIFIED reference's autograd -- ``loss = model(x); loss.backward()`` as
+``lib/engine/train.py:60-64`` runs it -- in float64 (tight) and float32 (the reference's own precision)."""
+import pytest
+import torch
+
+from oracle import arch as A
+from oracle import ref_loader as R
+from oracle import restatement as S
+from oracle import train_restatement as TR
+
+pytestmark = pytest.mark.skipif(not R.reference_available(), reason='reference tree not mounted')
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-300)).item()
+
+
+@pytest.mark.parametrize('name,over,B,sharpen,dtype,tol', [
+    ('tiny', {}, 3, 1.0, torch.float64, 1e-6),
+    ('tiny', {}, 2, 5.0, torch.float64, 1e-6),
+    ('test5x5', {}, 2, 3.0, torch.float64, 1e-6),                 # 5x5 kernels, other channel widths
+    ('tiny', dict(iters=1), 2, 2.0, torch.float64, 1e-6),         # a single refiner call: no LSTM chain
+    ('tiny', dict(img_size=20, ref_layers=3), 2, 2.0, torch.float64, 1e-6),   # odd stride-2 sizes (output_padding)
+    ('tiny', {}, 3, 3.0, torch.float32, 2e-3),
+])
+def test_training_gradients_match_reference_autograd(name, over, B, sharpen, dtype, tol):
+    arch = A.arch_by_name(name, **over)
+    model = R.build_reference_model(arch, seed=0, sharpen=sharpen, dtype=dtype)
+    x, eps = R.make_inputs(arch, B, dtype=dtype)
+    ref_loss, ref_grads = R.run_reference_training_step(model, x, eps)
+    sd = S.state_dict_to(model.state_dict(), dtype)
+    loss, grads, elbos = TR.loss_and_grads(sd, arch, x, eps)
+    assert abs(loss.item() - ref_loss.item()) <= tol * abs(ref_loss.item())
+    assert set(grads) == set(ref_grads) == set(sd)
+    for k in sd:
+        assert grads[k].shape == ref_grads[k].shape, k
+        assert _rel(grads[k], ref_grads[k]) < tol, (k, _rel(grads[k], ref_grads[k]))
+    # every parameter takes part: no gradient of the reference is identically zero here (with a single refiner call
+    # the LSTM starts from h = 0, so weight_hh alone gets none)
+    assert all(ref_grads[k].abs().max() > 0 for k in sd if not (arch.ITERS == 1 and k == 'refine.lstm.weight_hh'))
+
+
+def test_forward_loss_matches_inference_restatement_elbos():
+    """the T+1 ELBOs of the training step are the inference loop's ELBOs plus the final one"""
+    arch = A.arch_by_name('tiny')
+    model = R.build_reference_model(arch, seed=0, sharpen=2.0, dtype=torch.float64)
+    x, eps = R.make_inputs(arch, 2, dtype=torch.float64)
+    sd = S.state_dict_to(model.state_dict(), torch.float64)
+    _, _, elbos = TR.loss_and_grads(sd, arch, x, eps)
+    tr = S.encode_trace(sd, arch, x, eps)
+    for i, st in enumerate(tr['steps']):
+        assert abs(elbos[i].item() - st['elbo'].item()) <= 1e-12 * abs(st['elbo'].item())
