@@ -12,7 +12,6 @@ import os
 import sys
 
 import numpy as np
-import torch
 
 from . import arch as A
 from . import ref_loader as R

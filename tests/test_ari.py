@@ -1,6 +1,5 @@
 """ARI evaluator tail: oracle vs the reference's known answer / live reference (CPU), and
 the device kernel vs the oracle, bit-exact on the contingency tables (GPU)."""
-import os
 import sys
 
 import numpy as np

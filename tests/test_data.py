@@ -6,7 +6,6 @@
 * the torchvision transforms the reference composes (``lib/data/clevr.py:26-38``), bit for bit,
 and the loader / prefetcher / evaluation-loop plumbing with stand-in models.
 """
-import io
 import os
 from types import SimpleNamespace as NS
 

@@ -11,9 +11,9 @@ import pytest
 import torch
 
 from oracle import arch as A
-from oracle import restatement as S
 
-from helpers import golden_state_dict, load_golden, rel_err, seeded_model, t
+
+from helpers import load_golden, rel_err, seeded_model, t
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
