@@ -57,6 +57,7 @@ def _worker(rank, world, port, B, out_dir):
         sd = S.state_dict_to(seeded_model(arch, 3.0).state_dict(), torch.float32)
         x, eps = _inputs(arch, B)
         sh = SlotShard(OracleModel(arch, sd))
+        assert not sh.native                      # gloo: the [T,2] table goes through dist.all_reduce
         pred, mask, mean = sh.reconstruct(x, eps, gather=True)
         res = {'pred': pred, 'mask': mask, 'elbo': sh.elbo_per_step(), 'terms': sh.elbo_terms,
                'gb': sh.global_batch}
