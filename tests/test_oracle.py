@@ -41,9 +41,16 @@ def test_restatement_matches_golden_clevr6():
 
 
 @pytest.mark.skipif(not R.reference_available(), reason='reference tree not mounted')
-@pytest.mark.parametrize('arch_name,B,sharpen', [('tiny', 3, 1.0), ('tiny', 1, 7.0), ('test5x5', 2, 3.0)])
-def test_restatement_matches_live_reference(arch_name, B, sharpen):
-    arch = A.arch_by_name(arch_name)
+@pytest.mark.parametrize('arch_name,over,B,sharpen', [
+    ('tiny', {}, 3, 1.0), ('tiny', {}, 1, 7.0), ('test5x5', {}, 2, 3.0),
+    ('tiny', dict(layernorm=False), 2, 3.0),                       # ARCH.LAYERNORM off (iodine.py:264, 300-330)
+    ('tiny', dict(slots=11, iters=7), 1, 4.0),                     # BASELINE config #4's K / T
+    ('tiny', dict(slots=1), 2, 2.0),                               # a single slot: softmax / leave-one-out degenerate
+    ('tiny', dict(img_size=24, ref_layers=3, dec_layers=3), 2, 2.0),
+    ('dsprites', dict(img_size=32), 1, 3.0),                       # config #1's layer counts and widths, smaller image
+])
+def test_restatement_matches_live_reference(arch_name, over, B, sharpen):
+    arch = A.arch_by_name(arch_name, **over)
     model = R.build_reference_model(arch, sharpen=sharpen)
     x, eps = R.make_inputs(arch, B, seed_x=7, seed_eps=11)
     ref = R.run_reference_trace(model, x, eps)
