@@ -47,6 +47,10 @@ def test_plan_create_rejects_bad_shapes_without_gpu_work():
     assert b'K' in lib.iodine_last_error()
     s.K, s.dec_chan = 3, 48
     assert lib.iodine_plan_create(ctypes.byref(s), ctypes.byref(plan)) != 0
+    # null handles are refused with a message, not dereferenced
+    assert lib.iodine_plan_set_comm(None, None, 0, 1) != 0 and b'plan' in lib.iodine_last_error()
+    n = ctypes.c_size_t()
+    assert lib.iodine_plan_workspace_bytes(None, ctypes.byref(n)) != 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='CPU-only check')
