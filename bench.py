@@ -167,8 +167,10 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warm, 'ms_per_step': med * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'CLEVR6 128x128 K=7 T=5, reconstruct() on host cores, B=%d sample '
-                               '(steps/s is flat in B on CPU)' % Bs,
+        'config': {'workload': 'CLEVR6 128x128 K=7 T=5 B=32 per GPU (configs[1]); step = one IODINE.encode() over the '
+                               'batch',
+                   'sample': 'reference CPU path on the host cores: reconstruct() of B=%d images per step (steps/s is '
+                             'flat in B on CPU)' % Bs,
                    'note': '/root/reference is absent on the GPU box: oracle port of the reference '
                            'algorithm (torch CPU ops, closed-form grads, no unused weight-grads)'},
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
