@@ -63,3 +63,26 @@ def test_no_cpu_fallback():
         m.reconstruct(torch.rand(1, 3, 16, 16))
     with pytest.raises(_cabi.IodineError):
         m(torch.rand(1, 3, 16, 16))
+
+
+def test_plain_c_host_compiles_and_links(tmp_path):
+    """examples/host_c.c: the ABI is usable from C99 with nothing but the header and the .so (run on a B200:
+    INTEGRATION.md); here it is compiled with -Wall -Werror and linked, not executed."""
+    import shutil
+    import subprocess
+    if not shutil.which('gcc'):
+        pytest.skip('no gcc')
+    from iodine_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    cuda = next((d for d in ('/usr/local/cuda/lib64', '/usr/local/cuda/targets/x86_64-linux/lib')
+                 if os.path.exists(os.path.join(d, 'libcudart.so'))), None)
+    if cuda is None:
+        pytest.skip('no libcudart to link against')
+    _cabi.load()
+    out = str(tmp_path / 'host_c')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', os.path.join(root, 'examples', 'host_c.c'),
+                        '-I', os.path.join(root, 'include'), '-L', libdir, '-liodine_b200', '-L', cuda, '-lcudart',
+                        '-Wl,-rpath,' + libdir, '-o', out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert os.path.exists(out)
