@@ -153,20 +153,26 @@ def refine_backward(sd, t, g_dmu, g_dlv, dh_next, dc_next, grads, stride=2):
 
 
 # --------------------------------------------------------------------------- the training step
-def loss_and_grads(sd, arch, x, eps):
+def loss_and_grads(sd, arch, x, eps, global_batch=None):
     """``-weighted ELBO`` of ``IODINE.forward`` and its gradient w.r.t. every entry of the state_dict.
-    x: [B,3,H,W]; eps: [T+1,B,K,L] (the T+1 ``torch.randn_like`` draws).  Returns (loss, grads, elbos[T+1])."""
+    x: [B,3,H,W]; eps: [T+1,B,K,L] (the T+1 ``torch.randn_like`` draws).  Returns (loss, grads, elbos[T+1]).
+
+    ``global_batch``: slot-shard data parallelism (SURVEY.md 8e "Training"): x holds only this rank's images of a
+    batch of ``global_batch``; every batch mean divides by the GLOBAL size, so loss, ELBOs and gradients are this
+    rank's additive share and ONE sum all-reduce of the gradients (4.4 MB) gives the full-batch result -- nothing
+    else crosses ranks, the loop and both backward passes are per image."""
     B, K, L, T = x.shape[0], arch.SLOTS, arch.DIM_LATENT, arch.ITERS
+    Bg = B if global_batch is None else int(global_batch)
     grads, tapes, post_grads, elbos = {}, [], [], []
     mu = sd['posterior.init_mean'][None, None].expand(B, K, L).clone()
     lv = sd['posterior.init_logvar'][None, None].expand(B, K, L).clone()
     hidden = None
     for i in range(T + 1):
-        coef = -((i + 1) / (T + 1)) / B
+        coef = -((i + 1) / (T + 1)) / Bg
         z = mu + torch.exp(0.5 * lv) * eps[i]
         mean, logits, acts, _ = S.decoder_forward(sd, z, arch.IMG_SIZE)
         mx = S.mixture(x, mean, logits, arch.SIGMA)
-        elbos.append((mx['ll_sum'] - S.kl_elementwise(mu, lv).sum()) / B)
+        elbos.append((mx['ll_sum'] - S.kl_elementwise(mu, lv).sum()) / Bg)
         dz = decoder_param_grads(sd, z, acts, mx['seed4'], coef, grads).reshape(B, K, L)
         mu_grad = dz - mu                                              # dJ_i / d(posterior_i), as in the loop
         lv_grad = dz * 0.5 * torch.exp(0.5 * lv) * eps[i] - 0.5 * (torch.exp(lv) - 1)

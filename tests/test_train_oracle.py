@@ -51,3 +51,46 @@ def test_forward_loss_matches_inference_restatement_elbos():
     tr = S.encode_trace(sd, arch, x, eps)
     for i, st in enumerate(tr['steps']):
         assert abs(elbos[i].item() - st['elbo'].item()) <= 1e-12 * abs(st['elbo'].item())
+
+
+def _shard_worker(rank, world, port, B, out_dir):
+    import os
+    import torch.distributed as dist
+    from iodine_b200.parallel import shard_bounds
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        arch = A.arch_by_name('tiny')
+        model = R.build_reference_model(arch, seed=0, sharpen=2.0, dtype=torch.float64)
+        sd = S.state_dict_to(model.state_dict(), torch.float64)
+        x, eps = R.make_inputs(arch, B, dtype=torch.float64)
+        b0, b1 = shard_bounds(B, world, rank)
+        loss, grads, _ = TR.loss_and_grads(sd, arch, x[b0:b1], eps[:, b0:b1], global_batch=B)
+        flat = torch.cat([loss.reshape(1)] + [grads[k].reshape(-1) for k in sorted(grads)])
+        dist.all_reduce(flat)                              # the training exchange: one sum over ranks
+        torch.save(flat, os.path.join(out_dir, 'r%d.pt' % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('B', [4, 3])                      # equal shards and a ragged split
+def test_sharded_gradients_sum_to_the_full_batch(B, tmp_path):
+    """SURVEY.md 8e 'Training': whole-image shards + ONE sum all-reduce of the gradients (gloo, 2 ranks) reproduce
+    the single-process gradients of the global batch."""
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_shard_worker, args=(2, port, B, str(tmp_path)), nprocs=2, join=True)
+    arch = A.arch_by_name('tiny')
+    model = R.build_reference_model(arch, seed=0, sharpen=2.0, dtype=torch.float64)
+    sd = S.state_dict_to(model.state_dict(), torch.float64)
+    x, eps = R.make_inputs(arch, B, dtype=torch.float64)
+    loss, grads, _ = TR.loss_and_grads(sd, arch, x, eps)
+    want = torch.cat([loss.reshape(1)] + [grads[k].reshape(-1) for k in sorted(grads)])
+    for r in range(2):
+        got = torch.load(os.path.join(str(tmp_path), 'r%d.pt' % r))
+        assert _rel(got, want) < 1e-12, r
