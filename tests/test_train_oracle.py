@@ -9,13 +9,14 @@ from oracle import ref_loader as R
 from oracle import restatement as S
 from oracle import train_restatement as TR
 
-pytestmark = pytest.mark.skipif(not R.reference_available(), reason='reference tree not mounted')
+needs_reference = pytest.mark.skipif(not R.reference_available(), reason='reference tree not mounted')
 
 
 def _rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-300)).item()
 
 
+@needs_reference
 @pytest.mark.parametrize('name,over,B,sharpen,dtype,tol', [
     ('tiny', {}, 3, 1.0, torch.float64, 1e-6),
     ('tiny', {}, 2, 5.0, torch.float64, 1e-6),
@@ -41,6 +42,7 @@ def test_training_gradients_match_reference_autograd(name, over, B, sharpen, dty
     assert all(ref_grads[k].abs().max() > 0 for k in sd if not (arch.ITERS == 1 and k == 'refine.lstm.weight_hh'))
 
 
+@needs_reference
 def test_forward_loss_matches_inference_restatement_elbos():
     """the T+1 ELBOs of the training step are the inference loop's ELBOs plus the final one"""
     arch = A.arch_by_name('tiny')
@@ -74,6 +76,7 @@ def _shard_worker(rank, world, port, B, out_dir):
         dist.destroy_process_group()
 
 
+@needs_reference
 @pytest.mark.parametrize('B', [4, 3])                      # equal shards and a ragged split
 def test_sharded_gradients_sum_to_the_full_batch(B, tmp_path):
     """SURVEY.md 8e 'Training': whole-image shards + ONE sum all-reduce of the gradients (gloo, 2 ranks) reproduce
@@ -94,3 +97,34 @@ def test_sharded_gradients_sum_to_the_full_batch(B, tmp_path):
     for r in range(2):
         got = torch.load(os.path.join(str(tmp_path), 'r%d.pt' % r))
         assert _rel(got, want) < 1e-12, r
+
+
+# --------------------------------------------------------------------------- committed fixtures (no reference tree needed)
+def _golden_case(name):
+    import os
+    import numpy as np
+    from oracle import make_train_golden as MTG
+    from helpers import GOLDEN, seeded_model
+    g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    arch_name, over, B, sharpen = MTG.CASES[name]
+    arch = A.arch_by_name(arch_name, **over)
+    sd = S.state_dict_to(seeded_model(arch, sharpen).state_dict(), torch.float32)
+    return g, arch, sd
+
+
+@pytest.mark.parametrize('name', ['train_tiny_b2_sharp', 'train_test5x5_b2_sharp'])
+def test_training_gradients_match_committed_reference_vectors(name):
+    """the fixtures hold the reference's fp32 autograd gradients; the restatement runs in fp64 on the same fp32
+    weights / inputs, so the residual is the reference's own fp32 rounding"""
+    import numpy as np
+    from oracle import make_golden as MG
+    g, arch, sd = _golden_case(name)
+    cs = MG.weights_checksum(sd)
+    assert abs(cs - float(g['weights_checksum'])) <= 1e-9 * abs(cs)
+    sd64 = S.state_dict_to(sd, torch.float64)
+    x, eps = torch.from_numpy(g['x']).double(), torch.from_numpy(g['eps']).double()
+    loss, grads, _ = TR.loss_and_grads(sd64, arch, x, eps)
+    assert abs(loss.item() - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    for k in sd:
+        ref = torch.from_numpy(np.asarray(g['grad/' + k])).double()
+        assert _rel(grads[k], ref) < 2e-3, (k, _rel(grads[k], ref))
