@@ -22,13 +22,13 @@ def imread(path):
         return np.asarray(im)
 
 
-def center_crop(img, size):
+def center_crop(img, size, fill=0):
     w, h = img.size
     th = tw = int(size)
     if tw > w or th > h:                         # torchvision pads with zeros first
         pl, pt = max((tw - w) // 2, 0), max((th - h) // 2, 0)
         pr, pb = max((tw - w + 1) // 2, 0), max((th - h + 1) // 2, 0)
-        canvas = Image.new(img.mode, (w + pl + pr, h + pt + pb), 0)
+        canvas = Image.new(img.mode, (w + pl + pr, h + pt + pb), fill)
         canvas.paste(img, (pl, pt))
         img = canvas
         w, h = img.size
