@@ -41,7 +41,8 @@ extern "C" {
 enum IodinePrecision {
   IODINE_FP32 = 0,  /* FFMA, fp32 activations: the exact path                           */
   IODINE_BF16 = 1,  /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate in TMEM)      */
-  IODINE_TF32 = 2,  /* reserved: tcgen05 kind::tf32                                     */
+  IODINE_TF32 = 2,  /* tcgen05 kind::tf32: fp32 activations and weights rounded to tf32 (10-bit mantissa, 8-bit
+                       exponent), fp32 accumulate in TMEM -- what cuDNN runs the reference's nn.Conv2d with on a GPU */
   IODINE_FP16 = 3   /* tcgen05 kind::f16 with fp16 operands (10-bit mantissa), fp32 accumulate */
 };
 
@@ -160,13 +161,32 @@ IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_ho
                                   float* pred_host, float* mask_host, float* mean_host,
                                   float* z_host, float* elbo_terms_host, void* stream);
 
+/* The evaluation flow with HOST buffers: lib/engine/eval.py:21-30 (`model.reconstruct(image)` per batch) followed
+ * by what lib/eval/ari_eval.py:32-39 keeps of the result -- the per-pixel ARGMAX over the K predicted masks.  Same
+ * sequence as iodine_reconstruct_host[_async] (x and eps host->device, encode + decode, results device->host), but
+ * the masks come back as argmax_host[B,H,W] uint8 (first maximum, as torch.argmax) instead of the fp32
+ * [B,K,1,H,W] + [B,K,3,H,W] tensors: 1 byte per pixel instead of 4*4*K.  pred_host[B,3,H,W], z_host[B,K,L],
+ * elbo_terms_host[T,2] as in iodine_reconstruct_host; any output may be NULL. */
+IODINE_API int iodine_evaluate_host(IodinePlan* plan, const float* x_host, const float* eps_host, float* pred_host,
+                         uint8_t* argmax_host, float* z_host, float* elbo_terms_host, void* stream);
+IODINE_API int iodine_evaluate_host_async(IodinePlan* plan, const float* x_host, const float* eps_host,
+                               float* pred_host, uint8_t* argmax_host, float* z_host, float* elbo_terms_host,
+                               void* stream);
+
+/* The logger side channel of IODINE.elbo (iodine.py:225-239): what the reference hands to `logger.update` on every
+ * elbo() evaluation -- pred[0], mask[0,i,0] and mean[0,i] of image 0.  Returns those of the LAST elbo() evaluated by
+ * this plan (the last refinement step of encode()/reconstruct(), or iodine_elbo): pred0[3,H,W], mask0[K,H,W],
+ * mean0[K,3,H,W], device memory, any may be NULL. */
+IODINE_API int iodine_plan_last_elbo_image0(IodinePlan* plan, float* pred0, float* mask0, float* mean0, void* stream);
+
 /* Multi-GPU (replaces torch.nn.DataParallel, lib/modeling/build.py:11-12, and the replica-mean of
  * lib/engine/train.py:61).  The path shards by whole images, one process and one plan per GPU; every K-way reduction
  * is inside one image, so the ONLY cross-rank quantity is the [T,2] table of batch sums behind the ELBO means
  * (iodine.py:193, 220).  After this call iodine_encode / iodine_reconstruct / iodine_reconstruct_host[_async]
  * sum that table over the communicator with one ncclAllReduce on the caller's stream (stream-ordered, no host
- * synchronisation) before they return it; nothing else crosses ranks.  All ranks must make the same calls, with
- * elbo_terms_out given on all of them or on none.  iodine_refine_step / iodine_elbo stay rank-local.
+ * synchronisation) before they return it; iodine_elbo does the same with its two sums; nothing else crosses ranks.
+ * All ranks must make the same calls, with elbo_terms_out given on all of them or on none.  iodine_refine_step stays
+ * rank-local.
  *   nccl_comm: an ncclComm_t of the calling process (NULL uninstalls); NCCL is resolved from the process at run
  *   time (dlopen of libnccl.so.2), the library does not link against it. */
 IODINE_API int iodine_plan_set_comm(IodinePlan* plan, void* nccl_comm, int32_t rank, int32_t nranks);

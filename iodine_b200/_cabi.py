@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libiodine_b200.so')
 
 MAX_LAYERS = 8
 FP32, BF16, TF32, FP16 = 0, 1, 2, 3
-PRECISIONS = {'fp32': FP32, 'bf16': BF16, 'fp16': FP16}
+PRECISIONS = {'fp32': FP32, 'bf16': BF16, 'fp16': FP16, 'tf32': TF32}
 
 EXPORTS = [
     'iodine_abi_version', 'iodine_last_error', 'iodine_plan_create', 'iodine_plan_destroy',
@@ -19,7 +19,7 @@ EXPORTS = [
     'iodine_init_state', 'iodine_refine_step', 'iodine_elbo', 'iodine_encode', 'iodine_decode',
     'iodine_reconstruct', 'iodine_reconstruct_host', 'iodine_reconstruct_host_async', 'iodine_debug_read',
     'iodine_plan_launch_count', 'iodine_plan_profile', 'iodine_plan_profile_read', 'iodine_ari',
-    'iodine_plan_set_comm',
+    'iodine_plan_set_comm', 'iodine_plan_last_elbo_image0', 'iodine_evaluate_host', 'iodine_evaluate_host_async',
 ]
 
 
@@ -85,6 +85,9 @@ def load():
         'iodine_plan_profile_read': [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
         'iodine_ari': [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
         'iodine_plan_set_comm': [vp, vp, i32, i32],
+        'iodine_plan_last_elbo_image0': [vp] * 5,
+        'iodine_evaluate_host': [vp] * 8,
+        'iodine_evaluate_host_async': [vp] * 8,
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

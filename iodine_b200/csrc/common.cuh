@@ -89,9 +89,13 @@ struct Plan {
   struct EncodeGraph {
     cudaGraphExec_t exec = nullptr;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    const void* seen[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pointers of the previous eager call
+    bool warm = false;                                                      // key was seen by one eager call
+    uint64_t used = 0;                                                      // graph_clock of the last use (LRU)
     uint64_t kernels = 0;                                                   // kernel launches inside the graph
-  } graph;
+  };
+  static constexpr int N_GRAPHS = 4;
+  EncodeGraph graph[N_GRAPHS];
+  uint64_t graph_clock = 0;
   cudaStream_t gstream = nullptr;
   cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   bool graphs = true;
@@ -149,14 +153,26 @@ struct Plan {
   float* hpred = nullptr;         // [B,3,H,W]
   float* hmask = nullptr;         // [B,K,1,H,W]
   float* hmean = nullptr;         // [B,K,3,H,W]
+  uint8_t* hamax = nullptr;       // [B,H,W] argmax over the K masks (iodine_evaluate_host)
+  // logger side channel: image 0 of the last elbo() evaluation (iodine.py:225-239)
+  float* log_pred = nullptr;      // [3,H,W]
+  float* log_mask = nullptr;      // [K,H,W]
+  float* log_mean = nullptr;      // [K,3,H,W]
 };
 
 // split-K factor of the LSTM gate GEMM (head.cu); the gates buffer holds that many partial sums
 constexpr int LSTM_KSPLIT = 8;
 
-// tensor-core modes keep the decoder activations as 16-bit values (bf16 or fp16), chunk-planar
-inline bool tc_mode(const Plan* p) { return p->s.precision == IODINE_BF16 || p->s.precision == IODINE_FP16; }
-inline size_t act_elem_bytes(const Plan* p) { return tc_mode(p) ? 2 : 4; }
+// tensor-core modes keep the decoder activations chunk-planar: 16 bytes per pixel and plane = 8 channels of 16-bit
+// values (bf16 / fp16) or 4 channels of fp32 values rounded to tf32 (IODINE_TF32)
+inline bool tc_mode(const Plan* p) {
+  return p->s.precision == IODINE_BF16 || p->s.precision == IODINE_FP16 || p->s.precision == IODINE_TF32;
+}
+inline bool tf_mode(const Plan* p) { return p->s.precision == IODINE_TF32; }
+inline size_t act_elem_bytes(const Plan* p) { return !tc_mode(p) ? 4 : tf_mode(p) ? 4 : 2; }
+// operand format of the 16-bit tensor-core kernels of a mode: IEEE half for IODINE_FP16 and for the refinement
+// encoder of IODINE_TF32 (same 10-bit mantissa; its inputs are layer-normalised / bounded), bfloat16 for IODINE_BF16
+inline int half_is_f16(const Plan* p) { return p->s.precision != IODINE_BF16; }
 
 // 16-bit pair packing selected at run time (helper kernels) -- f16 != 0: IEEE half, else bfloat16
 __device__ __forceinline__ uint32_t pack_h2(float a, float b, int f16) {
@@ -181,7 +197,8 @@ int launch_refine_convs(Plan* p, const float* x, cudaStream_t st);
 
 // ------------------------------------------------------------------ launchers (mixture.cu)
 int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st);
-int launch_recombine(Plan* p, float* pred, float* mask, float* mean, cudaStream_t st);
+int launch_recombine(Plan* p, float* pred, float* mask, float* mean, int n_images, cudaStream_t st,
+                     uint8_t* amax = nullptr);   // amax[B,H,W]: argmax over the K masks (evaluator tail)
 int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st);
 int launch_assemble16(Plan* p, const float* x, cudaStream_t st);   // 16-bit modes: writes p->enc16
 

@@ -51,7 +51,7 @@ constexpr int TC_ISSUERS = 2;
 __host__ __device__ constexpr int tc_epi_warps(int N) { return N >= 32 ? 8 : 4; }
 __host__ __device__ constexpr int tc_threads(int N) { return 32 * (1 + TC_ISSUERS) + 32 * tc_epi_warps(N); }
 constexpr int TC_ACC_STAGES = 4;
-constexpr int TC_RS_UNIT = 5;        // input rows per issue unit of the row-streaming variant (<= 16, < ring rows)
+constexpr int TC_RS_UNIT = 5;        // input rows per issue unit of the row-streaming variant (<= 16; TcParams::rs_unit < ring rows)
 constexpr int TC_RS_SLOTS = 8;       // accumulator slots of the row-streaming variant (one per output row in flight)
 
 // EPI_DSUM: data-gradient whose output is not stored but reduced over the border classes of the collapsed first
@@ -69,7 +69,11 @@ struct alignas(64) TcParams {
   int32_t dbg;                    // IODINE_TC_DEBUG bit mask (timing experiments only; results are wrong when set):
                                   // 1 no TMEM reads, 2 no epilogue stores, 4 no TMA (generic producer), 8 no activation loads
   int32_t nch_in;                 // input planes
-  int32_t nch_out;                // output planes (N/8) for the bf16 epilogues
+  int32_t nch_out;                // output planes of the whole layer (all channel splits)
+  int32_t n_tot;                  // output channels of the whole layer
+  int32_t nsplit;                 // CTAs sharing one work range, each computing N of the n_tot output channels
+                                  // (grid = nsplit x ranges; CTA c: range c / nsplit, channel block c % nsplit).
+                                  // tf32 C=64: the 147 KB weight image does not fit beside a ring, two halves do
   int32_t H, W;
   int32_t pad;
   int32_t Ps;                     // ring row pitch, positions
@@ -80,6 +84,7 @@ struct alignas(64) TcParams {
   int32_t strips;                 // ceil(H / TH)
   int32_t items;                  // BK * strips (row-streaming: * rs_segs)
   int32_t rs_segs;                // row-streaming: 128-column segments per image row (an item is one of them)
+  int32_t rs_unit;                // row-streaming: input rows per issue unit (all waits first, then the MMAs), < R
   // row-streaming work list: every CTA owns ONE contiguous range of the flattened (slot-image, segment, row)
   // space, cut only at image boundaries -- items of up to H rows instead of TH-row strips: rows per CTA are
   // balanced to +-1 (strips: 25 vs 24 per CTA at B = 32) and a CTA restarts the row stream 2-3 times per launch
@@ -95,7 +100,7 @@ struct alignas(64) TcParams {
   int32_t n_full;                 // full 128-pixel boxes per halo row
   int32_t tail_px;                // pixels of the tail box (0 = none)
   uint32_t plane_stride16;        // ring plane stride, 16-byte units
-  uint32_t a_off[16];             // A-descriptor offset of (dx, K-step): dx + 2*ks*plane_stride16 (read as constants)
+  uint32_t a_off[40];             // A-descriptor offset of (dx, K-step): dx + 2*ks*plane_stride16 (read as constants)
   const void* wimg;               // packed bf16 weights (global), layout = smem image
   const uint4* in;                // row-streaming: chunk-planar source activation (1-D bulk row copies)
   const uint4* zero_row;          // row-streaming: W x 16 zero bytes (rows outside the image)
@@ -133,9 +138,9 @@ __device__ __forceinline__ int tc_num_tiles(const TcParams& p, int th) {
 // B image (weights) is [mma][k-half][n][8]: LBO = N (16-byte units), SBO = 128 B for A and B.
 //   PST16 > 0: the plane stride is a compile-time constant (geometry-specialised instantiation): every A
 //   offset becomes an immediate, which is what keeps ptxas from hoisting/spilling uniform registers.
-template <int N, int KS, int NKS, int PST16>
+template <int N, int KS, int NKS, int PST16, bool TF>
 __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, const uint32_t (&rb)[KS], uint32_t Ps,
-                                              const uint32_t (&a_off)[16], uint32_t w_base16, uint32_t idesc) {
+                                              const uint32_t (&a_off)[40], uint32_t w_base16, uint32_t idesc) {
   constexpr uint64_t DESC_HI = (uint64_t)(8u | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
   // start addresses stay below 2^14, so the LBO field can be OR-ed in once and offsets added after
   const uint32_t wb = w_base16 | ((uint32_t)N << 16);
@@ -148,8 +153,8 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, const uint32_t (&
         for (int ks = 0; ks < NKS; ++ks) {
           const int e = (dy * KS + dx) * NKS + ks;
           const uint32_t off = PST16 ? (uint32_t)(dx + 2 * ks * PST16) : a_off[dx * NKS + ks];
-          tc_mma_bf16(d_tmem, DESC_HI | (rb[dy] + off),
-                      DESC_HI | (wb + (uint32_t)(e * 2 * N)), idesc, e > 0 ? 1u : 0u);
+          tc_mma<TF>(d_tmem, DESC_HI | (rb[dy] + off),
+                     DESC_HI | (wb + (uint32_t)(e * 2 * N)), idesc, e > 0 ? 1u : 0u);
         }
       }
     }
@@ -161,8 +166,8 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, const uint32_t (&
       const int tb = ta + 1;
       const uint32_t sa = (uint32_t)(ta / KS) * Ps + (uint32_t)(ta % KS);
       const uint32_t sb = (uint32_t)(tb / KS) * Ps + (uint32_t)(tb % KS);
-      tc_mma_bf16(d_tmem, DESC_HI | ((rb[ta / KS] + (uint32_t)(ta % KS)) | ((sb - sa) << 16)),
-                  DESC_HI | (wb + (uint32_t)(q * 2 * N)), idesc, q > 0 ? 1u : 0u);
+      tc_mma<TF>(d_tmem, DESC_HI | ((rb[ta / KS] + (uint32_t)(ta % KS)) | ((sb - sa) << 16)),
+                 DESC_HI | (wb + (uint32_t)(q * 2 * N)), idesc, q > 0 ? 1u : 0u);
     }
   }
 }
@@ -179,8 +184,8 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, const uint32_t (&
 // WRAP: the accumulator blocks straddle the end of the slot ring (second run from slot 0) -- a compile-time
 // flag so that the common case carries no predicated-off instructions; id0/id1/id1n/idn are the instruction
 // descriptors (N = blocks * Cout) loaded once per row, not once per MMA.
-template <int N, int KS, int NKS, int PST16, bool WRAP>
-__device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, uint32_t rb, const uint32_t (&a_off)[16],
+template <int N, int KS, int NKS, int PST16, bool WRAP, bool TF>
+__device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, uint32_t rb, const uint32_t (&a_off)[40],
                                              uint32_t w_base16, int c0, int c1, int boff, bool has_new, int n0, int n1,
                                              uint32_t id_c0, uint32_t id_c1, uint32_t id_n0, uint32_t id_n1, uint32_t id_1) {
   constexpr uint64_t DESC_HI = (uint64_t)(8u | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
@@ -199,12 +204,12 @@ __device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, ui
       const uint64_t ad = DESC_HI | (rb + off);
       const uint32_t eo = (uint32_t)e * 2u * NB;
       if (e == 0) {
-        if (n0 > 0) tc_mma_bf16(d0, ad, DESC_HI | (wb + eo), id_n0, 1u);
-        if (WRAP && n1 > 0) tc_mma_bf16(tmem_base, ad, DESC_HI | (wb1 + eo), id_n1, 1u);
-        if (has_new) tc_mma_bf16(dn, ad, DESC_HI | (wn + eo), id_1, 0u);
+        if (n0 > 0) tc_mma<TF>(d0, ad, DESC_HI | (wb + eo), id_n0, 1u);
+        if (WRAP && n1 > 0) tc_mma<TF>(tmem_base, ad, DESC_HI | (wb1 + eo), id_n1, 1u);
+        if (has_new) tc_mma<TF>(dn, ad, DESC_HI | (wn + eo), id_1, 0u);
       } else {
-        tc_mma_bf16(d0, ad, DESC_HI | (wb + eo), id_c0, 1u);
-        if (WRAP) tc_mma_bf16(tmem_base, ad, DESC_HI | (wb1 + eo), id_c1, 1u);
+        tc_mma<TF>(d0, ad, DESC_HI | (wb + eo), id_c0, 1u);
+        if (WRAP) tc_mma<TF>(tmem_base, ad, DESC_HI | (wb1 + eo), id_c1, 1u);
       }
     }
   }
@@ -219,6 +224,7 @@ struct TcTileIter {
   int xoff = 0;                                  // row-streaming: first image column of the item's 128-column segment
   int ps = 0;                                    // compile-time ring pitch of a specialised kernel (0: p.Ps)
   int it_end = 0;                                // table mode (row-streaming): item = index into p.itab
+  int cta = 0, ncta = 1;                         // work range of this CTA / number of ranges (grid / nsplit)
   __device__ __forceinline__ void load_item(const TcParams& p) {
     if (p.itab) {
       if (item < it_end) {
@@ -241,14 +247,15 @@ struct TcTileIter {
     t = 0; row = 0; rem = 0; seg = 0;
   }
   __device__ __forceinline__ void init(const TcParams& p) {
-    if (p.itab) { item = __ldg(p.coff + blockIdx.x); it_end = __ldg(p.coff + blockIdx.x + 1); }
-    else item = blockIdx.x;
+    cta = (int)blockIdx.x / p.nsplit; ncta = (int)gridDim.x / p.nsplit;
+    if (p.itab) { item = __ldg(p.coff + cta); it_end = __ldg(p.coff + cta + 1); }
+    else item = cta;
     load_item(p);
   }
   __device__ __forceinline__ bool valid(const TcParams& p) const { return p.itab ? item < it_end : item < p.items; }
   __device__ __forceinline__ bool last_of_item() const { return t + 1 >= ntiles; }
   __device__ __forceinline__ void next(const TcParams& p) {
-    if (++t >= ntiles) { item += p.itab ? 1 : (int)gridDim.x; load_item(p); return; }
+    if (++t >= ntiles) { item += p.itab ? 1 : ncta; load_item(p); return; }
     if (p.itab) { ++row; return; }
     const int Ps = ps ? ps : p.Ps;
     if (p.segs) {
@@ -285,9 +292,13 @@ __device__ __forceinline__ void tc_transposed_sum(float* v, int lane) {
 
 // PS / PST16: ring pitch and plane stride as compile-time constants (0 = read them from the parameters).
 // RS: row-streaming variant (W == 128, one tile per output row): see tc_issue_row.
-template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS>
+// TF: tf32 operands -- planes hold 4 fp32 channels (still 16 bytes per pixel), K = 8 per MMA = two planes, NKS = C/8.
+template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS, bool TF>
 __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int PW = TF ? 4 : 8;                       // channels per plane
+  const int cta = (int)blockIdx.x / p.nsplit, ncta = (int)gridDim.x / p.nsplit;
+  const int csplit = (int)blockIdx.x - cta * p.nsplit; // this CTA's block of N output channels
   constexpr int NTHREADS = tc_threads(N);
   constexpr int EW = tc_epi_warps(N);
   constexpr int NC = (EW == 8) ? N / 2 : N;            // accumulator columns per epilogue warp
@@ -348,7 +359,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       if (warp == 0 && lane == 0) {                // weights: one shot, resident for the whole kernel
         const uint32_t wbar = smem_u32(&sb->wbar);
         mbar_expect_tx(wbar, p.w_bytes);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)csplit * p.w_bytes;
         for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
           const uint32_t n = (p.w_bytes - off < 16384u) ? (p.w_bytes - off) : 16384u;
           bulk_load_1d(smem_u32(s_w + off), src + off, n, wbar);
@@ -369,7 +380,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       int g_row = 0, slot2 = 0;
       uint32_t phase2 = 0;
       if (prod_leader) {
-        for (int item = __ldg(p.coff + blockIdx.x), it_end = __ldg(p.coff + blockIdx.x + 1); item < it_end; ++item) {
+        for (int item = __ldg(p.coff + cta), it_end = __ldg(p.coff + cta + 1); item < it_end; ++item) {
           const int4 d = __ldg(p.itab + item);
           const int n = d.x, y0 = d.y, seg = d.w >> 7;
           const int nrows = d.z + 2 * pad;
@@ -408,8 +419,10 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
             // have requested (microseconds under load), which three tiles of register prefetch do not cover --
             // pull the row into L2 now.
             if (p.apf && inside && j >= pad && j < nrows - pad) {
-              const uint4* ap = p.actp + ((size_t)n * p.nch_out + c_lo) * plane_px + (size_t)y * p.W + seg * 128;
-              for (int c = c_lo; c < c_hi; ++c) {
+              // (this CTA's N/PW planes of the saved activation, half of them per producer warp)
+              const int np = N / PW, q_lo = (np * pw) / 2, q_hi = (np * (pw + 1)) / 2;
+              const uint4* ap = p.actp + ((size_t)n * p.nch_out + csplit * np + q_lo) * plane_px + (size_t)y * p.W + seg * 128;
+              for (int c = q_lo; c < q_hi; ++c) {
                 bulk_prefetch_l2(ap, 128u * 16u);
                 ap += plane_px;
               }
@@ -427,7 +440,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     if (lane == 0) {  // weights: one shot, resident for the whole kernel
       const uint32_t wbar = smem_u32(&sb->wbar);
       mbar_expect_tx(wbar, p.w_bytes);
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)csplit * p.w_bytes;
       for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
         const uint32_t n = (p.w_bytes - off < 16384u) ? (p.w_bytes - off) : 16384u;
         bulk_load_1d(smem_u32(s_w + off), src + off, n, wbar);
@@ -442,7 +455,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     const bool prod_leader = elect_one_sync();
     int slot = 0;
     uint32_t phase = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    for (int item = cta; item < p.items; item += ncta) {
       const int im = p.rev ? p.items - 1 - item : item;
       const int n = im / p.strips, y0 = (im - n * p.strips) * p.TH;
       const int th = (p.H - y0 < p.TH) ? (p.H - y0) : p.TH;
@@ -485,14 +498,15 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         const uint32_t w_base16 = smem_u32(s_w) >> 4;
         int slot = 0; uint32_t rph = 0;            // ring slot / phase of the next input row
         int qg = 0;                                // output rows (tiles) of all previous items of this CTA
-        for (int item = __ldg(p.coff + blockIdx.x), it_end = __ldg(p.coff + blockIdx.x + 1); item < it_end; ++item) {
+        for (int item = __ldg(p.coff + cta), it_end = __ldg(p.coff + cta + 1); item < it_end; ++item) {
           const int TH = __ldg(p.itab + item).z;   // rows of this item (1 .. H)
           const int nrows = TH + 2 * pad;
           // Rows are handled in units of TC_RS_UNIT: all barrier waits of a unit first, then its MMAs back to
           // back.  A wait costs 70-150 cycles even when the barrier has long completed, and the tensor pipe's
           // instruction queue is short, so per-row waits left the pipe idle between rows.
-          for (int j0 = 0; j0 < nrows; j0 += TC_RS_UNIT) {
-            const int ju = (nrows - j0 < TC_RS_UNIT) ? nrows - j0 : TC_RS_UNIT;
+          const int unit = p.rs_unit;
+          for (int j0 = 0; j0 < nrows; j0 += unit) {
+            const int ju = (nrows - j0 < unit) ? nrows - j0 : unit;
             // lanes wait in parallel: lane u on the ring row of unit row u, lane 16+u on the accumulator slot
             // that row opens (a wait costs 70-150 cycles even when the barrier completed long ago)
             if (lane < ju) {
@@ -526,10 +540,10 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
                              id_1 = p.idesc_n[1];
               if (leader) {
                 if (c1 > 0)
-                  tc_issue_row<N, KS, NKS, PST16, true>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
+                  tc_issue_row<N, KS, NKS, PST16, true, TF>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
                                                         id_c1, id_n0, id_n1, id_1);
                 else
-                  tc_issue_row<N, KS, NKS, PST16, false>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
+                  tc_issue_row<N, KS, NKS, PST16, false, TF>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
                                                          id_c1, id_n0, id_n1, id_1);
                 if (j >= KS - 1) tc_commit(smem_u32(&sb->tfull[(qg + j - (KS - 1)) & (ACC - 1)]));   // row complete
                 tc_commit(smem_u32(&sb->empty[slot]));                                             // ring row consumed
@@ -557,7 +571,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     // Lean tile iterator: every work item is TH rows (TH divides H), so a tile is (item ordinal k, tile t)
     // with constant tiles / halo rows per item, stepped without divisions.
     const int NT = p.NT, nrows = p.TH + 2 * pad, segs = p.segs;
-    const int my_items = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_items = ((int)p.items - cta + ncta - 1) / ncta;
     int k = 0, t = 0, row = 0, rem = 0, seg = 0;
     // ring bookkeeping in (slot, phase) form; g_* count halo rows since the kernel started
     int g0 = 0, slot0 = 0;                         // first halo row of the iterator's current item
@@ -614,7 +628,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       for (int i = 0; i < TC_ISSUERS && k < my_items; ++i) advance();
       const int free_upto = (k < my_items) ? g0 + row : g0;
       if (leader) {
-        tc_issue_tile<N, KS, NKS, PST16>(d_tmem, rb, (uint32_t)Ps, p.a_off, wb_t, p.idesc);
+        tc_issue_tile<N, KS, NKS, PST16, TF>(d_tmem, rb, (uint32_t)Ps, p.a_off, wb_t, p.idesc);
         tc_commit(smem_u32(&sb->tfull[stage]));
         int f = fs;
         for (int rf = g_freed; rf < free_upto; ++rf) {
@@ -639,7 +653,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
     const int half = (EW == 8) ? (warp - 1 - TC_ISSUERS) / 4 : 0;
     const int col0 = half * NC;                    // first accumulator column / output channel
-    const int k0 = col0 / 8;                       // first output plane
+    const int k0 = csplit * (N / PW) + col0 / PW;   // first output plane of this warp in the layer's plane list
     const int H = p.H, W = p.W;
     const size_t plane_sz = (size_t)H * W;
     constexpr bool DG = (EPI == EPI_DGRAD || EPI == EPI_DSUM);   // epilogues that read the saved activation
@@ -647,9 +661,9 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     constexpr int NB = (EPI == EPI_FWD) ? NC : 4;
     float bias_r[NB];
 #pragma unroll
-    for (int i = 0; i < NB; ++i) bias_r[i] = DG ? 0.f : __ldg(p.bias + col0 + i);
+    for (int i = 0; i < NB; ++i) bias_r[i] = DG ? 0.f : __ldg(p.bias + csplit * N + col0 + i);
 
-    constexpr int NAV = DG ? NC / 8 : 1;
+    constexpr int NAV = DG ? NC / PW : 1;
     // position of this thread's output pixel in tile `it`, or -1
     auto pix_of = [&](const TcTileIter& it) -> long long {
       int r = it.row, c = it.rem + quad * 32 + lane;
@@ -661,7 +675,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     auto load_prev = [&](const TcTileIter& it, long long pix, uint4* av) {
 #pragma unroll
       for (int k = 0; k < NAV; ++k)
-        av[k] = (pix >= 0 && !(p.dbg & 8)) ? __ldg(p.actp + ((size_t)it.n * (N / 8) + k0 + k) * plane_sz + (size_t)pix)
+        av[k] = (pix >= 0 && !(p.dbg & 8)) ? __ldg(p.actp + ((size_t)it.n * p.nch_out + k0 + k) * plane_sz + (size_t)pix)
                            : make_uint4(0u, 0u, 0u, 0u);
     };
 
@@ -675,9 +689,9 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
     int ntotal;                                    // tiles this CTA writes
     if (p.itab) {
       ntotal = 0;
-      for (int i = __ldg(p.coff + blockIdx.x); i < __ldg(p.coff + blockIdx.x + 1); ++i) ntotal += __ldg(p.itab + i).z;
+      for (int i = __ldg(p.coff + cta); i < __ldg(p.coff + cta + 1); ++i) ntotal += __ldg(p.itab + i).z;
     } else {
-      const int my_items_e = ((int)p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int my_items_e = ((int)p.items - cta + ncta - 1) / ncta;
       ntotal = (my_items_e > 0 ? my_items_e : 0) * p.NT;
     }
     // EPI_DSUM keeps NC running sums per thread; it pays for those registers with the prefetch queue (one tile of
@@ -732,9 +746,9 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
           }
           tc_transposed_sum<DS_NV, 16>(ds_sum, lane);               // lane (j << DS_SH): row-class sum of channel j
           if ((lane & ((1 << DS_SH) - 1)) == 0) {
-            float* g = p.G + ((size_t)ds_n * 9 + ds_rc * 3) * N + col0 + (lane >> DS_SH);
-            atomicAdd(g + N, ds_sum[0] - col);                      // interior columns
-            if (bl) atomicAdd(g + side * N, col);
+            float* g = p.G + ((size_t)ds_n * 9 + ds_rc * 3) * p.n_tot + csplit * N + col0 + (lane >> DS_SH);
+            atomicAdd(g + p.n_tot, ds_sum[0] - col);                // interior columns
+            if (bl) atomicAdd(g + side * p.n_tot, col);
           }
         }
 #pragma unroll
@@ -773,19 +787,30 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         ds_pix = pi;
         auto accumulate = [&](auto h16) {
           constexpr bool H16 = decltype(h16)::value;
+          if constexpr (TF) {
 #pragma unroll
-          for (int k = 0; k < NC / 8; ++k) {
-            const uint32_t aw[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+            for (int k = 0; k < NC / 4; ++k) {
+              const uint32_t aw[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 a;
-              if constexpr (H16) a = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
-              else a = make_float2(__uint_as_float(aw[e] << 16), __uint_as_float(aw[e] & 0xffff0000u));
-              // ELU'(x) from a = ELU(x): 1 for a > 0, a + 1 otherwise = min(a, 0) + 1
-              ds_sum[k * 8 + 2 * e] = fmaf(__uint_as_float(acc[k * 8 + 2 * e]), fminf(a.x, 0.f) + 1.f, ds_sum[k * 8 + 2 * e]);
-              ds_sum[k * 8 + 2 * e + 1] = fmaf(__uint_as_float(acc[k * 8 + 2 * e + 1]), fminf(a.y, 0.f) + 1.f, ds_sum[k * 8 + 2 * e + 1]);
+              for (int e = 0; e < 4; ++e)
+                ds_sum[k * 4 + e] = fmaf(__uint_as_float(acc[k * 4 + e]), fminf(__uint_as_float(aw[e]), 0.f) + 1.f, ds_sum[k * 4 + e]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < NC / 8; ++k) {
+              const uint32_t aw[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 a;
+                if constexpr (H16) a = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
+                else a = make_float2(__uint_as_float(aw[e] << 16), __uint_as_float(aw[e] & 0xffff0000u));
+                // ELU'(x) from a = ELU(x): 1 for a > 0, a + 1 otherwise = min(a, 0) + 1
+                ds_sum[k * 8 + 2 * e] = fmaf(__uint_as_float(acc[k * 8 + 2 * e]), fminf(a.x, 0.f) + 1.f, ds_sum[k * 8 + 2 * e]);
+                ds_sum[k * 8 + 2 * e + 1] = fmaf(__uint_as_float(acc[k * 8 + 2 * e + 1]), fminf(a.y, 0.f) + 1.f, ds_sum[k * 8 + 2 * e + 1]);
+              }
             }
           }
+          (void)H16;
         };
         if (F16) accumulate(std::true_type{});
         else accumulate(std::false_type{});
@@ -800,6 +825,27 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
           reinterpret_cast<float4*>(p.out)[(size_t)cn * plane_sz + (size_t)pix] = o;
         } else {
           uint4* outp = reinterpret_cast<uint4*>(p.out);
+          if constexpr (TF) {
+#pragma unroll
+            for (int k = 0; k < NC / 4; ++k) {
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(acc[k * 4 + e]);
+              if constexpr (EPI == EPI_FWD) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = elu_fast(v[e] + bias_r[k * 4 + e]);
+              } else {
+                const uint32_t aw[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] *= elu_grad_from_act(__uint_as_float(aw[e]));
+              }
+              // stored ROUNDED to tf32: the next layer's tensor core would otherwise truncate the low 13 bits
+              uint4 o;
+              o.x = __float_as_uint(to_tf32(v[0])); o.y = __float_as_uint(to_tf32(v[1]));
+              o.z = __float_as_uint(to_tf32(v[2])); o.w = __float_as_uint(to_tf32(v[3]));
+              outp[((size_t)cn * p.nch_out + k0 + k) * plane_sz + (size_t)pix] = o;
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < NC / 8; ++k) {
             float v[8];
@@ -822,7 +868,8 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
             o.y = pack_h2(v[2], v[3], F16);
             o.z = pack_h2(v[4], v[5], F16);
             o.w = pack_h2(v[6], v[7], F16);
-            outp[((size_t)cn * (N / 8) + k0 + k) * plane_sz + (size_t)pix] = o;
+            outp[((size_t)cn * p.nch_out + k0 + k) * plane_sz + (size_t)pix] = o;
+          }
           }
         }
       }
@@ -876,11 +923,17 @@ struct TcState {
   uint16_t* w_bwd_rs[IODINE_MAX_LAYERS];
   uint16_t* w_out_rs = nullptr;
   void* zero_row = nullptr;              // W x 16 zero bytes
-  int4* itab = nullptr;                  // row-streaming work list (device)
-  int32_t* coff = nullptr;
-  int rs_grid = 0;
+  // row-streaming work lists (device): [0] one CTA per range (grid = SMs), [1] nsplit_cc CTAs per range
+  int4* itab[2] = {nullptr, nullptr};
+  int32_t* coff[2] = {nullptr, nullptr};
+  int rs_grid[2] = {0, 0};
   TcGeom g_cc_rs, g_out_rs;
   bool attr_done = false;
+  bool tf = false;                       // tf32 operands (planes of 4 fp32 channels)
+  int pw = 8;                            // channels per plane
+  int nsplit_cc = 1;                     // CTAs per work range of the C->C layers (output-channel blocks)
+  int nsplit_in4 = 1;                    // the same for the 4->C data-gradient (tf32 C=64: the epilogue's prefetch
+                                         // queue of the saved activation would not fit the register file at N=64)
 };
 
 static TcState* tc_state(Plan* p) { return reinterpret_cast<TcState*>(p->tc); }
@@ -955,19 +1008,62 @@ static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo
   return g->smem <= (size_t)227 * 1024;
 }
 
+// C->C layers: geometry for `nsplit` CTAs per work range, each computing C / nsplit output channels
+static bool tc_geometry_cc(const Plan* p, int nsplit, bool rs, TcGeom* g) {
+  const IodineShape& s = p->s;
+  const int pw = tf_mode(p) ? 4 : 8, planes = p->C / pw, kk = s.dec_k * s.dec_k;
+  const int N = p->C / nsplit;
+  if (N < 16 || N % 16) return false;
+  return tc_geometry(p, planes, N, kk * (planes / 2), 0, g, rs);
+}
+static bool tc_rs_shape(const Plan* p) {
+  return p->s.W % 128 == 0 && p->s.dec_k == 3 && !getenv("IODINE_TC_NO_RS");
+}
+// smallest channel split whose weight image leaves room for the ring (row-streaming: >= 4 ring rows)
+static int tc_pick_split(const Plan* p, bool rs, TcGeom* g) {
+  for (int ns = 1; ns <= 2; ns *= 2)
+    if (tc_geometry_cc(p, ns, rs, g) && (!rs || g->R >= 4)) return ns;
+  return 0;
+}
+
 int tc_supported(const Plan* p) {
   const IodineShape& s = p->s;
-  const int C = s.dec_chan, kk = s.dec_k * s.dec_k;
+  const int C = s.dec_chan;
   TcGeom g;
-  if (C % 16 != 0) { set_error("16-bit modes: DEC.CONV_CHAN=%d must be a multiple of 16", C); return 0; }
-  const int n_cc = kk * (C / 16);
-  const bool rs_ok = s.W % 128 == 0 && s.dec_k == 3 && !getenv("IODINE_TC_NO_RS") && tc_geometry(p, C / 8, C, n_cc, 0, &g, true);
-  if (!rs_ok && !tc_geometry(p, C / 8, C, n_cc, 0, &g)) {
-    set_error("16-bit modes: decoder shape (C=%d, k=%d, W=%d) does not fit the tensor-core kernel's shared memory",
-              C, s.dec_k, s.W);
-    return 0;
+  if (C % 16 != 0) { set_error("tensor-core modes: DEC.CONV_CHAN=%d must be a multiple of 16", C); return 0; }
+  if ((tc_rs_shape(p) && tc_pick_split(p, true, &g)) || tc_pick_split(p, false, &g)) return 1;
+  set_error("tensor-core modes: decoder shape (C=%d, k=%d, W=%d) does not fit the tensor-core kernel's shared memory",
+            C, s.dec_k, s.W);
+  return 0;
+}
+
+// work list: CTA range c owns units [c U / G, (c+1) U / G) of the flattened (slot-image, segment, row) space
+static int tc_build_worklist(Plan* p, TcState* st, int which, int G_max) {
+  const IodineShape& s = p->s;
+  const int segs = s.W / 128;
+  const long long U = (long long)p->BK * segs * s.H;
+  const int G = (int)(U < G_max ? U : G_max);
+  std::vector<int4> items;
+  std::vector<int32_t> off(G + 1);
+  for (int c = 0; c < G; ++c) {
+    off[c] = (int32_t)items.size();
+    long long u0 = U * c / G;
+    const long long u1 = U * (c + 1) / G;
+    while (u0 < u1) {
+      const long long col = u0 / s.H;
+      const int y0 = (int)(u0 - col * s.H);
+      const int th = (int)((s.H - y0 < u1 - u0) ? (s.H - y0) : (u1 - u0));
+      items.push_back(make_int4((int)(col / segs), y0, th, (int)(col % segs) * 128));
+      u0 += th;
+    }
   }
-  return 1;
+  off[G] = (int32_t)items.size();
+  st->rs_grid[which] = G;
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->itab[which], items.size() * sizeof(int4)));
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->coff[which], off.size() * sizeof(int32_t)));
+  IOD_CHECK_CUDA(cudaMemcpy(st->itab[which], items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  IOD_CHECK_CUDA(cudaMemcpy(st->coff[which], off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return 0;
 }
 
 int tc_alloc(Plan* p) {
@@ -975,63 +1071,47 @@ int tc_alloc(Plan* p) {
   p->tc = st;
   const IodineShape& s = p->s;
   const int C = p->C, kk = s.dec_k * s.dec_k, pad = s.dec_k / 2;
+  st->tf = tf_mode(p);
+  st->pw = st->tf ? 4 : 8;
+  const int planes = C / st->pw;
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { st->w_fwd[l] = nullptr; st->w_bwd[l] = nullptr; }
-  st->n_ent_cc = kk * (C / 16);
+  st->n_ent_cc = kk * (planes / 2);
   st->n_ent_in4 = (kk + 1) / 2;
   const int Ps = round_up(s.W + 2 * pad, 8);
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { st->w_fwd_rs[l] = nullptr; st->w_bwd_rs[l] = nullptr; }
-  st->rs = s.W % 128 == 0 && s.dec_k == 3 && !getenv("IODINE_TC_NO_RS") &&
-           tc_geometry(p, C / 8, C, st->n_ent_cc, 0, &st->g_cc_rs, true) &&
-           tc_geometry(p, C / 8, 16, st->n_ent_cc, 0, &st->g_out_rs, true);
+  st->rs = false;
+  if (tc_rs_shape(p)) {
+    const int ns = tc_pick_split(p, true, &st->g_cc_rs);
+    if (ns && tc_geometry(p, planes, 16, st->n_ent_cc, 0, &st->g_out_rs, true)) { st->rs = true; st->nsplit_cc = ns; }
+  }
   if (!st->rs) {
-    IOD_REQUIRE(tc_geometry(p, C / 8, C, st->n_ent_cc, 0, &st->g_cc), "tc geometry (C->C) failed");
-    IOD_REQUIRE(tc_geometry(p, C / 8, 16, st->n_ent_cc, 0, &st->g_out), "tc geometry (C->4) failed");
+    st->nsplit_cc = tc_pick_split(p, false, &st->g_cc);
+    IOD_REQUIRE(st->nsplit_cc > 0, "tc geometry (C->C) failed");
+    IOD_REQUIRE(tc_geometry(p, planes, 16, st->n_ent_cc, 0, &st->g_out), "tc geometry (C->4) failed");
   } else {
     st->g_cc = st->g_cc_rs;                    // (sizes the weight images; the generic C->C kernels are not launched)
     st->g_out = st->g_out_rs;
   }
-  IOD_REQUIRE(tc_geometry(p, 1, C, st->n_ent_in4, Ps, &st->g_in4), "tc geometry (4->C) failed");
+  st->nsplit_in4 = (st->tf && C == 64) ? 2 : 1;
+  IOD_REQUIRE(tc_geometry(p, 1, C / st->nsplit_in4, st->n_ent_in4, Ps, &st->g_in4), "tc geometry (4->C) failed");
+  const size_t cc_bytes = (size_t)st->g_cc.w_bytes * st->nsplit_cc;   // one image per output-channel block
   if (st->rs) {
     for (int l = 1; l < s.dec_layers; ++l) {
-      IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd_rs[l], st->g_cc_rs.w_bytes));
-      IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_bwd_rs[l], st->g_cc_rs.w_bytes));
+      IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd_rs[l], cc_bytes));
+      IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_bwd_rs[l], cc_bytes));
     }
     IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_out_rs, st->g_out_rs.w_bytes));
     IOD_CHECK_CUDA(cudaMalloc(&st->zero_row, 4096));
     IOD_CHECK_CUDA(cudaMemset(st->zero_row, 0, 4096));
-    // work list: CTA c owns units [c U / G, (c+1) U / G) of the flattened (slot-image, segment, row) space
-    {
-      const int segs = s.W / 128;
-      const long long U = (long long)p->BK * segs * s.H;
-      const int G = (int)(U < p->num_sms ? U : p->num_sms);
-      std::vector<int4> items;
-      std::vector<int32_t> off(G + 1);
-      for (int c = 0; c < G; ++c) {
-        off[c] = (int32_t)items.size();
-        long long u0 = U * c / G;
-        const long long u1 = U * (c + 1) / G;
-        while (u0 < u1) {
-          const long long col = u0 / s.H;
-          const int y0 = (int)(u0 - col * s.H);
-          const int th = (int)((s.H - y0 < u1 - u0) ? (s.H - y0) : (u1 - u0));
-          items.push_back(make_int4((int)(col / segs), y0, th, (int)(col % segs) * 128));
-          u0 += th;
-        }
-      }
-      off[G] = (int32_t)items.size();
-      st->rs_grid = G;
-      IOD_CHECK_CUDA(cudaMalloc((void**)&st->itab, items.size() * sizeof(int4)));
-      IOD_CHECK_CUDA(cudaMalloc((void**)&st->coff, off.size() * sizeof(int32_t)));
-      IOD_CHECK_CUDA(cudaMemcpy(st->itab, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
-      IOD_CHECK_CUDA(cudaMemcpy(st->coff, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    }
+    if (tc_build_worklist(p, st, 0, p->num_sms)) return 1;
+    if (st->nsplit_cc > 1 && tc_build_worklist(p, st, 1, p->num_sms / st->nsplit_cc)) return 1;
   }
   for (int l = 1; l < s.dec_layers; ++l) {
-    IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd[l], st->g_cc.w_bytes));
-    IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_bwd[l], st->g_cc.w_bytes));
+    IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_fwd[l], cc_bytes));
+    IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_bwd[l], cc_bytes));
   }
   IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_out, st->g_out.w_bytes));
-  IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_in4, st->g_in4.w_bytes));
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_in4, (size_t)st->g_in4.w_bytes * st->nsplit_in4));
   IOD_CHECK_CUDA(cudaMalloc((void**)&st->ptab_c, (size_t)p->HW * C * sizeof(float)));
   return 0;
 }
@@ -1044,8 +1124,7 @@ void tc_free(Plan* p) {
   }
   cudaFree(st->w_out_rs);
   cudaFree(st->zero_row);
-  cudaFree(st->itab);
-  cudaFree(st->coff);
+  for (int i = 0; i < 2; ++i) { cudaFree(st->itab[i]); cudaFree(st->coff[i]); }
   cudaFree(st->w_out); cudaFree(st->w_in4); cudaFree(st->ptab_c);
   delete st;
   p->tc = nullptr;
@@ -1054,7 +1133,7 @@ void tc_free(Plan* p) {
 int tc_on_workspace(Plan* p) {
   TcState* st = tc_state(p);
   const IodineShape& s = p->s;
-  const int pad = s.dec_k / 2, planes = p->C / 8;
+  const int pad = s.dec_k / 2, planes = p->C / st->pw;
   for (int l = 0; l < s.dec_layers; ++l)
     if (make_map(&st->map_act[l], p->act[l], s.W, s.H, planes, p->BK, pad)) return 1;
   if (s.dec_layers > 1)
@@ -1079,41 +1158,52 @@ __device__ __forceinline__ float from_h(uint16_t u, int f16) {
   return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
 }
 
-__global__ void tc_pack_cc_kernel(const float* __restrict__ w, uint16_t* __restrict__ fwd,
-                                  uint16_t* __restrict__ bwd, int C, int NO, int N, int KS, int f16) {
-  // w is OIHW [NO][C][KS][KS]; fwd image has N >= NO output rows (zero padded); bwd needs NO == C == N
-  const int nks = C / 16;
-  const int total = KS * KS * nks * 2 * N * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i % 8, n = (i / 8) % N, kc = (i / (8 * N)) % 2, ks = (i / (16 * N)) % nks, tap = i / (16 * N * nks);
-    const int dy = tap / KS, dx = tap % KS;
-    const int k = (2 * ks + kc) * 8 + e;
-    if (fwd) fwd[i] = to_h(n < NO ? w[(((size_t)n * C + k) * KS + dy) * KS + dx] : 0.f, f16);
-    if (bwd) bwd[i] = to_h(w[(((size_t)k * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)], f16);
+// One kernel for every C -> X weight image.  rs = 0: entry = tap*nks + ks (image [entry][k-half][n][PW]);
+// rs = 1: entry = dx*nks + ks and the KS tap rows stacked along n (image [entry][k-half][b*N + n][PW], block b <-> tap
+// row dy = KS-1-b: the oldest of the KS output rows an input row feeds comes first).  PW = 8 16-bit elements or 4 tf32
+// elements per (n, k-half); nks = C / (2 PW) K-steps per tap.  `nsplit` images follow each other, image h holding the
+// output channels h*N .. h*N+N-1 (forward: co, data-gradient: ci).
+__global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ fwd, void* __restrict__ bwd, int C, int NO,
+                               int N, int nsplit, int KS, int rs, int tf, int f16) {
+  const int PW = tf ? 4 : 8, nks = C / (2 * PW);
+  const int per = KS * KS * nks * 2 * N * PW;
+  const int total = per * nsplit;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+    const int h = j / per, i = j - h * per;
+    const int e = i % PW, n = (i / PW) % N;
+    int kc, ks, dy, dx;
+    if (rs) {
+      const int b = (i / (PW * N)) % KS;
+      kc = (i / (PW * N * KS)) % 2; ks = (i / (2 * PW * N * KS)) % nks; dx = i / (2 * PW * N * KS * nks);
+      dy = KS - 1 - b;
+    } else {
+      kc = (i / (PW * N)) % 2; ks = (i / (2 * PW * N)) % nks;
+      const int tap = i / (2 * PW * N * nks);
+      dy = tap / KS; dx = tap % KS;
+    }
+    const int k = (2 * ks + kc) * PW + e, ng = h * N + n;
+    if (fwd) {
+      const float v = ng < NO ? w[(((size_t)ng * C + k) * KS + dy) * KS + dx] : 0.f;
+      if (tf) reinterpret_cast<float*>(fwd)[j] = to_tf32(v);
+      else reinterpret_cast<uint16_t*>(fwd)[j] = to_h(v, f16);
+    }
+    if (bwd) {
+      const float v = w[(((size_t)k * C + ng) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)];
+      if (tf) reinterpret_cast<float*>(bwd)[j] = to_tf32(v);
+      else reinterpret_cast<uint16_t*>(bwd)[j] = to_h(v, f16);
+    }
   }
 }
-// Row-streaming image: [entry = dx*(C/16) + ks][k-half][n' = b*N + n][8], block b <-> tap row dy = KS-1-b
-// (the oldest of the KS output rows an input row feeds comes first); fwd/bwd element as above.
-__global__ void tc_pack_rs_kernel(const float* __restrict__ w, uint16_t* __restrict__ fwd,
-                                  uint16_t* __restrict__ bwd, int C, int NO, int N, int KS, int f16) {
-  const int nks = C / 16;
-  const int total = KS * nks * 2 * KS * N * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i % 8, n = (i / 8) % N, b = (i / (8 * N)) % KS, kc = (i / (8 * N * KS)) % 2,
-              ks = (i / (16 * N * KS)) % nks, dx = i / (16 * N * KS * nks);
-    const int dy = KS - 1 - b;
-    const int k = (2 * ks + kc) * 8 + e;
-    if (fwd) fwd[i] = to_h(n < NO ? w[(((size_t)n * C + k) * KS + dy) * KS + dx] : 0.f, f16);
-    if (bwd) bwd[i] = to_h(w[(((size_t)k * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)], f16);
-  }
-}
-// 4->C data-gradient of decoder.conv [4][C][k][k]; entry = tap pair (2q, 2q+1); the odd tail
-// reuses the previous tap with zero weights in its first half.  B[n=ci][k=o] (o < 4 real).
-__global__ void tc_pack_in4_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int C, int KS, int f16) {
+// 4->C data-gradient of decoder.conv [4][C][k][k]; entry = tap pair (2q, 2q+1), one tap per K half; the odd tail
+// reuses the previous tap with zero weights in its first half.  B[n=ci][k=o] (o < 4 real; 16-bit planes carry 4 zeros).
+__global__ void tc_pack_in4_kernel(const float* __restrict__ w, void* __restrict__ img, int C, int N, int KS, int tf, int f16) {
+  const int PW = tf ? 4 : 8;
   const int kk = KS * KS, npair = (kk + 1) / 2;
-  const int total = npair * 2 * C * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i % 8, n = (i / 8) % C, kc = (i / (8 * C)) % 2, q = i / (16 * C);
+  const int per = npair * 2 * N * PW;                 // one image per block of N output channels
+  const int total = per * (C / N);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+    const int h = j / per, i = j - h * per;
+    const int e = i % PW, n = h * N + (i / PW) % N, kc = (i / (PW * N)) % 2, q = i / (2 * PW * N);
     int tap = 2 * q + kc;
     bool zero = false;
     if (2 * q + 1 >= kk) {            // odd tail: (kk-2, kk-1) with the first half zeroed
@@ -1123,58 +1213,65 @@ __global__ void tc_pack_in4_kernel(const float* __restrict__ w, uint16_t* __rest
     const int dy = tap / KS, dx = tap % KS;
     float v = 0.f;
     if (!zero && e < 4) v = w[(((size_t)e * C + n) * KS + (KS - 1 - dy)) * KS + (KS - 1 - dx)];
-    img[i] = to_h(v, f16);
+    if (tf) reinterpret_cast<float*>(img)[j] = to_tf32(v);
+    else reinterpret_cast<uint16_t*>(img)[j] = to_h(v, f16);
   }
 }
-__global__ void tc_ptab_planar_kernel(const float* __restrict__ ptab, float* __restrict__ ptab_c, int HW, int C) {
+__global__ void tc_ptab_planar_kernel(const float* __restrict__ ptab, float* __restrict__ ptab_c, int HW, int C, int PW) {
   const int total = HW * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i % 8, pix = (i / 8) % HW, k = i / (8 * HW);
-    ptab_c[i] = ptab[(size_t)pix * C + k * 8 + e];
+    const int e = i % PW, pix = (i / PW) % HW, k = i / (PW * HW);
+    ptab_c[i] = ptab[(size_t)pix * C + k * PW + e];
   }
 }
 
 int tc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
   TcState* st = tc_state(p);
   const IodineShape& s = p->s;
-  const int C = p->C, KS = s.dec_k, f16 = s.precision == IODINE_FP16;
-  for (int l = 1; l < s.dec_layers; ++l) {
-    tc_pack_cc_kernel<<<64, 256, 0, st_>>>(w->dec_w[l], st->w_fwd[l], st->w_bwd[l], C, C, C, KS, f16);
-    IOD_LAUNCH_CHECK(p);
-  }
-  tc_pack_cc_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_out, nullptr, C, 4, 16, KS, f16);
+  const int C = p->C, KS = s.dec_k, f16 = half_is_f16(p), tf = st->tf ? 1 : 0, ns = st->nsplit_cc, Ncc = C / ns;
+  if (!st->rs)
+    for (int l = 1; l < s.dec_layers; ++l) {
+      tc_pack_kernel<<<64, 256, 0, st_>>>(w->dec_w[l], st->w_fwd[l], st->w_bwd[l], C, C, Ncc, ns, KS, 0, tf, f16);
+      IOD_LAUNCH_CHECK(p);
+    }
+  tc_pack_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_out, nullptr, C, 4, 16, 1, KS, 0, tf, f16);
   IOD_LAUNCH_CHECK(p);
-  tc_pack_in4_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_in4, C, KS, f16);
+  tc_pack_in4_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_in4, C, C / st->nsplit_in4, KS, tf, f16);
   IOD_LAUNCH_CHECK(p);
   if (st->rs) {
     for (int l = 1; l < s.dec_layers; ++l) {
-      tc_pack_rs_kernel<<<64, 256, 0, st_>>>(w->dec_w[l], st->w_fwd_rs[l], st->w_bwd_rs[l], C, C, C, KS, f16);
+      tc_pack_kernel<<<64, 256, 0, st_>>>(w->dec_w[l], st->w_fwd_rs[l], st->w_bwd_rs[l], C, C, Ncc, ns, KS, 1, tf, f16);
       IOD_LAUNCH_CHECK(p);
     }
-    tc_pack_rs_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_out_rs, nullptr, C, 4, 16, KS, f16);
+    tc_pack_kernel<<<16, 256, 0, st_>>>(w->dec_out_w, st->w_out_rs, nullptr, C, 4, 16, 1, KS, 1, tf, f16);
     IOD_LAUNCH_CHECK(p);
   }
-  tc_ptab_planar_kernel<<<256, 256, 0, st_>>>(p->ptab, st->ptab_c, p->HW, C);   // after pack_ptab (same stream)
+  tc_ptab_planar_kernel<<<256, 256, 0, st_>>>(p->ptab, st->ptab_c, p->HW, C, st->pw);   // after pack_ptab (same stream)
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
 // ---- launch -------------------------------------------------------------------------------------
-static uint32_t make_idesc(int N, bool f16) {
-  // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major A and B,
-  // n_dim = N>>3 @17, m_dim = 128>>4 @24
-  const uint32_t fmt = f16 ? 0u : 1u;           // F16F32Format: 0 = F16, 1 = BF16
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+static uint32_t make_idesc(int N, int fmt) {
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format @7/@10 (F16F32Format: 0 = F16, 1 = BF16, 2 = TF32),
+  // K-major A and B, n_dim = N>>3 @17, m_dim = 128>>4 @24
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+static int operand_fmt(const Plan* p) { return tf_mode(p) ? 2 : (p->s.precision == IODINE_FP16 ? 0 : 1); }
 
-static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcParams* q) {
+// N = output channels computed by one CTA, n_tot = output channels of the layer (nsplit = n_tot / N CTAs per range)
+static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, int n_tot, TcParams* q) {
   const IodineShape& s = p->s;
+  const int pw = tf_mode(p) ? 4 : 8;
   q->nch_in = nch_in;
-  q->nch_out = N / 8;
+  q->nch_out = n_tot / pw;
+  q->n_tot = n_tot;
+  q->nsplit = n_tot / N;
   q->H = s.H; q->W = s.W; q->pad = s.dec_k / 2;
   q->Ps = g.Ps; q->R = g.R; q->m = g.m; q->segs = g.segs; q->TH = g.TH;
   q->strips = (s.H + g.TH - 1) / g.TH;
   q->rs_segs = 0;
+  q->rs_unit = g.R >= 7 ? TC_RS_UNIT : (g.R / 2 > 0 ? g.R / 2 : 1);
   q->rev = 0;
   q->itab = nullptr;
   q->coff = nullptr;
@@ -1182,8 +1279,9 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->apf = 0;
   q->lead = getenv("IODINE_TC_LEAD") ? atoi(getenv("IODINE_TC_LEAD")) : 0;
   q->items = p->BK * q->strips;
-  q->idesc = make_idesc(N, s.precision == IODINE_FP16);
-  for (int c = 0; c < 8; ++c) q->idesc_n[c] = (c >= 1 && c * N <= 256) ? make_idesc(c * N, s.precision == IODINE_FP16) : 0u;
+  const int fmt = operand_fmt(p);
+  q->idesc = make_idesc(N, fmt);
+  for (int c = 0; c < 8; ++c) q->idesc_n[c] = (c >= 1 && c * N <= 256) ? make_idesc(c * N, fmt) : 0u;
   q->f16 = s.precision == IODINE_FP16;
   {
     static const int dbg = getenv("IODINE_TC_DEBUG") ? atoi(getenv("IODINE_TC_DEBUG")) : 0;
@@ -1196,24 +1294,25 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, TcPar
   q->plane_stride16 = g.plane_stride16;
   q->NT = g.segs ? g.TH * g.segs : ((g.TH - 1) * g.Ps + s.W - 1) / 128 + 1;
   const int nks = nch_in / 2, ks_dim = s.dec_k;
-  for (int i = 0; i < 16; ++i) q->a_off[i] = 0;
+  for (int i = 0; i < 40; ++i) q->a_off[i] = 0;
   if (nks > 0)
     for (int dx = 0; dx < ks_dim; ++dx)
       for (int ks = 0; ks < nks; ++ks)
-        if (dx * nks + ks < 16) q->a_off[dx * nks + ks] = (uint32_t)dx + (uint32_t)(2 * ks) * g.plane_stride16;
+        if (dx * nks + ks < 40) q->a_off[dx * nks + ks] = (uint32_t)dx + (uint32_t)(2 * ks) * g.plane_stride16;
 }
 
 // dispatch on the compile-time shape <N, EPI, KS, NKS>
-template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS = false>
+template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS = false, bool TF = false>
 static int tc_launch_g(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
-  auto kern = conv_tc_kernel<N, EPI, KS, NKS, PS, PST16, RS>;
+  auto kern = conv_tc_kernel<N, EPI, KS, NKS, PS, PST16, RS, TF>;
   static bool attr_done = false;
   if (!attr_done) {
     IOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  const int grid = q.items < p->num_sms ? q.items : p->num_sms;
-  kern<<<grid, tc_threads(N), smem, st_>>>(q);
+  const int ranges_max = p->num_sms / q.nsplit;
+  const int ranges = q.items < ranges_max ? q.items : ranges_max;
+  kern<<<ranges * q.nsplit, tc_threads(N), smem, st_>>>(q);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -1232,11 +1331,31 @@ static int tc_launch_k(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_
   if (getenv("IODINE_TC_VERBOSE")) fprintf(stderr, "conv_tc: generic kernel for N=%d EPI=%d KS=%d NKS=%d (Ps=%d, plane stride %d)\n", N, EPI, KS, NKS, ps, pst);
   return tc_launch_g<N, EPI, KS, NKS, 0, 0>(p, q, smem, st_);
 }
+// tf32 instantiations (run-time geometry; NKS = C/8 K-steps of two 4-channel planes)
+template <int N, int EPI, int KS, int NKS>
+static int tc_launch_tf(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
+  if (getenv("IODINE_TC_VERBOSE")) fprintf(stderr, "conv_tc: tf32 kernel N=%d EPI=%d KS=%d NKS=%d nsplit=%d (Ps=%d, plane stride %d, R=%d)\n", N, EPI, KS, NKS, q.nsplit, q.Ps, (int)q.plane_stride16, q.R);
+  return tc_launch_g<N, EPI, KS, NKS, 0, 0, false, true>(p, q, smem, st_);
+}
 
 // row-streaming variant (W == 128, 3x3): C -> C layers and decoder.conv forward
 template <int EPI>
 static int tc_launch_rs(Plan* p, const TcParams& q, size_t smem, bool out4, cudaStream_t st_) {
   const int C = p->C, pst = (int)q.plane_stride16;
+  if (tf_mode(p)) {
+    if (!out4) {
+      if (C == 64 && q.nsplit == 2) return pst == 544 ? tc_launch_g<32, EPI, 3, 8, 136, 544, true, true>(p, q, smem, st_)
+                                                      : tc_launch_g<32, EPI, 3, 8, 136, 0, true, true>(p, q, smem, st_);
+      if (C == 32 && q.nsplit == 1) return tc_launch_g<32, EPI, 3, 4, 136, 0, true, true>(p, q, smem, st_);
+      if (C == 16 && q.nsplit == 1) return tc_launch_g<16, EPI, 3, 2, 136, 0, true, true>(p, q, smem, st_);
+    } else {
+      if (C == 64) return tc_launch_g<16, EPI_OUT4, 3, 8, 136, 0, true, true>(p, q, smem, st_);
+      if (C == 32) return tc_launch_g<16, EPI_OUT4, 3, 4, 136, 0, true, true>(p, q, smem, st_);
+      if (C == 16) return tc_launch_g<16, EPI_OUT4, 3, 2, 136, 0, true, true>(p, q, smem, st_);
+    }
+    set_error("conv_tc (row-streaming, tf32): unsupported C=%d / split %d", C, q.nsplit);
+    return 1;
+  }
   if (!out4) {
     if (C == 64) return pst == 1224 ? tc_launch_g<64, EPI, 3, 4, 136, 1224, true>(p, q, smem, st_)
                                     : tc_launch_g<64, EPI, 3, 4, 136, 0, true>(p, q, smem, st_);
@@ -1252,10 +1371,20 @@ static int tc_launch_rs(Plan* p, const TcParams& q, size_t smem, bool out4, cuda
   return 1;
 }
 
-// C -> C layers (forward / data-gradient): N = C, NKS = C/16
+// C -> C layers (forward / data-gradient): N = C / nsplit, NKS = K-steps per tap
 template <int EPI>
 static int tc_launch_cc(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
   const int C = p->C, KS = p->s.dec_k;
+  if (tf_mode(p)) {
+    if (KS == 3 && C == 64 && q.nsplit == 2) return tc_launch_tf<32, EPI, 3, 8>(p, q, smem, st_);
+    if (KS == 3 && C == 32 && q.nsplit == 1) return tc_launch_tf<32, EPI, 3, 4>(p, q, smem, st_);
+    if (KS == 3 && C == 16 && q.nsplit == 1) return tc_launch_tf<16, EPI, 3, 2>(p, q, smem, st_);
+    if (KS == 5 && C == 32 && q.nsplit == 1) return tc_launch_tf<32, EPI, 5, 4>(p, q, smem, st_);
+    if (KS == 5 && C == 16 && q.nsplit == 1) return tc_launch_tf<16, EPI, 5, 2>(p, q, smem, st_);
+    set_error("conv_tc (tf32): unsupported C=%d k=%d split %d", C, KS, q.nsplit);
+    return 1;
+  }
+  if (q.nsplit != 1) { set_error("conv_tc: channel split %d is a tf32-only geometry", q.nsplit); return 1; }
   if (KS == 3 && C == 64) return tc_launch_k<64, EPI, 3, 4>(p, q, smem, st_);
   if (KS == 3 && C == 32) return tc_launch_k<32, EPI, 3, 2>(p, q, smem, st_);
   if (KS == 3 && C == 16) return tc_launch_k<16, EPI, 3, 1>(p, q, smem, st_);
@@ -1264,9 +1393,18 @@ static int tc_launch_cc(Plan* p, const TcParams& q, size_t smem, cudaStream_t st
   set_error("conv_tc: unsupported C=%d k=%d", C, KS);
   return 1;
 }
-// decoder.conv forward: N = 16 (4 real outputs), NKS = C/16
+// decoder.conv forward: N = 16 (4 real outputs)
 static int tc_launch_o4(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
   const int C = p->C, KS = p->s.dec_k;
+  if (tf_mode(p)) {
+    if (KS == 3 && C == 64) return tc_launch_tf<16, EPI_OUT4, 3, 8>(p, q, smem, st_);
+    if (KS == 3 && C == 32) return tc_launch_tf<16, EPI_OUT4, 3, 4>(p, q, smem, st_);
+    if (KS == 3 && C == 16) return tc_launch_tf<16, EPI_OUT4, 3, 2>(p, q, smem, st_);
+    if (KS == 5 && C == 32) return tc_launch_tf<16, EPI_OUT4, 5, 4>(p, q, smem, st_);
+    if (KS == 5 && C == 16) return tc_launch_tf<16, EPI_OUT4, 5, 2>(p, q, smem, st_);
+    set_error("conv_tc (tf32): unsupported C=%d k=%d", C, KS);
+    return 1;
+  }
   if (KS == 3 && C == 64) return tc_launch_k<16, EPI_OUT4, 3, 4>(p, q, smem, st_);
   if (KS == 3 && C == 32) return tc_launch_k<16, EPI_OUT4, 3, 2>(p, q, smem, st_);
   if (KS == 3 && C == 16) return tc_launch_k<16, EPI_OUT4, 3, 1>(p, q, smem, st_);
@@ -1275,9 +1413,18 @@ static int tc_launch_o4(Plan* p, const TcParams& q, size_t smem, cudaStream_t st
   set_error("conv_tc: unsupported C=%d k=%d", C, KS);
   return 1;
 }
-// decoder.conv data-gradient: one 8-channel input plane, tap pairs (NKS = 0), N = C
+// decoder.conv data-gradient: one input plane (the 4 gradient channels), tap pairs (NKS = 0), N = C
 static int tc_launch_i4(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_) {
   const int C = p->C, KS = p->s.dec_k;
+  if (tf_mode(p)) {
+    if (KS == 3 && C == 64 && q.nsplit == 2) return tc_launch_tf<32, EPI_DGRAD, 3, 0>(p, q, smem, st_);
+    if (KS == 3 && C == 32) return tc_launch_tf<32, EPI_DGRAD, 3, 0>(p, q, smem, st_);
+    if (KS == 3 && C == 16) return tc_launch_tf<16, EPI_DGRAD, 3, 0>(p, q, smem, st_);
+    if (KS == 5 && C == 32) return tc_launch_tf<32, EPI_DGRAD, 5, 0>(p, q, smem, st_);
+    if (KS == 5 && C == 16) return tc_launch_tf<16, EPI_DGRAD, 5, 0>(p, q, smem, st_);
+    set_error("conv_tc (tf32): unsupported C=%d k=%d", C, KS);
+    return 1;
+  }
   if (KS == 3 && C == 64) return tc_launch_k<64, EPI_DGRAD, 3, 0>(p, q, smem, st_);
   if (KS == 3 && C == 32) return tc_launch_k<32, EPI_DGRAD, 3, 0>(p, q, smem, st_);
   if (KS == 3 && C == 16) return tc_launch_k<16, EPI_DGRAD, 3, 0>(p, q, smem, st_);
@@ -1303,6 +1450,13 @@ int tc_dsum_fused(const Plan* p) {
   return st && st->rs && p->s.dec_k == 3 && !getenv("IODINE_TC_NO_DSUM");
 }
 
+static void use_worklist(const Plan* p, const TcState* st, int which, TcParams* q) {
+  q->rs_segs = p->s.W / 128;
+  q->items = st->rs_grid[which];
+  q->itab = st->itab[which];
+  q->coff = st->coff[which];
+}
+
 int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* act_prev, void* out, float* G,
                    cudaStream_t st_) {
   TcState* st = tc_state(p);
@@ -1311,8 +1465,8 @@ int tc_launch_conv(Plan* p, int layer, bool dgrad, const void* in, const void* a
   IOD_REQUIRE(!G || (dgrad && tc_dsum_fused(p)), "conv_tc: fused class sums need the row-streaming data-gradient");
   TcParams q;
   q.maps = *map;
-  fill_common(p, st->rs ? st->g_cc_rs : st->g_cc, p->C / 8, p->C, &q);
-  if (st->rs) { q.rs_segs = p->s.W / 128; q.items = st->rs_grid; q.itab = st->itab; q.coff = st->coff; }
+  fill_common(p, st->rs ? st->g_cc_rs : st->g_cc, p->C / st->pw, p->C / st->nsplit_cc, p->C, &q);
+  if (st->rs) use_worklist(p, st, st->nsplit_cc > 1 ? 1 : 0, &q);
   q.G = G;
   q.apf = (dgrad && st->rs && !getenv("IODINE_TC_NO_APF")) ? 1 : 0;
   // traversal direction: read a buffer in the opposite direction to the one it was written in (the collapsed
@@ -1339,8 +1493,8 @@ int tc_launch_out4(Plan* p, const void* in, float* out4, cudaStream_t st_) {
   IOD_REQUIRE(map != nullptr, "conv_tc: source buffer has no tensor map");
   TcParams q;
   q.maps = *map;
-  fill_common(p, st->rs ? st->g_out_rs : st->g_out, p->C / 8, 16, &q);
-  if (st->rs) { q.rs_segs = p->s.W / 128; q.items = st->rs_grid; q.itab = st->itab; q.coff = st->coff; }
+  fill_common(p, st->rs ? st->g_out_rs : st->g_out, p->C / st->pw, 16, 16, &q);
+  if (st->rs) use_worklist(p, st, 0, &q);
   if (!getenv("IODINE_TC_NO_REV")) q.rev = ((p->s.dec_layers - 1) % 2 == 0);   // opposite to the last forward layer (or to layer 1)
   q.wimg = st->rs ? st->w_out_rs : st->w_out;
   q.bias = p->out_b;
@@ -1357,7 +1511,7 @@ int tc_launch_dgrad_in4(Plan* p, const float* seed8, const void* act_prev, void*
   (void)seed8;
   TcParams q;
   q.maps = st->map_seed;
-  fill_common(p, st->g_in4, 1, p->C, &q);
+  fill_common(p, st->g_in4, 1, p->C / st->nsplit_in4, p->C, &q);
   q.wimg = st->w_in4;
   q.bias = nullptr;
   q.actp = reinterpret_cast<const uint4*>(act_prev);
@@ -1370,59 +1524,87 @@ int tc_launch_dgrad_in4(Plan* p, const float* seed8, const void* act_prev, void*
 // A thread owns one (pixel, 8-channel plane) and walks TC_L1_NB slot-images with the coordinate-table
 // values in registers (the table is read once per group of images, not once per image).
 constexpr int TC_L1_NB = 8;
+// mode: 0 = bf16 planes of 8, 1 = fp16 planes of 8, 2 = tf32 planes of 4 (two planes per thread, same 8 channels)
 __global__ void __launch_bounds__(256)
 tc_layer1_kernel(const float* __restrict__ u, const float* __restrict__ ptab_c, uint4* __restrict__ act0,
-                 int H, int W, int C, int KS, int BK, int f16) {
-  const int k = blockIdx.y;
+                 int H, int W, int C, int KS, int BK, int mode) {
+  const int k = blockIdx.y;                            // group of 8 channels
   const int P = KS / 2, HW = H * W;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= HW) return;
   const int y = pix / W, x = pix - y * W;
   const int cls = border_class(y, H, P) * KS + border_class(x, W, P);
-  const float4* pv = reinterpret_cast<const float4*>(ptab_c + ((size_t)k * HW + pix) * 8);
-  const float4 p0 = __ldg(pv), p1 = __ldg(pv + 1);
+  float4 p0, p1;
+  if (mode == 2) {                                     // ptab_c is [C/4][HW][4]
+    p0 = __ldg(reinterpret_cast<const float4*>(ptab_c + ((size_t)(2 * k) * HW + pix) * 4));
+    p1 = __ldg(reinterpret_cast<const float4*>(ptab_c + ((size_t)(2 * k + 1) * HW + pix) * 4));
+  } else {                                             // [C/8][HW][8]
+    const float4* pv = reinterpret_cast<const float4*>(ptab_c + ((size_t)k * HW + pix) * 8);
+    p0 = __ldg(pv); p1 = __ldg(pv + 1);
+  }
   const int n0 = blockIdx.z * TC_L1_NB;
   const int n1 = (n0 + TC_L1_NB < BK) ? n0 + TC_L1_NB : BK;
 #pragma unroll 4
   for (int n = n0; n < n1; ++n) {
     const float4* uv = reinterpret_cast<const float4*>(u + ((size_t)n * KS * KS + cls) * C + k * 8);
     const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
-    uint4 o;
-    // hardware exponential: |error| ~1e-7 absolute, far below the 16-bit rounding that follows (the
+    // hardware exponential: |error| ~1e-7 absolute, far below the operand rounding that follows (the
     // libm expm1f made this bandwidth-bound kernel compute-bound)
-    o.x = pack_h2(elu_fast(u0.x + p0.x), elu_fast(u0.y + p0.y), f16);
-    o.y = pack_h2(elu_fast(u0.z + p0.z), elu_fast(u0.w + p0.w), f16);
-    o.z = pack_h2(elu_fast(u1.x + p1.x), elu_fast(u1.y + p1.y), f16);
-    o.w = pack_h2(elu_fast(u1.z + p1.z), elu_fast(u1.w + p1.w), f16);
-    act0[((size_t)n * (C / 8) + k) * HW + pix] = o;
+    const float v0 = elu_fast(u0.x + p0.x), v1 = elu_fast(u0.y + p0.y), v2 = elu_fast(u0.z + p0.z), v3 = elu_fast(u0.w + p0.w),
+                v4 = elu_fast(u1.x + p1.x), v5 = elu_fast(u1.y + p1.y), v6 = elu_fast(u1.z + p1.z), v7 = elu_fast(u1.w + p1.w);
+    if (mode == 2) {
+      const uint4 a = make_uint4(__float_as_uint(to_tf32(v0)), __float_as_uint(to_tf32(v1)), __float_as_uint(to_tf32(v2)), __float_as_uint(to_tf32(v3)));
+      const uint4 b = make_uint4(__float_as_uint(to_tf32(v4)), __float_as_uint(to_tf32(v5)), __float_as_uint(to_tf32(v6)), __float_as_uint(to_tf32(v7)));
+      act0[((size_t)n * (C / 4) + 2 * k) * HW + pix] = a;
+      act0[((size_t)n * (C / 4) + 2 * k + 1) * HW + pix] = b;
+    } else {
+      uint4 o;
+      o.x = pack_h2(v0, v1, mode); o.y = pack_h2(v2, v3, mode); o.z = pack_h2(v4, v5, mode); o.w = pack_h2(v6, v7, mode);
+      act0[((size_t)n * (C / 8) + k) * HW + pix] = o;
+    }
   }
 }
+
+static int plane_mode(const Plan* p) { return tf_mode(p) ? 2 : (p->s.precision == IODINE_FP16 ? 1 : 0); }
 
 int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st_) {
   TcState* st = tc_state(p);
   dim3 grid((p->HW + 255) / 256, p->C / 8, (p->BK + TC_L1_NB - 1) / TC_L1_NB);
   tc_layer1_kernel<<<grid, 256, 0, st_>>>(p->u, st->ptab_c, reinterpret_cast<uint4*>(act0), p->s.H, p->s.W, p->C,
-                                          p->s.dec_k, p->BK, p->s.precision == IODINE_FP16);
+                                          p->s.dec_k, p->BK, plane_mode(p));
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
-// G[n][class][co] = sum over pixels of the class of g[n][co/8][y][x][co%8]  (layer-1 dgrad collapse)
+// one plane value (16 bytes) -> up to 8 floats; returns the number of channels it holds
+__device__ __forceinline__ int plane_unpack(const uint4& v, int mode, float* o) {
+  if (mode == 2) {
+    o[0] = __uint_as_float(v.x); o[1] = __uint_as_float(v.y); o[2] = __uint_as_float(v.z); o[3] = __uint_as_float(v.w);
+    o[4] = o[5] = o[6] = o[7] = 0.f;
+    return 4;
+  }
+  const float2 a = unpack_h2(v.x, mode), b = unpack_h2(v.y, mode), c = unpack_h2(v.z, mode), d = unpack_h2(v.w, mode);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+  return 8;
+}
+
+// G[n][class][co] = sum over pixels of the class of g[n][plane][y][x][co in plane]  (layer-1 dgrad collapse)
 // The block walks its rows in maximal runs of equal row class.  Inside a run a thread owns column
 // x = tid % min(W,256) and every (256/W)-th row, four loads in flight; its column class is fixed, so
 // interior columns are block-reduced once per run and the 2*(k/2) border columns flush their own sums:
 // a handful of atomics per (block, run) instead of one per border pixel.
 __global__ void __launch_bounds__(256)
 tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, int W, int C, int KS, int rows_per_block,
-                    int f16) {
-  const int n = blockIdx.z, k = blockIdx.y;
+                    int mode) {
+  const int PW = mode == 2 ? 4 : 8;
+  const int n = blockIdx.z, k = blockIdx.y;            // k: plane
   const int P = KS / 2, HW = H * W;
   const int y_lo = blockIdx.x * rows_per_block;
   const int y_hi = (y_lo + rows_per_block < H) ? y_lo + rows_per_block : H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ float red[8][8];
-  float* Gn = G + (size_t)n * KS * KS * C + k * 8;
-  const uint4* gp = g + ((size_t)n * (C / 8) + k) * HW;
+  float* Gn = G + (size_t)n * KS * KS * C + k * PW;
+  const uint4* gp = g + ((size_t)n * (C / PW) + k) * HW;
   const int Wc = W < 256 ? W : 256;
   const int nsub = 256 / Wc;                        // rows in flight per pass (1 when W >= 256)
   const int x0 = threadIdx.x % Wc, ysub = threadIdx.x / Wc;
@@ -1432,9 +1614,10 @@ tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, i
 #pragma unroll
   for (int e = 0; e < 8; ++e) { run[e] = 0.f; brun[e] = 0.f; }
   auto add = [&](const uint4& v, float* acc) {
-    const float2 a = unpack_h2(v.x, f16), b = unpack_h2(v.y, f16), c = unpack_h2(v.z, f16), d = unpack_h2(v.w, f16);
-    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-    acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    float f[8];
+    plane_unpack(v, mode, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
   };
   int y = y_lo;
   while (y < y_hi) {
@@ -1461,7 +1644,7 @@ tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, i
             else {
               float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               add(w, t);
-              for (int e = 0; e < 8; ++e) atomicAdd(Gn + (size_t)(cy * KS + cx) * C + e, t[e]);
+              for (int e = 0; e < PW; ++e) atomicAdd(Gn + (size_t)(cy * KS + cx) * C + e, t[e]);
             }
           }
         }
@@ -1470,7 +1653,10 @@ tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, i
     // flush the run
     if (active && cx0 != P) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { atomicAdd(Gn + (size_t)(cy * KS + cx0) * C + e, brun[e]); brun[e] = 0.f; }
+      for (int e = 0; e < 8; ++e) {
+        if (e < PW) atomicAdd(Gn + (size_t)(cy * KS + cx0) * C + e, brun[e]);
+        brun[e] = 0.f;
+      }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) run[e] = warp_sum(run[e]);
@@ -1479,7 +1665,7 @@ tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, i
 #pragma unroll
       for (int e = 0; e < 8; ++e) red[warp][e] = run[e];
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if (threadIdx.x < PW) {
       float t = 0.f;
       for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
       atomicAdd(Gn + (size_t)(cy * KS + P) * C + threadIdx.x, t);
@@ -1492,41 +1678,42 @@ tc_class_sum_kernel(const uint4* __restrict__ g, float* __restrict__ G, int H, i
 
 int tc_launch_class_sum(Plan* p, const void* g, cudaStream_t st_) {
   const int rpb = 32;
-  dim3 grid((p->s.H + rpb - 1) / rpb, p->C / 8, p->BK);
+  dim3 grid((p->s.H + rpb - 1) / rpb, p->C / tc_state(p)->pw, p->BK);
   tc_class_sum_kernel<<<grid, 256, 0, st_>>>(reinterpret_cast<const uint4*>(g), p->G, p->s.H, p->s.W, p->C,
-                                             p->s.dec_k, rpb, p->s.precision == IODINE_FP16);
+                                             p->s.dec_k, rpb, plane_mode(p));
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
-// chunk-planar bf16 [n][C/8][HW][8] -> NHWC fp32 [n][HW][C]   (debug reads only)
-__global__ void tc_export_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, size_t total,
-                                 int HW, int C, int f16) {
+// chunk-planar [n][C/PW][HW][PW] -> NHWC fp32 [n][HW][C]   (debug reads only)
+__global__ void tc_export_kernel(const void* __restrict__ src, float* __restrict__ dst, size_t total,
+                                 int HW, int C, int mode) {
+  const int PW = mode == 2 ? 4 : 8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const size_t pn = i / C;
     const int pix = (int)(pn % HW);
     const size_t n = pn / HW;
-    dst[i] = from_h(src[((n * (C / 8) + c / 8) * HW + pix) * 8 + c % 8], f16);
+    const size_t j = ((n * (C / PW) + c / PW) * HW + pix) * PW + c % PW;
+    dst[i] = mode == 2 ? reinterpret_cast<const float*>(src)[j] : from_h(reinterpret_cast<const uint16_t*>(src)[j], mode);
   }
 }
 
 int tc_export_f32(Plan* p, const void* src_bf16, float* dst, size_t n, cudaStream_t st_) {
-  tc_export_kernel<<<p->num_sms * 4, 256, 0, st_>>>(reinterpret_cast<const uint16_t*>(src_bf16), dst, n, p->HW,
-                                                    p->C, p->s.precision == IODINE_FP16);
+  tc_export_kernel<<<p->num_sms * 4, 256, 0, st_>>>(src_bf16, dst, n, p->HW, p->C, plane_mode(p));
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
 
-// seed8 (bf16 [n][HW][8], 4 real channels) -> fp32 [n][HW][4]   (debug reads only)
-__global__ void tc_export_seed_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, size_t npix, int f16) {
+// seed plane (16-bit: [n][HW][8], 4 real channels; tf32: [n][HW][4] fp32) -> fp32 [n][HW][4]   (debug reads only)
+__global__ void tc_export_seed_kernel(const void* __restrict__ src, float* __restrict__ dst, size_t npix, int mode) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix * 4; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = from_h(src[(i / 4) * 8 + i % 4], f16);
+    dst[i] = mode == 2 ? reinterpret_cast<const float*>(src)[i]
+                       : from_h(reinterpret_cast<const uint16_t*>(src)[(i / 4) * 8 + i % 4], mode);
 }
 
 int tc_export_seed(Plan* p, const void* seed8, float* dst, cudaStream_t st_) {
-  tc_export_seed_kernel<<<p->num_sms * 4, 256, 0, st_>>>(reinterpret_cast<const uint16_t*>(seed8), dst,
-                                                         (size_t)p->BK * p->HW, p->s.precision == IODINE_FP16);
+  tc_export_seed_kernel<<<p->num_sms * 4, 256, 0, st_>>>(seed8, dst, (size_t)p->BK * p->HW, plane_mode(p));
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

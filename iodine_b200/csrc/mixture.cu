@@ -221,11 +221,11 @@ int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st) {
   if (s.K <= 8)
     mixture_kernel<8><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
                                             p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads,
-                                            tc_mode(p) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0);
+                                            (tc_mode(p) && !tf_mode(p)) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0);
   else
     mixture_kernel<16><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
                                              p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads,
-                                             tc_mode(p) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0);
+                                             (tc_mode(p) && !tf_mode(p)) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -335,7 +335,7 @@ assemble16_kernel(const float* __restrict__ auxs, const float* __restrict__ lik,
 int launch_assemble16(Plan* p, const float* x, cudaStream_t st) {
   dim3 grid((p->HW + 255) / 256, p->BK);
   assemble16_kernel<<<grid, 256, 0, st>>>(p->auxs, p->lik, x, p->stats, reinterpret_cast<uint4*>(p->enc16), p->s.K,
-                                          p->HW, p->s.layernorm, p->s.precision == IODINE_FP16);
+                                          p->HW, p->s.layernorm, half_is_f16(p));
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -376,7 +376,7 @@ int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st) 
   const bool rtc = rtc_enabled(p);
   export_aux_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->enc20, rtc ? reinterpret_cast<const uint16_t*>(p->enc16) : nullptr,
                                                     p->xin, aux_out, p->BK, p->s.H, p->s.W, p->M, 4 * p->s.L,
-                                                    p->s.precision == IODINE_FP16);
+                                                    half_is_f16(p));
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -387,7 +387,7 @@ int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st) 
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 recombine_kernel(const float* __restrict__ out4, float* __restrict__ pred, float* __restrict__ mask,
-                 float* __restrict__ mean, int K, int HW) {
+                 float* __restrict__ mean, uint8_t* __restrict__ amax, int K, int HW) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= HW) return;
@@ -398,9 +398,12 @@ recombine_kernel(const float* __restrict__ out4, float* __restrict__ pred, float
   for (int k = 0; k < K; ++k) den += expf(out4[(((size_t)(b * K + k)) * HW + pix) * 4 + 3] - lmax);
   const float inv = 1.f / den;
   float pr = 0.f, pg = 0.f, pb = 0.f;
+  float mbest = -1.f;
+  int kbest = 0;
   for (int k = 0; k < K; ++k) {
     const float4 v = reinterpret_cast<const float4*>(out4)[((size_t)(b * K + k)) * HW + pix];
     const float m = expf(v.w - lmax) * inv;
+    if (m > mbest) { mbest = m; kbest = k; }         // first maximum, as torch.argmax (lib/eval/ari_eval.py:32-39)
     const float r = sigmoid_f(v.x), g = sigmoid_f(v.y), bl = sigmoid_f(v.z);
     pr += m * r; pg += m * g; pb += m * bl;
     if (mask) mask[((size_t)(b * K + k)) * HW + pix] = m;
@@ -410,6 +413,7 @@ recombine_kernel(const float* __restrict__ out4, float* __restrict__ pred, float
       mean[(((size_t)(b * K + k)) * 3 + 2) * HW + pix] = bl;
     }
   }
+  if (amax) amax[(size_t)b * HW + pix] = (uint8_t)kbest;
   if (pred) {
     pred[((size_t)b * 3 + 0) * HW + pix] = pr;
     pred[((size_t)b * 3 + 1) * HW + pix] = pg;
@@ -417,9 +421,9 @@ recombine_kernel(const float* __restrict__ out4, float* __restrict__ pred, float
   }
 }
 
-int launch_recombine(Plan* p, float* pred, float* mask, float* mean, cudaStream_t st) {
-  dim3 grid((p->HW + 255) / 256, p->s.B);
-  recombine_kernel<<<grid, 256, 0, st>>>(p->out4, pred, mask, mean, p->s.K, p->HW);
+int launch_recombine(Plan* p, float* pred, float* mask, float* mean, int n_images, cudaStream_t st, uint8_t* amax) {
+  dim3 grid((p->HW + 255) / 256, n_images);
+  recombine_kernel<<<grid, 256, 0, st>>>(p->out4, pred, mask, mean, amax, p->s.K, p->HW);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

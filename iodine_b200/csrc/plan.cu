@@ -61,7 +61,8 @@ static size_t carve(Plan* p, char* base) {
   p->accum = (double*)take(2 * sizeof(double));
   p->pool = (float*)take(BK * Cr * sizeof(float));
   p->xin = (float*)take(BK * (M + 4 * L) * sizeof(float));
-  p->gates = (float*)take((size_t)LSTM_KSPLIT * BK * 4 * M * sizeof(float));
+  // split-K partial sums of the LSTM gate GEMM [BK,4M] and, later in the step, of the two heads [BK,2L]
+  p->gates = (float*)take((size_t)LSTM_KSPLIT * BK * (4 * M > 2 * L ? 4 * M : 2 * L) * sizeof(float));
   p->st_mean = (float*)take(BK * L * sizeof(float));
   p->st_logvar = (float*)take(BK * L * sizeof(float));
   p->st_h = (float*)take(BK * M * sizeof(float));
@@ -73,6 +74,11 @@ static size_t carve(Plan* p, char* base) {
   p->hpred = (float*)take((size_t)s.B * 3 * HW * sizeof(float));
   p->hmask = (float*)take(BK * HW * sizeof(float));
   p->hmean = (float*)take(BK * 3 * HW * sizeof(float));
+  p->hamax = (uint8_t*)take((size_t)s.B * HW);
+  // logger side channel (iodine.py:226-239): image 0 of the last elbo() evaluation
+  p->log_pred = (float*)take((size_t)3 * HW * sizeof(float));
+  p->log_mask = (float*)take((size_t)s.K * HW * sizeof(float));
+  p->log_mean = (float*)take((size_t)s.K * 3 * HW * sizeof(float));
   return off;
 }
 
@@ -158,6 +164,7 @@ static int refine_step(Plan* p, const float* x, const float* eps_t, float* mu, f
                        float* c, float* terms_out, float* aux_out, cudaStream_t st) {
   if (decoder_forward(p, mu, lv, eps_t, nullptr, st)) return 1;
   if (launch_mixture(p, x, true, st)) return 1;
+  if (launch_recombine(p, p->log_pred, p->log_mask, p->log_mean, 1, st)) return 1;   // what elbo() hands the logger
   if (decoder_dgrad(p, st)) return 1;
   if (launch_post_grads(p, mu, lv, eps_t, nullptr, st)) return 1;
   if (rtc_enabled(p)) {
@@ -204,24 +211,40 @@ static int do_encode(Plan* p, const float* x, const float* eps, float* z_out, fl
 
 // encode() through a CUDA graph.  The first call with a given pointer tuple runs eagerly, the second captures
 // (on a plan-owned stream: the caller's may be the legacy default stream, which cannot be captured) and every
-// later one replays.  Profiling brackets (events) and IODINE_NO_GRAPH=1 keep the eager path.
+// later one replays.  A plan keeps Plan::N_GRAPHS instantiated graphs keyed by the pointer tuple (least recently
+// used one evicted), so that a caller alternating between buffer sets -- double buffering -- still replays.
+// Profiling brackets (events) and IODINE_NO_GRAPH=1 keep the eager path.
 static int do_encode_g(Plan* p, const float* x, const float* eps, float* z_out, float* terms, float* post_out,
                        cudaStream_t st) {
   if (!p->graphs || p->profiling) return do_encode(p, x, eps, z_out, terms, post_out, st);
   const void* key[5] = {x, eps, z_out, terms, post_out};
-  Plan::EncodeGraph& g = p->graph;
-  const bool hit = g.exec && !memcmp(g.key, key, sizeof(key));
-  if (!hit) {
-    const bool warm = !memcmp(g.seen, key, sizeof(key));
-    memcpy(g.seen, key, sizeof(key));
-    if (!warm) return do_encode(p, x, eps, z_out, terms, post_out, st);
-    // capture
+  Plan::EncodeGraph* g = nullptr;
+  for (int i = 0; i < Plan::N_GRAPHS; ++i)
+    if (p->graph[i].exec && !memcmp(p->graph[i].key, key, sizeof(key))) g = &p->graph[i];
+  if (!g) {
+    // seen once before (eagerly)?  then capture now; otherwise remember the tuple and run eagerly
+    int seen = -1;
+    for (int i = 0; i < Plan::N_GRAPHS; ++i)
+      if (!p->graph[i].exec && p->graph[i].warm && !memcmp(p->graph[i].key, key, sizeof(key))) seen = i;
+    if (seen < 0) {
+      int victim = 0;                               // a free slot, else the least recently used one
+      for (int i = 0; i < Plan::N_GRAPHS; ++i) {
+        if (!p->graph[i].exec && !p->graph[i].warm) { victim = i; break; }
+        if (p->graph[i].used < p->graph[victim].used) victim = i;
+      }
+      Plan::EncodeGraph& v = p->graph[victim];
+      if (v.exec) { cudaGraphExecDestroy(v.exec); v.exec = nullptr; }
+      memcpy(v.key, key, sizeof(key));
+      v.warm = true;
+      v.used = ++p->graph_clock;
+      return do_encode(p, x, eps, z_out, terms, post_out, st);
+    }
+    g = &p->graph[seen];
     if (!p->gstream) {
       IOD_CHECK_CUDA(cudaStreamCreateWithFlags(&p->gstream, cudaStreamNonBlocking));
       IOD_CHECK_CUDA(cudaEventCreateWithFlags(&p->gev_in, cudaEventDisableTiming));
       IOD_CHECK_CUDA(cudaEventCreateWithFlags(&p->gev_out, cudaEventDisableTiming));
     }
-    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     const uint64_t n0 = p->launches;
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(p->gstream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -233,23 +256,23 @@ static int do_encode_g(Plan* p, const float* x, const float* eps, float* z_out, 
     const cudaError_t ce = cudaStreamEndCapture(p->gstream, &graph);
     const uint64_t nk = p->launches - n0;
     p->launches = n0;
-    if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+    if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g->exec, graph, 0) != cudaSuccess) {
       cudaGetLastError();
       if (graph) cudaGraphDestroy(graph);
-      g.exec = nullptr;
+      g->exec = nullptr;
       p->graphs = false;                        // this driver cannot capture the sequence: stay eager
       return do_encode(p, x, eps, z_out, terms, post_out, st);
     }
     cudaGraphDestroy(graph);
-    memcpy(g.key, key, sizeof(key));
-    g.kernels = nk;
+    g->kernels = nk;
   }
+  g->used = ++p->graph_clock;
   IOD_CHECK_CUDA(cudaEventRecord(p->gev_in, st));
   IOD_CHECK_CUDA(cudaStreamWaitEvent(p->gstream, p->gev_in, 0));
-  IOD_CHECK_CUDA(cudaGraphLaunch(g.exec, p->gstream));
+  IOD_CHECK_CUDA(cudaGraphLaunch(g->exec, p->gstream));
   IOD_CHECK_CUDA(cudaEventRecord(p->gev_out, p->gstream));
   IOD_CHECK_CUDA(cudaStreamWaitEvent(st, p->gev_out, 0));
-  p->launches += g.kernels;
+  p->launches += g->kernels;
   return 0;
 }
 
@@ -286,9 +309,9 @@ static int resolve_nccl() {
 }
 
 // sum the per-step table over the communicator (no-op for a single rank or a null table)
-static int reduce_terms(Plan* p, float* terms, cudaStream_t st) {
-  if (!p->comm || !terms) return 0;
-  const int rc = g_nccl_allreduce(terms, terms, (size_t)p->s.T * 2, /*ncclFloat32*/ 7, /*ncclSum*/ 0, p->comm, st);
+static int reduce_terms(Plan* p, float* terms, size_t count, cudaStream_t st) {
+  if (!p->comm || !terms || !count) return 0;
+  const int rc = g_nccl_allreduce(terms, terms, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, p->comm, st);
   if (rc != 0) {
     set_error("ncclAllReduce of the ELBO table failed on rank %d/%d: %s", p->comm_rank, p->comm_nranks,
               g_nccl_errstr ? g_nccl_errstr(rc) : "?");
@@ -297,9 +320,10 @@ static int reduce_terms(Plan* p, float* terms, cudaStream_t st) {
   return 0;
 }
 
-static int do_decode(Plan* p, const float* z, float* pred, float* mask, float* mean, cudaStream_t st) {
+static int do_decode(Plan* p, const float* z, float* pred, float* mask, float* mean, cudaStream_t st,
+                     uint8_t* amax = nullptr) {
   if (decoder_forward(p, nullptr, nullptr, nullptr, z, st)) return 1;
-  return launch_recombine(p, pred, mask, mean, st);
+  return launch_recombine(p, pred, mask, mean, p->s.B, st, amax);
 }
 
 }  // namespace iod
@@ -311,6 +335,8 @@ extern "C" {
 
 IODINE_API int iodine_abi_version(void) { return IODINE_ABI_VERSION; }
 IODINE_API const char* iodine_last_error(void) { return g_err; }
+
+static int plan_build(Plan* p, const IodineShape& s);
 
 IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_out) {
   IOD_REQUIRE(shape && plan_out, "iodine_plan_create: null argument");
@@ -327,11 +353,22 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
   IOD_REQUIRE(s.ref_stride == 1 || s.ref_stride == 2, "unsupported REF.STRIDE=%d", s.ref_stride);
   IOD_REQUIRE(s.H >= 2 * s.dec_k && s.W >= 2 * s.dec_k, "image %dx%d too small for kernel %d", s.H, s.W, s.dec_k);
   IOD_REQUIRE(s.mlp_units >= 1 && s.T >= 0 && s.sigma > 0.f, "bad MLP_UNITS/ITERS/SIGMA");
-  IOD_REQUIRE(s.precision == IODINE_FP32 || s.precision == IODINE_BF16 || s.precision == IODINE_FP16,
+  IOD_REQUIRE(s.precision == IODINE_FP32 || s.precision == IODINE_BF16 || s.precision == IODINE_FP16 ||
+                  s.precision == IODINE_TF32,
               "unsupported precision %d", s.precision);
 
   Plan* p = new Plan();
+  if (plan_build(p, s)) {                       // nothing half-built survives a failed create
+    iodine_plan_destroy(reinterpret_cast<IodinePlan*>(p));
+    return 1;
+  }
+  *plan_out = reinterpret_cast<IodinePlan*>(p);
+  return 0;
+}
+
+static int plan_build(Plan* p, const IodineShape& s) {
   p->s = s;
+  for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { p->ref_wp[l] = nullptr; p->ref_b[l] = nullptr; }
   p->graphs = getenv("IODINE_NO_GRAPH") == nullptr;
   IOD_CHECK_CUDA(cudaGetDevice(&p->device));
   IOD_CHECK_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
@@ -344,9 +381,7 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
     p->ref_w[l + 1] = (p->ref_w[l] + 2 * pad - s.ref_k) / s.ref_stride + 1;
     IOD_REQUIRE(p->ref_h[l + 1] >= 1 && p->ref_w[l + 1] >= 1, "refine layer %d output is empty", l);
   }
-  if (tc_mode(p)) {
-    if (!tc_supported(p)) { delete p; return 1; }
-  }
+  if (tc_mode(p) && !tc_supported(p)) return 1;
   const size_t C = p->C, L = s.L, M = p->M, Cr = p->Cr, kk = (size_t)s.dec_k * s.dec_k,
                rkk = (size_t)s.ref_k * s.ref_k;
   if (alloc_f(&p->wsum, kk * C * L) || alloc_f(&p->wsumT, kk * C * L) || alloc_f(&p->ptab, (size_t)p->HW * C)) return 1;
@@ -367,17 +402,19 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
   if (tc_mode(p) && tc_alloc(p)) return 1;
   if (tc_mode(p) && !getenv("IODINE_REFINE_FFMA") && rtc_alloc(p)) return 1;
   p->ws_need = carve(p, nullptr);
-  *plan_out = reinterpret_cast<IodinePlan*>(p);
   return 0;
 }
 
 IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
   Plan* p = reinterpret_cast<Plan*>(plan);
   if (!p) return 0;
+  int cur_dev = -1;                              // the plan's allocations live on ITS device
+  cudaGetDevice(&cur_dev);
+  if (cur_dev != p->device) cudaSetDevice(p->device);
   cudaFree(p->wsum); cudaFree(p->wsumT); cudaFree(p->ptab);
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) {
     cudaFree(p->dec[l].w); cudaFree(p->dec[l].wt); cudaFree(p->dec[l].b);
-    if (l < p->s.ref_layers) { cudaFree(p->ref_wp[l]); cudaFree(p->ref_b[l]); }
+    cudaFree(p->ref_wp[l]); cudaFree(p->ref_b[l]);
   }
   cudaFree(p->out_w); cudaFree(p->out_wt); cudaFree(p->out_b); cudaFree(p->ref_w0);
   cudaFree(p->mlp_w); cudaFree(p->mlp_b); cudaFree(p->w_ih); cudaFree(p->w_hh); cudaFree(p->b_ih);
@@ -386,9 +423,13 @@ IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
   tc_free(p);
   rtc_free(p);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
-  if (p->graph.exec) cudaGraphExecDestroy(p->graph.exec);
+  for (int i = 0; i < Plan::N_GRAPHS; ++i)
+    if (p->graph[i].exec) cudaGraphExecDestroy(p->graph[i].exec);
   if (p->gstream) { cudaStreamDestroy(p->gstream); cudaEventDestroy(p->gev_in); cudaEventDestroy(p->gev_out); }
+  const int plan_dev = p->device;
   delete p;
+  if (cur_dev >= 0 && cur_dev != plan_dev) cudaSetDevice(cur_dev);
+  cudaGetLastError();
   return 0;
 }
 
@@ -404,7 +445,10 @@ IODINE_API int iodine_plan_set_workspace(IodinePlan* plan, void* workspace, size
   IOD_REQUIRE(bytes >= p->ws_need, "workspace too small: %zu < %zu", bytes, p->ws_need);
   IOD_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
   p->ws = workspace; p->ws_bytes = bytes;
-  if (p->graph.exec) { cudaGraphExecDestroy(p->graph.exec); p->graph.exec = nullptr; }
+  for (int i = 0; i < Plan::N_GRAPHS; ++i) {     // captured graphs point into the old workspace
+    if (p->graph[i].exec) cudaGraphExecDestroy(p->graph[i].exec);
+    p->graph[i] = Plan::EncodeGraph();
+  }
   carve(p, (char*)workspace);
   if (tc_mode(p) && tc_on_workspace(p)) return 1;
   return 0;
@@ -446,10 +490,11 @@ IODINE_API int iodine_elbo(IodinePlan* plan, const float* x, const float* eps_t,
   cudaStream_t st = (cudaStream_t)stream;
   if (decoder_forward(p, post_mean, post_logvar, eps_t, nullptr, st)) return 1;
   if (launch_mixture(p, x, false, st)) return 1;
+  if (launch_recombine(p, p->log_pred, p->log_mask, p->log_mean, 1, st)) return 1;
   if (launch_kl(p, post_mean, post_logvar, st)) return 1;
   terms_kernel<<<1, 32, 0, st>>>(p->accum, elbo_terms_out);
   IOD_LAUNCH_CHECK(p);
-  return 0;
+  return reduce_terms(p, elbo_terms_out, 2, st);
 }
 
 IODINE_API int iodine_encode(IodinePlan* plan, const float* x, const float* eps, float* z_out,
@@ -458,7 +503,7 @@ IODINE_API int iodine_encode(IodinePlan* plan, const float* x, const float* eps,
   if (check_ready(p)) return 1;
   IOD_REQUIRE(x && eps && z_out, "null tensor argument");
   if (do_encode_g(p, x, eps, z_out, elbo_terms_out, post_out, (cudaStream_t)stream)) return 1;
-  return reduce_terms(p, elbo_terms_out, (cudaStream_t)stream);
+  return reduce_terms(p, elbo_terms_out, (size_t)p->s.T * 2, (cudaStream_t)stream);
 }
 
 IODINE_API int iodine_plan_set_comm(IodinePlan* plan, void* nccl_comm, int32_t rank, int32_t nranks) {
@@ -490,11 +535,22 @@ IODINE_API int iodine_reconstruct(IodinePlan* plan, const float* x, const float*
   IOD_REQUIRE(x && eps, "null tensor argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (do_encode_g(p, x, eps, p->st_z, elbo_terms_out, nullptr, st)) return 1;
-  if (reduce_terms(p, elbo_terms_out, st)) return 1;
+  if (reduce_terms(p, elbo_terms_out, (size_t)p->s.T * 2, st)) return 1;
   if (z_out)
     IOD_CHECK_CUDA(cudaMemcpyAsync(z_out, p->st_z, (size_t)p->BK * p->s.L * sizeof(float),
                                    cudaMemcpyDeviceToDevice, st));
   return do_decode(p, p->st_z, pred_out, mask_out, mean_out, st);
+}
+
+IODINE_API int iodine_plan_last_elbo_image0(IodinePlan* plan, float* pred0, float* mask0, float* mean0, void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t HW = p->HW, K = p->s.K;
+  if (pred0) IOD_CHECK_CUDA(cudaMemcpyAsync(pred0, p->log_pred, 3 * HW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (mask0) IOD_CHECK_CUDA(cudaMemcpyAsync(mask0, p->log_mask, K * HW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (mean0) IOD_CHECK_CUDA(cudaMemcpyAsync(mean0, p->log_mean, K * 3 * HW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
 
 IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_host, const float* eps_host,
@@ -509,7 +565,7 @@ IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_ho
   IOD_CHECK_CUDA(cudaMemcpyAsync(p->hx, x_host, (size_t)s.B * 3 * HW * sizeof(float), cudaMemcpyHostToDevice, st));
   IOD_CHECK_CUDA(cudaMemcpyAsync(p->heps, eps_host, (size_t)(s.T + 1) * BK * s.L * sizeof(float), cudaMemcpyHostToDevice, st));
   if (do_encode_g(p, p->hx, p->heps, p->st_z, p->st_terms, nullptr, st)) return 1;
-  if (reduce_terms(p, p->st_terms, st)) return 1;
+  if (reduce_terms(p, p->st_terms, (size_t)p->s.T * 2, st)) return 1;
   if (do_decode(p, p->st_z, pred_host ? p->hpred : nullptr, mask_host ? p->hmask : nullptr,
                 mean_host ? p->hmean : nullptr, st))
     return 1;
@@ -518,6 +574,34 @@ IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_ho
   if (mean_host) IOD_CHECK_CUDA(cudaMemcpyAsync(mean_host, p->hmean, BK * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (z_host) IOD_CHECK_CUDA(cudaMemcpyAsync(z_host, p->st_z, BK * s.L * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (elbo_terms_host) IOD_CHECK_CUDA(cudaMemcpyAsync(elbo_terms_host, p->st_terms, (size_t)s.T * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+IODINE_API int iodine_evaluate_host_async(IodinePlan* plan, const float* x_host, const float* eps_host,
+                               float* pred_host, uint8_t* argmax_host, float* z_host, float* elbo_terms_host,
+                               void* stream) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (check_ready(p)) return 1;
+  IOD_REQUIRE(x_host && eps_host, "null tensor argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const IodineShape& s = p->s;
+  const size_t HW = p->HW, BK = p->BK;
+  IOD_CHECK_CUDA(cudaMemcpyAsync(p->hx, x_host, (size_t)s.B * 3 * HW * sizeof(float), cudaMemcpyHostToDevice, st));
+  IOD_CHECK_CUDA(cudaMemcpyAsync(p->heps, eps_host, (size_t)(s.T + 1) * BK * s.L * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (do_encode_g(p, p->hx, p->heps, p->st_z, p->st_terms, nullptr, st)) return 1;
+  if (reduce_terms(p, p->st_terms, (size_t)p->s.T * 2, st)) return 1;
+  if (do_decode(p, p->st_z, pred_host ? p->hpred : nullptr, nullptr, nullptr, st, argmax_host ? p->hamax : nullptr)) return 1;
+  if (pred_host) IOD_CHECK_CUDA(cudaMemcpyAsync(pred_host, p->hpred, (size_t)s.B * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (argmax_host) IOD_CHECK_CUDA(cudaMemcpyAsync(argmax_host, p->hamax, (size_t)s.B * HW, cudaMemcpyDeviceToHost, st));
+  if (z_host) IOD_CHECK_CUDA(cudaMemcpyAsync(z_host, p->st_z, BK * s.L * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (elbo_terms_host) IOD_CHECK_CUDA(cudaMemcpyAsync(elbo_terms_host, p->st_terms, (size_t)s.T * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+IODINE_API int iodine_evaluate_host(IodinePlan* plan, const float* x_host, const float* eps_host, float* pred_host,
+                         uint8_t* argmax_host, float* z_host, float* elbo_terms_host, void* stream) {
+  if (iodine_evaluate_host_async(plan, x_host, eps_host, pred_host, argmax_host, z_host, elbo_terms_host, stream)) return 1;
+  IOD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
 

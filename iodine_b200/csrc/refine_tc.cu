@@ -397,7 +397,7 @@ int rtc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
   RtcState* st = rtc_state(p);
   if (!st || !st->ok) return 0;
   const IodineShape& s = p->s;
-  const int Cr = p->Cr, f16 = s.precision == IODINE_FP16;
+  const int Cr = p->Cr, f16 = half_is_f16(p);
   for (int l = 0; l < s.ref_layers; ++l) {
     rtc_pack_kernel<<<32, 256, 0, st_>>>(w->ref_w[l], st->w[l], Cr, l == 0 ? 17 : Cr, l == 0 ? 15 : Cr, st->cin[l], s.ref_k,
                                          f16);
@@ -460,7 +460,7 @@ int rtc_launch_refine_convs(Plan* p, cudaStream_t st_) {
     q.cin_planes = st->cin[l] / 8;
     q.total = p->BK * q.Hout * q.Wout;
     q.tiles = (q.total + 127) / 128;
-    q.f16 = s.precision == IODINE_FP16;
+    q.f16 = half_is_f16(p);
     const uint32_t fmt = q.f16 ? 0u : 1u;
     q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cr >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int nks = st->cin[l] / 16;
@@ -477,7 +477,7 @@ int rtc_launch_refine_convs(Plan* p, cudaStream_t st_) {
   }
   const int HWo = p->ref_h[s.ref_layers] * p->ref_w[s.ref_layers];
   rtc_pool_kernel<<<p->BK, 256, 0, st_>>>(reinterpret_cast<const uint4*>(cur), p->pool, HWo, Cr,
-                                          s.precision == IODINE_FP16);
+                                          half_is_f16(p));
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

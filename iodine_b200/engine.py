@@ -212,6 +212,34 @@ class RefinementEngine:
                 _ptr(out['mean']), _ptr(out['z']), _ptr(out['terms']), _stream()))
         return out
 
+    def evaluate_host(self, x_host, eps_host, out=None, sync=True):
+        """The evaluation flow with HOST (ideally pinned) buffers: like ``reconstruct_host`` but the masks come back
+        as their per-pixel argmax (uint8 [B,H,W]) -- what lib/eval/ari_eval.py:32-39 keeps of them.  ``out`` may carry
+        pre-allocated pinned tensors 'pred','argmax','z','terms'."""
+        B, K, L, T = self.B, self.K, self.L, self.T
+        assert x_host.device.type == 'cpu' and eps_host.device.type == 'cpu'
+        x_host = x_host.to(torch.float32).contiguous()
+        eps_host = eps_host.to(torch.float32).contiguous()
+        if out is None:
+            pin = torch.cuda.is_available()
+            out = dict(pred=torch.empty(B, 3, self.H, self.W, pin_memory=pin),
+                       argmax=torch.empty(B, self.H, self.W, dtype=torch.uint8, pin_memory=pin),
+                       z=torch.empty(B, K, L, pin_memory=pin), terms=torch.empty(max(T, 1), 2, pin_memory=pin))
+        with torch.cuda.device(self.device):
+            fn = self.lib.iodine_evaluate_host if sync else self.lib.iodine_evaluate_host_async
+            _cabi.check(fn(self._plan, _ptr(x_host), _ptr(eps_host), _ptr(out.get('pred')), _ptr(out.get('argmax')),
+                           _ptr(out.get('z')), _ptr(out.get('terms')), _stream()))
+        return out
+
+    def last_elbo_image0(self):
+        """(pred[3,H,W], mask[K,H,W], mean[K,3,H,W]) of image 0 as the LAST elbo() evaluation of this plan produced
+        them -- what the reference hands its logger (iodine.py:225-239)."""
+        K, H, W = self.K, self.H, self.W
+        pred, mask, mean = self._new(3, H, W), self._new(K, H, W), self._new(K, 3, H, W)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.iodine_plan_last_elbo_image0(self._plan, _ptr(pred), _ptr(mask), _ptr(mean), _stream()))
+        return pred, mask, mean
+
     def debug_read(self, name, dtype=torch.float32):
         need = C.c_size_t()
         _cabi.check(self.lib.iodine_debug_read(self._plan, name.encode(), None, 0, C.byref(need), _stream()))

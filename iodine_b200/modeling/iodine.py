@@ -73,6 +73,11 @@ class _Gaussian(nn.Module):
         self.init_logvar = nn.Parameter(data=torch.zeros(dim_latent))
 
 
+# image-shaped encodings -> their channels in the full stack (reference code order, iodine.py:277-340)
+_SPATIAL_ENCODINGS = (('image', (0, 1, 2)), ('means', (3, 4, 5)), ('mask', (6,)), ('mask_logits', (7,)),
+                      ('mask_posterior', (8,)), ('grad_means', (9, 10, 11)), ('grad_mask', (12,)),
+                      ('likelihood', (13,)), ('leave_one_out_likelihood', (14,)), ('coordinate', (15, 16)))
+
 ALL_ENCODINGS = ('posterior', 'grad_post', 'image', 'means', 'mask', 'mask_logits',
                  'mask_posterior', 'grad_means', 'grad_mask', 'likelihood',
                  'leave_one_out_likelihood', 'coordinate')
@@ -94,11 +99,19 @@ class IODINE(nn.Module):
         if precision not in _cabi.PRECISIONS:
             raise ValueError('precision must be one of %s' % sorted(_cabi.PRECISIONS))
         self.precision = precision
-        missing = [e for e in ALL_ENCODINGS if e not in self.encodings]
-        if missing:
-            # every shipped config of the reference enables all twelve (configs/*.yaml)
-            raise NotImplementedError('the native engine implements the full encoding set; '
-                                      'missing from ARCH.ENCODING: %s' % missing)
+        unknown = [e for e in self.encodings if e not in ALL_ENCODINGS]
+        if unknown:
+            raise ValueError('unknown entries in ARCH.ENCODING: %s' % unknown)
+        if 'posterior' not in self.encodings or 'grad_post' not in self.encodings:
+            # the reference's LSTMCell is built for M + 4L inputs whatever the list says (iodine.py:462), so its
+            # forward fails on the concatenation without both latent encodings; refuse at construction instead
+            raise ValueError("ARCH.ENCODING must contain 'posterior' and 'grad_post' (the reference's LSTMCell "
+                             'input is MLP_UNITS + 4*DIM_LATENT wide, lib/modeling/iodine.py:462)')
+        # channels of the FULL 17-channel stack (reference code order, iodine.py:277-340) that this list selects,
+        # in the order get_input_encoding() concatenates them
+        self._enc_channels = [c for name, chans in _SPATIAL_ENCODINGS if name in self.encodings for c in chans]
+        if not self._enc_channels:
+            raise ValueError('ARCH.ENCODING selects no image-shaped encoding')
         if self.img_channels != 3:
             raise NotImplementedError('ARCH.IMG_CHANNELS must be 3')
 
@@ -120,25 +133,67 @@ class IODINE(nn.Module):
         self._engines = {}
         self._comm = None           # (NcclComm, rank, nranks) installed by set_comm()
         self._weights_sig = {}
+        self._weights_epoch = 0
         self.max_images_per_call = None   # None = automatic (fit the workspace in free HBM)
+        # with a communicator installed the engine returns ELBO sums over ALL ranks' images; means are then taken
+        # over this many images (set by iodine_b200.parallel.SlotShard; None = the local batch)
+        self.global_batch = None
 
     # ------------------------------------------------------------------ bookkeeping
     def get_input_size(self):
-        """reference iodine.py:345-374 with every encoding enabled: (17, 4L)."""
-        return 3 * self.img_channels + 8, 4 * self.dim_latent
+        """reference iodine.py:345-374: (channels of the refinement input, width of the latent vector)."""
+        return len(self._enc_channels), 4 * self.dim_latent
+
+    def _engine_state_dict(self):
+        """state_dict in the shapes the engine takes (the full 17-channel stack).  A partial ARCH.ENCODING list
+        means a first refinement conv with fewer input channels: its weight is scattered into the full layout with
+        zeros for the channels the list leaves out, which is arithmetically the reference's smaller convolution
+        (the engine still evaluates all 17 channels; a NaN in an unselected channel -- the reference's own
+        un-stabilised mask_posterior can produce one -- would leak through the zero weight)."""
+        sd = self.state_dict()
+        if len(self._enc_channels) != 17:
+            w = sd['refine.mlc.layers.0.weight']
+            full = w.new_zeros(w.shape[0], 17, w.shape[2], w.shape[3])
+            full[:, self._enc_channels] = w
+            sd = dict(sd)
+            sd['refine.mlc.layers.0.weight'] = full
+        return sd
 
     def _device(self):
         return self.posterior.init_mean.device
 
     def _sig(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self._weights_epoch,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate_weights(self):
+        """Force the engines to repack the weights on their next call.  Parameter changes that go through autograd-
+        visible in-place ops (optimizers, ``load_state_dict``, ``p.mul_``) are detected automatically from the
+        tensors' version counters; edits through ``p.data`` do not bump those counters and need this call."""
+        self._weights_epoch += 1
+
+    def load_state_dict(self, *args, **kw):
+        out = super().load_state_dict(*args, **kw)
+        self.invalidate_weights()
+        return out
+
+    def _apply(self, fn, *args, **kw):
+        out = super()._apply(fn, *args, **kw)         # .to() / .cuda() / .half(): new storages
+        if hasattr(self, '_weights_epoch'):
+            self.invalidate_weights()
+        return out
+
+    def _mean_batch(self, B):
+        """number of images the engine's batch sums cover: all ranks' when a communicator is installed"""
+        if self._comm is not None and self.global_batch:
+            return int(self.global_batch)
+        return B
 
     def _engine(self, B):
         dev = self._device()
         key = (int(B), str(dev), self.precision)
         eng = self._engines.get(key)
         if eng is None:
-            if len(self._engines) >= 2:          # keep at most two plans (full + tail chunk)
+            if len(self._engines) >= 3:          # a few plans (full chunk, tail chunk, a second batch size)
                 old = next(iter(self._engines))
                 self._engines.pop(old).close()
                 self._weights_sig.pop(old, None)
@@ -148,7 +203,7 @@ class IODINE(nn.Module):
             self._engines[key] = eng
         sig = self._sig()
         if self._weights_sig.get(key) != sig:
-            eng.set_weights(self.state_dict())
+            eng.set_weights(self._engine_state_dict())
             self._weights_sig[key] = sig
         return eng
 
@@ -210,7 +265,10 @@ class IODINE(nn.Module):
         eps = self._noise(B, eps)
         zs, terms, posts = [], 0, []
         for b0, b1 in self._spans(B):
-            z, t, post = self._engine(b1 - b0).encode(x[b0:b1], eps[:, b0:b1])
+            eng = self._engine(b1 - b0)
+            z, t, post = eng.encode(x[b0:b1], eps[:, b0:b1])
+            if b0 == 0 and self.n_iters > 0:
+                self._log_last_elbo(x, eng)
             zs.append(z)
             posts.append(post)
             terms = terms + t
@@ -229,13 +287,15 @@ class IODINE(nn.Module):
         eps = self._noise(B, eps)
         outs, terms = [], 0
         for b0, b1 in self._spans(B):
-            pred, mask, mean, z, t = self._engine(b1 - b0).reconstruct(x[b0:b1], eps[:, b0:b1])
+            eng = self._engine(b1 - b0)
+            pred, mask, mean, z, t = eng.reconstruct(x[b0:b1], eps[:, b0:b1])
+            if b0 == 0 and self.n_iters > 0:
+                self._log_last_elbo(x, eng)
             outs.append((pred, mask, mean, z))
             terms = terms + t
         pred, mask, mean, z = (torch.cat(t, dim=0) if len(t) > 1 else t[0] for t in zip(*outs))
         self.elbo_terms, self.z, self.mean, self.mask = terms, z, mean, mask
         self._log_scalars(B)
-        self._log_images(x, pred, mask, mean)
         return pred, mask, mean
 
     @torch.no_grad()
@@ -252,15 +312,19 @@ class IODINE(nn.Module):
             eps = torch.randn(B, K, L, device=self._device())
         terms = 0
         for b0, b1 in self._spans(B):
-            terms = terms + self._engine(b1 - b0).elbo_terms(x[b0:b1], eps[b0:b1], mu[b0:b1], lv[b0:b1])
-        logger.update(kl=terms[1] / B, likelihood=terms[0] / B)
-        return (terms[0] - terms[1]) / B
+            eng = self._engine(b1 - b0)
+            terms = terms + eng.elbo_terms(x[b0:b1], eps[b0:b1], mu[b0:b1], lv[b0:b1])
+            if b0 == 0:
+                self._log_last_elbo(x, eng)
+        nb = self._mean_batch(B)
+        logger.update(kl=terms[1] / nb, likelihood=terms[0] / nb)
+        return (terms[0] - terms[1]) / nb
 
     def elbo_per_step(self, B=None):
         """ELBO of every refinement step of the last encode()/reconstruct() call, as the
         reference would have returned from elbo() inside the loop (mean over batch)."""
         t = self.elbo_terms
-        B = B or self.z.shape[0]
+        B = self._mean_batch(B or self.z.shape[0])
         return (t[:, 0] - t[:, 1]) / B
 
     @torch.no_grad()
@@ -279,9 +343,14 @@ class IODINE(nn.Module):
         elbos = list(self.elbo_per_step(B))
         final = 0
         for b0, b1 in self._spans(B):
-            final = final + self._engine(b1 - b0).elbo_terms(x[b0:b1], eps[T, b0:b1], self.posterior.mean[b0:b1],
-                                                            self.posterior.logvar[b0:b1])
-        elbos.append((final[0] - final[1]) / B)
+            eng = self._engine(b1 - b0)
+            final = final + eng.elbo_terms(x[b0:b1], eps[T, b0:b1], self.posterior.mean[b0:b1],
+                                           self.posterior.logvar[b0:b1])
+            if b0 == 0:
+                self._log_last_elbo(x, eng)
+        nb = self._mean_batch(B)
+        elbos.append((final[0] - final[1]) / nb)
+        logger.update(kl=final[1] / nb, likelihood=final[0] / nb)          # the last elbo() call is the final one
         loss = 0
         for i, e in enumerate(elbos):
             loss = loss + (i + 1) / len(elbos) * e
@@ -290,14 +359,21 @@ class IODINE(nn.Module):
         return -loss
 
     # ------------------------------------------------------------------ side channel (A9)
+    # The reference writes to the logger inside EVERY elbo() call (iodine.py:225-239), each write replacing the
+    # previous one, so what a consumer finds after encode()/reconstruct() are the quantities of the LAST in-loop
+    # elbo() -- refinement step T-1, not the final decode -- and after forward()/elbo() those of that last call.
+    # The engine keeps image 0 of its last elbo() evaluation for exactly this (iodine_plan_last_elbo_image0).
     def _log_scalars(self, B):
         if self.elbo_terms is not None and self.elbo_terms.numel():
-            logger.update(kl=self.elbo_terms[-1, 1] / B, likelihood=self.elbo_terms[-1, 0] / B)
+            nb = self._mean_batch(B)
+            logger.update(kl=self.elbo_terms[-1, 1] / nb, likelihood=self.elbo_terms[-1, 0] / nb)
 
-    def _log_images(self, x, pred, mask, mean):
-        logger.update(image=x[0], pred=pred[0])
-        logger.update(**{'mask_{}'.format(i): mask[0, i, 0] for i in range(self.K)})
-        logger.update(**{'pred_{}'.format(i): mean[0, i] for i in range(self.K)})
+    def _log_last_elbo(self, x, eng):
+        """``eng`` has just processed the chunk that holds image 0"""
+        pred0, mask0, mean0 = eng.last_elbo_image0()
+        logger.update(image=x[0], pred=pred0)
+        logger.update(**{'mask_{}'.format(i): mask0[i] for i in range(self.K)})
+        logger.update(**{'pred_{}'.format(i): mean0[i] for i in range(self.K)})
 
     def state_for_debug(self, B):
         return self._engine(B)

@@ -111,39 +111,62 @@ class SlotShard:
         self.native = bool(native_comm) and self.world > 1
         self._comm = None
         self._calls_checked = set()
+        self._local_mode = False
         if self.native:
             self._comm = NcclComm(group=group)
             model.set_comm(self._comm, self.rank, self.world)
 
     # ------------------------------------------------------------------ plumbing
     def _local(self, x, eps, local):
+        self._local_mode = bool(local)
         if local or self.world == 1:
             n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
             if self.world > 1:
                 dist.all_reduce(n, group=self.group)
-            self.global_batch = int(n.item())
+            self._set_global_batch(int(n.item()))
             return x, eps
         B = x.shape[0]
-        self.global_batch = B
+        self._set_global_batch(B)
         b0, b1 = shard_bounds(B, self.world, self.rank)
         if b1 <= b0:
             raise ValueError('rank %d of %d has no image: global batch %d is smaller than the '
                              'world size (K-split mode is not implemented)' % (self.rank, self.world, B))
         return x[b0:b1], (None if eps is None else eps[:, b0:b1])
 
+    def _set_global_batch(self, n):
+        self.global_batch = n
+        if self.native:
+            # the engine now returns sums over all ranks' images: the model's means (elbo_per_step, the logged
+            # kl / likelihood, forward()'s loss) are over the global batch
+            self.model.global_batch = n
+
     def _check_calls(self, n_local):
         """native mode: the library all-reduces once per engine call, so every rank must make the same number of
-        calls (the model chunks a shard that does not fit HBM); checked once per local batch size."""
-        if not self.native or n_local in self._calls_checked or not hasattr(self.model, '_spans'):
+        calls (the model chunks a shard that does not fit HBM).  The decision to run this check is keyed on the
+        GLOBAL batch size, which is identical on every rank -- never on the local shard size, which is not when the
+        shards are ragged (a rank-dependent skip would leave some ranks inside this all-reduce and the others
+        inside the library's).  The chunk size itself is agreed once (minimum over ranks) and then frozen in
+        ``model.max_images_per_call`` so that later calls cannot drift apart with each rank's free memory."""
+        if not self.native or not hasattr(self.model, '_spans'):
             return
+        key = int(self.global_batch)
+        if key in self._calls_checked:
+            return
+        dev = self.model._device()
+        if not getattr(self.model, 'max_images_per_call', None):
+            biggest = max(b1 - b0 for b0, b1 in shard_table(self.global_batch, self.world)) if not self._local_mode \
+                else n_local
+            c = torch.tensor([self.model._chunk(biggest)], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.MIN, group=self.group)
+            self.model.max_images_per_call = int(c.item())
         n = len(self.model._spans(n_local))
-        t = torch.tensor([n, -n], dtype=torch.int64, device=self.model._device())
+        t = torch.tensor([n, -n], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         if int(t[0]) != -int(t[1]):
-            raise RuntimeError('ranks would split their shards into different numbers of engine calls (%d..%d); set '
-                               'model.max_images_per_call so that they agree, or use native_comm=False'
-                               % (-int(t[1]), int(t[0])))
-        self._calls_checked.add(n_local)
+            raise RuntimeError('ranks would split their shards into different numbers of engine calls (%d..%d, chunk '
+                               '%s images); choose model.max_images_per_call so that they agree, or use '
+                               'native_comm=False' % (-int(t[1]), int(t[0]), self.model.max_images_per_call))
+        self._calls_checked.add(key)
 
     def _reduce_terms(self):
         t = self.model.elbo_terms

@@ -12,6 +12,12 @@ import sys
 import torch
 
 REFERENCE_ROOT = os.environ.get('IODINE_REFERENCE_ROOT', '/root/reference')
+# the GPU box has no /root/reference: oracle/build_ref.py leaves a byte-for-byte copy of the path's modules in
+# oracle/_ref (git-ignored build output that travels with the snapshot)
+_SHIPPED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, 'lib', 'modeling', 'iodine.py')) and \
+        os.path.isfile(os.path.join(_SHIPPED, 'lib', 'modeling', 'iodine.py')):
+    REFERENCE_ROOT = _SHIPPED
 
 
 def reference_available():

@@ -52,3 +52,43 @@ def rel_err(a, b):
 
 def t(x):
     return torch.from_numpy(np.asarray(x))
+
+
+def load_golden_size(name, precision='fp32'):
+    """Compact at-size golden (oracle/make_golden_size.py): inputs and weights are regenerated from their seeds and
+    pinned by the stored checksums.  Returns (golden dict, arch, B, x, eps, model)."""
+    from oracle import make_golden_size as MS
+    c = MS.CASES[name]
+    g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    arch, x, eps = MS.case_inputs(name)
+    assert abs(x.double().sum().item() - float(g['x_checksum'])) <= 1e-9 * abs(float(g['x_checksum']))
+    assert abs(eps.double().abs().sum().item() - float(g['eps_checksum'])) <= 1e-9 * abs(float(g['eps_checksum']))
+    m = seeded_model(arch, c['sharpen'], precision=precision)
+    cs = MG.weights_checksum(m.state_dict())
+    assert abs(cs - float(g['weights_checksum'])) <= 1e-9 * abs(cs), 'seeded weights differ from the golden ones'
+    return g, arch, c['B'], x, eps, m
+
+
+def compact_errors(g, arch, B, pred, mask, mean, z, elbo_steps):
+    """Errors of a reconstruct() result against a compact golden: sampled values (max |diff| / max |ref|), exact
+    per-image sums (relative), per-step ELBO (relative), z (relative L2) and the argmax of the masks on every pixel
+    whose reference top-2 margin exceeds 4e-3 (mismatch count)."""
+    from oracle import make_golden_size as MS
+    pred, mask, mean, z = (torch.as_tensor(v).detach().cpu() for v in (pred, mask, mean, z))
+    e = {}
+    for nm, v in (('pred', pred), ('mask', mask), ('mean', mean)):
+        flat = v.reshape(-1)
+        e[nm] = rel_err(flat[MS.sample_index(flat.numel())], g['final_%s_s' % nm])
+    e['pred_sum'] = rel_err(pred.double().sum(dim=(2, 3)), g['final_pred_sum'])
+    e['mask_sum'] = rel_err(mask.double().sum(dim=(2, 3, 4)), g['final_mask_sum'])
+    e['mean_sum'] = rel_err(mean.double().sum(dim=(3, 4)), g['final_mean_sum'])
+    want = torch.tensor([float(g['s%d_elbo' % i]) for i in range(arch.ITERS)], dtype=torch.float64)
+    got = torch.as_tensor(elbo_steps, dtype=torch.float64).cpu()
+    e['elbo'] = ((got - want).abs() / want.abs()).max().item()
+    zr = t(g['final_z']).double()
+    e['z_l2'] = ((z.double() - zr).norm() / zr.norm()).item()
+    am = mask[:, :, 0].argmax(dim=1).to(torch.uint8)
+    clear = t(g['final_mask_margin']).float() > 4e-3
+    e['argmax_mismatch'] = int(((am != t(g['final_mask_argmax'])) & clear).sum().item())
+    e['argmax_checked'] = int(clear.sum().item())
+    return e

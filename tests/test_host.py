@@ -67,7 +67,21 @@ def test_make_model_contract():
     assert isinstance(m, IODINE) and m.precision == 'fp16'
     with pytest.raises(ValueError):
         make_model(SimpleNamespace(MODEL=SimpleNamespace(NAME='VAE', DEVICE='cpu', PARALLEL=False), ARCH=arch))
+    # partial ARCH.ENCODING lists (reference iodine.py:345-374): fewer input channels of the first refinement conv,
+    # scattered into the engine's full 17-channel layout with zero weights for the rest
+    sub = A.arch_by_name('tiny')
+    sub.ENCODING = [e for e in sub.ENCODING if e not in ('coordinate', 'mask_posterior')]
+    ms = IODINE(sub)
+    assert ms.get_input_size() == (14, 4 * sub.DIM_LATENT)
+    assert tuple(ms.refine.mlc.layers[0].weight.shape[:2]) == (sub.REF.CONV_CHAN, 14)
+    full = ms._engine_state_dict()['refine.mlc.layers.0.weight']
+    assert tuple(full.shape[:2]) == (sub.REF.CONV_CHAN, 17)
+    assert full[:, [8, 15, 16]].abs().max() == 0 and torch.equal(full[:, :8], ms.refine.mlc.layers[0].weight[:, :8])
+    assert torch.equal(full[:, 9:15], ms.refine.mlc.layers[0].weight[:, 8:14])
     bad = A.arch_by_name('tiny')
-    bad.ENCODING = bad.ENCODING[:-1]
-    with pytest.raises(NotImplementedError):
+    bad.ENCODING = [e for e in bad.ENCODING if e != 'grad_post']
+    with pytest.raises(ValueError):
+        IODINE(bad)
+    bad.ENCODING = ['posterior', 'grad_post', 'not_an_encoding']
+    with pytest.raises(ValueError):
         IODINE(bad)
