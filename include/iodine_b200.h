@@ -34,7 +34,7 @@ extern "C" {
 #define IODINE_API
 #endif
 
-#define IODINE_ABI_VERSION 1
+#define IODINE_ABI_VERSION 2
 #define IODINE_MAX_LAYERS 8
 
 /* arithmetic of the decoder convolutions (everything else is always fp32) */
@@ -66,6 +66,13 @@ typedef struct IodineShape {
   int32_t layernorm;   /* ARCH.LAYERNORM                                                 */
   float   sigma;       /* ARCH.SIGMA                                                     */
   int32_t precision;   /* enum IodinePrecision                                           */
+  /* K-split (SURVEY.md 8e fallback, for B < number of GPUs -- e.g. one image with K = 16): slot_ranks > 1 makes
+   * this plan own the slots [slot_rank * K/slot_ranks, (slot_rank+1) * K/slot_ranks) of every image; K stays
+   * ARCH.SLOTS and must divide.  Every per-slot tensor of the entry points (eps, z, posterior, LSTM state) then
+   * holds K/slot_ranks slots; pred / mask / mean of decode()/reconstruct() are complete ([B,K,...]) on every rank.
+   * Needs iodine_plan_set_comm with exactly slot_ranks ranks before the first step.  0 or 1 = whole images. */
+  int32_t slot_ranks;
+  int32_t slot_rank;
 } IodineShape;
 
 /* One pointer per state_dict key of the reference model, PyTorch layouts
@@ -188,7 +195,15 @@ IODINE_API int iodine_plan_last_elbo_image0(IodinePlan* plan, float* pred0, floa
  * All ranks must make the same calls, with elbo_terms_out given on all of them or on none.  iodine_refine_step stays
  * rank-local.
  *   nccl_comm: an ncclComm_t of the calling process (NULL uninstalls); NCCL is resolved from the process at run
- *   time (dlopen of libnccl.so.2), the library does not link against it. */
+ *   time (dlopen of libnccl.so.2), the library does not link against it.
+ * K-split plans (IodineShape.slot_ranks > 1; replaces DataParallel, lib/modeling/build.py:11-12, for a batch smaller
+ * than the number of GPUs): the ranks hold different SLOTS of the same images, and the K-way reductions of
+ * IODINE.elbo (mask softmax iodine.py:185, mixture logsumexp 213-216, mask posterior 292, leave-one-out 324) cross
+ * ranks.  The exchange is ONE ncclAllGather per elbo() evaluation of the decoder's 4-channel output
+ * [B,K,H,W,4] fp32 (256 KB per slot at 128x128) on the stream of the call; every rank then evaluates the pixel
+ * mixture for all K slots and keeps the seeds / auxiliary channels of its own.  The ELBO table is summed as above
+ * (the image log-likelihood is contributed by slot_rank 0 only, the KL by every rank for its slots).  rank / nranks
+ * must equal slot_rank / slot_ranks. */
 IODINE_API int iodine_plan_set_comm(IodinePlan* plan, void* nccl_comm, int32_t rank, int32_t nranks);
 
 /* Evaluator tail: lib/eval/ari_eval.py:32-39 (argmax over the K predicted masks) +

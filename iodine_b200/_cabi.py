@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libiodine_b200.so')
 
 MAX_LAYERS = 8
+ABI_VERSION = 2
 FP32, BF16, TF32, FP16 = 0, 1, 2, 3
 PRECISIONS = {'fp32': FP32, 'bf16': BF16, 'fp16': FP16, 'tf32': TF32}
 
@@ -27,7 +28,7 @@ class IodineShape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'B', 'K', 'L', 'H', 'W', 'T', 'img_c', 'dec_layers', 'dec_chan', 'dec_k',
         'ref_layers', 'ref_chan', 'ref_k', 'ref_stride', 'mlp_units', 'layernorm')] + [
-        ('sigma', C.c_float), ('precision', C.c_int32)]
+        ('sigma', C.c_float), ('precision', C.c_int32), ('slot_ranks', C.c_int32), ('slot_rank', C.c_int32)]
 
 
 _FP = C.c_void_p
@@ -93,7 +94,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = i32
-    if lib.iodine_abi_version() != 1:
+    if lib.iodine_abi_version() != ABI_VERSION:
         raise IodineError('ABI version mismatch: %d' % lib.iodine_abi_version())
     _lib = lib
     return lib

@@ -73,6 +73,11 @@ struct Plan {
   int device = 0;
   int num_sms = 148;
   int BK = 0, HW = 0, M = 0, C = 0, Cr = 0;
+  // K-split (IodineShape.slot_ranks > 1): s.K is rewritten to the LOCAL slot count at create, so that every
+  // per-slot loop and buffer of the plan covers this rank's slots only; the pixel mixture and the recombination
+  // are the two places that see all K_total slots of an image (through out4_all)
+  int K_total = 0;            // ARCH.SLOTS
+  int ks_ranks = 1, ks_rank = 0;
   int n_class = 0;            // dec_k * dec_k border classes of decoder layer 1
   int ref_h[IODINE_MAX_LAYERS + 1];
   int ref_w[IODINE_MAX_LAYERS + 1];
@@ -123,7 +128,8 @@ struct Plan {
   size_t ws_bytes = 0, ws_need = 0;
   void* act[IODINE_MAX_LAYERS];   // [BK,H,W,C] fp32 (or bf16 in IODINE_BF16) post-activations
   void* gbuf[2];                  // dgrad ping-pong, same type as act
-  float* out4 = nullptr;          // [BK,H,W,4]
+  float* out4 = nullptr;          // [BK,H,W,4] this rank's slots (K-split: a window of out4_all)
+  float* out4_all = nullptr;      // [ks_ranks][B,K,H,W,4]: every rank's out4 after the all-gather (== out4 without K-split)
   float* seed4 = nullptr;         // [BK,H,W,4] fp32; IODINE_BF16: the same bytes hold [BK,H,W,8] bf16
                                   // (4 gradient channels + 4 zeros = one 8-channel plane)
   float* auxs = nullptr;          // [BK,H,W,12] per-slot raw aux channels
@@ -199,6 +205,12 @@ int launch_refine_convs(Plan* p, const float* x, cudaStream_t st);
 int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st);
 int launch_recombine(Plan* p, float* pred, float* mask, float* mean, int n_images, cudaStream_t st,
                      uint8_t* amax = nullptr);   // amax[B,H,W]: argmax over the K masks (evaluator tail)
+// slot (b, k) of an image, k in [0, K_total), inside out4_all [ks_ranks][B][Kl][HW] (float4 units): rank-major, as
+// ncclAllGather leaves it; without K-split (Kl == K_total) this is the plain (b * K + k) * HW
+__host__ __device__ __forceinline__ size_t out4_slot(int b, int k, int B, int Kl, int HW) {
+  const int r = k / Kl;
+  return ((size_t)(r * B + b) * Kl + (k - r * Kl)) * HW;
+}
 int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st);
 int launch_assemble16(Plan* p, const float* x, cudaStream_t st);   // 16-bit modes: writes p->enc16
 

@@ -21,8 +21,12 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
                float* __restrict__ seed4, float* __restrict__ auxs, float* __restrict__ lik,
                double* __restrict__ stats, double* __restrict__ accum,
                int K, int HW, float inv_2s2, float inv_s2, float ll_const, int want_grads,
-               int seed_half /* 0: fp32 float4, 1: bf16 x8, 2: fp16 x8 */) {
-  const int b = blockIdx.y;
+               int seed_half /* 0: fp32 float4, 1: bf16 x8, 2: fp16 x8 */,
+               int Kl, int k_off, int ll_on) {
+  // K-split: out4 holds all K slots of every image (out4_slot), this rank keeps the outputs of slots
+  // [k_off, k_off + Kl) under LOCAL slot numbers; whole images: Kl == K, k_off == 0.  ll_on: this rank adds the
+  // image log-likelihood to the step's sum (K-split: exactly one rank does).
+  const int b = blockIdx.y, B = gridDim.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = pix < HW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -40,7 +44,7 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
   for (int k = 0; k < KMAX; ++k) {
     lg[k] = -INFINITY; mr[k] = mg[k] = mb[k] = 0.f;
     if (k < K && live) {
-      const float4 v = reinterpret_cast<const float4*>(out4)[((size_t)(b * K + k)) * HW + pix];
+      const float4 v = reinterpret_cast<const float4*>(out4)[out4_slot(b, k, B, Kl, HW) + pix];
       mr[k] = sigmoid_f(v.x); mg[k] = sigmoid_f(v.y); mb[k] = sigmoid_f(v.z);
       lg[k] = v.w;
       lmax = fmaxf(lmax, v.w);
@@ -99,7 +103,7 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int w = 0; w < NW; ++w) t += red[w];
-      atomicAdd(&accum[0], t);
+      if (ll_on) atomicAdd(&accum[0], t);
     }
   }
   if (!want_grads) return;
@@ -142,7 +146,7 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
 #pragma unroll
       for (int kk = 0; kk < MIX_KB; ++kk) {
         const int k = bt * MIX_KB + kk;             // compile-time
-        if (k < KMAX && k < K && live) {
+        if (k < KMAX && k < K && live && k >= k_off && k < k_off + Kl) {
           const float mk = lg[k], m_r = mr[k], m_g = mg[k], m_b = mb[k], gmk = gm[k], lgr = logit_raw[k];
           const float dr = xr - m_r, dg = xg - m_g, db = xb - m_b;
           const float llr = -dr * dr * inv_2s2 + ll_const, llg = -dg * dg * inv_2s2 + ll_const,
@@ -154,7 +158,7 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
           const float Lk = expf(llr + llg + llb);
           const float mpost = Lk / kl_tot;                                   // (292) 0/0 -> NaN as ref
           const float loo = (mkl_tot - mk * Lk) / (1.f - mk + 1e-5f);        // (326-328)
-          const size_t sp = ((size_t)(b * K + k)) * HW + pix;
+          const size_t sp = ((size_t)(b * Kl + (k - k_off))) * HW + pix;
           float4* ax = reinterpret_cast<float4*>(auxs) + sp * 3;
           ax[0] = make_float4(m_r, m_g, m_b, mk);
           ax[1] = make_float4(lgr, mpost, gr, gg);
@@ -198,13 +202,13 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
     const double v = s_stat[bt][l];
     if (l < 30) {
       const int k = bt * MIX_KB + l / 6, j = l % 6;
-      if (k < K) {
+      if (k >= k_off && k < k_off + Kl) {
         const int grp = j >> 1, g = (grp == 2) ? 3 : grp;
-        atomicAdd(&stats[((size_t)(b * K + k) * 4 + g) * 2 + (j & 1)], v);
+        atomicAdd(&stats[((size_t)(b * Kl + (k - k_off)) * 4 + g) * 2 + (j & 1)], v);
       }
     } else if (bt == 0) {
       // likelihood statistics are per image; every slot of the image gets the same numbers
-      for (int k = 0; k < K; ++k) atomicAdd(&stats[((size_t)(b * K + k) * 4 + 2) * 2 + (l - 30)], v);
+      for (int k = 0; k < Kl; ++k) atomicAdd(&stats[((size_t)(b * Kl + k) * 4 + 2) * 2 + (l - 30)], v);
     }
   }
 }
@@ -218,14 +222,14 @@ int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st) {
   if (want_grads)
     IOD_CHECK_CUDA(cudaMemsetAsync(p->stats, 0, (size_t)p->BK * 8 * sizeof(double), st));
   dim3 grid((p->HW + 127) / 128, s.B);
-  if (s.K <= 8)
-    mixture_kernel<8><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
-                                            p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads,
-                                            (tc_mode(p) && !tf_mode(p)) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0);
+  const int seed_half = (tc_mode(p) && !tf_mode(p)) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0;
+  const int k_off = p->ks_rank * s.K, ll_on = p->ks_rank == 0;
+  if (p->K_total <= 8)
+    mixture_kernel<8><<<grid, 128, 0, st>>>(p->out4_all, x, p->seed4, p->auxs, p->lik, p->stats, p->accum, p->K_total,
+                                            p->HW, inv_2s2, inv_s2, ll_const, want_grads, seed_half, s.K, k_off, ll_on);
   else
-    mixture_kernel<16><<<grid, 128, 0, st>>>(p->out4, x, p->seed4, p->auxs, p->lik, p->stats,
-                                             p->accum, s.K, p->HW, inv_2s2, inv_s2, ll_const, want_grads,
-                                             (tc_mode(p) && !tf_mode(p)) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0);
+    mixture_kernel<16><<<grid, 128, 0, st>>>(p->out4_all, x, p->seed4, p->auxs, p->lik, p->stats, p->accum, p->K_total,
+                                             p->HW, inv_2s2, inv_s2, ll_const, want_grads, seed_half, s.K, k_off, ll_on);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -387,21 +391,22 @@ int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st) 
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 recombine_kernel(const float* __restrict__ out4, float* __restrict__ pred, float* __restrict__ mask,
-                 float* __restrict__ mean, uint8_t* __restrict__ amax, int K, int HW) {
+                 float* __restrict__ mean, uint8_t* __restrict__ amax, int K, int HW, int B, int Kl) {
+  // out4: all K slots of every image (out4_slot; K-split: gathered from the ranks); outputs are complete [B,K,...]
   const int b = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= HW) return;
   float lmax = -INFINITY;
   for (int k = 0; k < K; ++k)
-    lmax = fmaxf(lmax, out4[(((size_t)(b * K + k)) * HW + pix) * 4 + 3]);
+    lmax = fmaxf(lmax, out4[(out4_slot(b, k, B, Kl, HW) + pix) * 4 + 3]);
   float den = 0.f;
-  for (int k = 0; k < K; ++k) den += expf(out4[(((size_t)(b * K + k)) * HW + pix) * 4 + 3] - lmax);
+  for (int k = 0; k < K; ++k) den += expf(out4[(out4_slot(b, k, B, Kl, HW) + pix) * 4 + 3] - lmax);
   const float inv = 1.f / den;
   float pr = 0.f, pg = 0.f, pb = 0.f;
   float mbest = -1.f;
   int kbest = 0;
   for (int k = 0; k < K; ++k) {
-    const float4 v = reinterpret_cast<const float4*>(out4)[((size_t)(b * K + k)) * HW + pix];
+    const float4 v = reinterpret_cast<const float4*>(out4)[out4_slot(b, k, B, Kl, HW) + pix];
     const float m = expf(v.w - lmax) * inv;
     if (m > mbest) { mbest = m; kbest = k; }         // first maximum, as torch.argmax (lib/eval/ari_eval.py:32-39)
     const float r = sigmoid_f(v.x), g = sigmoid_f(v.y), bl = sigmoid_f(v.z);
@@ -423,7 +428,7 @@ recombine_kernel(const float* __restrict__ out4, float* __restrict__ pred, float
 
 int launch_recombine(Plan* p, float* pred, float* mask, float* mean, int n_images, cudaStream_t st, uint8_t* amax) {
   dim3 grid((p->HW + 255) / 256, n_images);
-  recombine_kernel<<<grid, 256, 0, st>>>(p->out4, pred, mask, mean, amax, p->s.K, p->HW);
+  recombine_kernel<<<grid, 256, 0, st>>>(p->out4_all, pred, mask, mean, amax, p->K_total, p->HW, p->s.B, p->s.K);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

@@ -40,7 +40,10 @@ static size_t carve(Plan* p, char* base) {
     const bool need = s.dec_layers > 1 || (i == 0 && tc_mode(p));
     p->gbuf[i] = take(need ? BK * HW * C * eb : 1024);
   }
-  p->out4 = (float*)take(BK * HW * 4 * sizeof(float));
+  // K-split: one buffer for all ranks' slots, rank-major as ncclAllGather fills it; this rank's decoder writes its
+  // own window in place (sendbuff == recvbuff + rank * count)
+  p->out4_all = (float*)take((size_t)p->ks_ranks * BK * HW * 4 * sizeof(float));
+  p->out4 = base ? p->out4_all + (size_t)p->ks_rank * BK * HW * 4 : nullptr;
   p->seed4 = (float*)take(BK * HW * 4 * sizeof(float));
   p->auxs = (float*)take(BK * HW * 12 * sizeof(float));
   const bool rtc = rtc_enabled(p);
@@ -72,13 +75,14 @@ static size_t carve(Plan* p, char* base) {
   p->hx = (float*)take((size_t)s.B * 3 * HW * sizeof(float));
   p->heps = (float*)take((size_t)(s.T + 1) * BK * L * sizeof(float));
   p->hpred = (float*)take((size_t)s.B * 3 * HW * sizeof(float));
-  p->hmask = (float*)take(BK * HW * sizeof(float));
-  p->hmean = (float*)take(BK * 3 * HW * sizeof(float));
+  const size_t BKt = (size_t)s.B * p->K_total;               // decode() returns all K slots of every image
+  p->hmask = (float*)take(BKt * HW * sizeof(float));
+  p->hmean = (float*)take(BKt * 3 * HW * sizeof(float));
   p->hamax = (uint8_t*)take((size_t)s.B * HW);
   // logger side channel (iodine.py:226-239): image 0 of the last elbo() evaluation
   p->log_pred = (float*)take((size_t)3 * HW * sizeof(float));
-  p->log_mask = (float*)take((size_t)s.K * HW * sizeof(float));
-  p->log_mean = (float*)take((size_t)s.K * 3 * HW * sizeof(float));
+  p->log_mask = (float*)take((size_t)p->K_total * HW * sizeof(float));
+  p->log_mean = (float*)take((size_t)p->K_total * 3 * HW * sizeof(float));
   return off;
 }
 
@@ -107,6 +111,8 @@ static void prof_mark(Plan* p, cudaStream_t st) {
   cudaEventRecord(p->prof_events[p->prof_used++], st);
 }
 
+static int gather_out4(Plan* p, cudaStream_t st);
+
 // ---------------------------------------------------------------- decoder forward / dgrad
 static int decoder_forward(Plan* p, const float* mu, const float* lv, const float* eps,
                            const float* z_in, cudaStream_t st) {
@@ -123,8 +129,12 @@ static int decoder_forward(Plan* p, const float* mu, const float* lv, const floa
     }
     prof_mark(p, st);
   }
-  if (tc_mode(p)) return tc_launch_out4(p, p->act[s.dec_layers - 1], p->out4, st);
-  return launch_conv_out4(p, (const float*)p->act[s.dec_layers - 1], p->out4, st);
+  if (tc_mode(p)) {
+    if (tc_launch_out4(p, p->act[s.dec_layers - 1], p->out4, st)) return 1;
+  } else {
+    if (launch_conv_out4(p, (const float*)p->act[s.dec_layers - 1], p->out4, st)) return 1;
+  }
+  return gather_out4(p, st);
 }
 
 static int decoder_dgrad(Plan* p, cudaStream_t st) {
@@ -286,7 +296,9 @@ static int do_encode_g(Plan* p, const float* x, const float* eps, float* z_out, 
 // never load it.  Prototype and enum values: nccl.h (ncclFloat32 = 7, ncclSum = 0, ncclSuccess = 0).
 // ------------------------------------------------------------------------------------------------
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef const char* (*nccl_errstr_fn)(int);
+static nccl_allgather_fn g_nccl_allgather = nullptr;
 static nccl_allreduce_fn g_nccl_allreduce = nullptr;
 static nccl_errstr_fn g_nccl_errstr = nullptr;
 
@@ -300,9 +312,27 @@ static int resolve_nccl() {
     return 1;
   }
   g_nccl_allreduce = reinterpret_cast<nccl_allreduce_fn>(dlsym(h, "ncclAllReduce"));
+  g_nccl_allgather = reinterpret_cast<nccl_allgather_fn>(dlsym(h, "ncclAllGather"));
   g_nccl_errstr = reinterpret_cast<nccl_errstr_fn>(dlsym(h, "ncclGetErrorString"));
-  if (!g_nccl_allreduce) {
-    set_error("iodine_plan_set_comm: libnccl has no ncclAllReduce");
+  if (!g_nccl_allreduce || !g_nccl_allgather) {
+    g_nccl_allreduce = nullptr;
+    set_error("iodine_plan_set_comm: libnccl has no ncclAllReduce / ncclAllGather");
+    return 1;
+  }
+  return 0;
+}
+
+// K-split: every rank's [B,K_local,H,W,4] decoder output -> out4_all on all ranks (in place), the one data-path
+// collective of that mode (SURVEY.md 8e "K-split fallback")
+static int gather_out4(Plan* p, cudaStream_t st) {
+  if (p->ks_ranks <= 1) return 0;
+  IOD_REQUIRE(p->comm != nullptr, "K-split plan (slot_ranks = %d) has no communicator: call iodine_plan_set_comm first",
+              p->ks_ranks);
+  const size_t count = (size_t)p->BK * p->HW * 4;
+  const int rc = g_nccl_allgather(p->out4, p->out4_all, count, /*ncclFloat32*/ 7, p->comm, st);
+  if (rc != 0) {
+    set_error("ncclAllGather of the decoder output failed on rank %d/%d: %s", p->comm_rank, p->comm_nranks,
+              g_nccl_errstr ? g_nccl_errstr(rc) : "?");
     return 1;
   }
   return 0;
@@ -356,6 +386,12 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
   IOD_REQUIRE(s.precision == IODINE_FP32 || s.precision == IODINE_BF16 || s.precision == IODINE_FP16 ||
                   s.precision == IODINE_TF32,
               "unsupported precision %d", s.precision);
+  IOD_REQUIRE(s.slot_ranks >= 0 && s.slot_ranks <= 16, "bad slot_ranks=%d", s.slot_ranks);
+  if (s.slot_ranks > 1) {
+    IOD_REQUIRE(s.K % s.slot_ranks == 0, "K-split: SLOTS=%d is not a multiple of slot_ranks=%d", s.K, s.slot_ranks);
+    IOD_REQUIRE(s.slot_rank >= 0 && s.slot_rank < s.slot_ranks, "K-split: slot_rank %d outside [0, %d)", s.slot_rank,
+                s.slot_ranks);
+  }
 
   Plan* p = new Plan();
   if (plan_build(p, s)) {                       // nothing half-built survives a failed create
@@ -366,10 +402,18 @@ IODINE_API int iodine_plan_create(const IodineShape* shape, IodinePlan** plan_ou
   return 0;
 }
 
-static int plan_build(Plan* p, const IodineShape& s) {
-  p->s = s;
+static int plan_build(Plan* p, const IodineShape& s_in) {
+  p->s = s_in;
+  p->K_total = s_in.K;
+  if (s_in.slot_ranks > 1) {                    // K-split: from here on the plan's K is its own share of the slots
+    p->ks_ranks = s_in.slot_ranks;
+    p->ks_rank = s_in.slot_rank;
+    p->s.K = s_in.K / s_in.slot_ranks;
+  }
+  const IodineShape& s = p->s;
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { p->ref_wp[l] = nullptr; p->ref_b[l] = nullptr; }
-  p->graphs = getenv("IODINE_NO_GRAPH") == nullptr;
+  // (K-split steps contain an NCCL collective: they run eagerly)
+  p->graphs = getenv("IODINE_NO_GRAPH") == nullptr && p->ks_ranks == 1;
   IOD_CHECK_CUDA(cudaGetDevice(&p->device));
   IOD_CHECK_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
   p->BK = s.B * s.K; p->HW = s.H * s.W; p->M = s.mlp_units; p->C = s.dec_chan; p->Cr = s.ref_chan;
@@ -514,6 +558,9 @@ IODINE_API int iodine_plan_set_comm(IodinePlan* plan, void* nccl_comm, int32_t r
     return 0;
   }
   IOD_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "iodine_plan_set_comm: rank %d outside [0, %d)", rank, nranks);
+  IOD_REQUIRE(p->ks_ranks == 1 || (nranks == p->ks_ranks && rank == p->ks_rank),
+              "iodine_plan_set_comm: a K-split plan (slot_rank %d of %d) needs a communicator of exactly those ranks "
+              "(got rank %d of %d)", p->ks_rank, p->ks_ranks, rank, nranks);
   if (resolve_nccl()) return 1;
   p->comm = nccl_comm; p->comm_rank = rank; p->comm_nranks = nranks;
   return 0;
@@ -546,7 +593,7 @@ IODINE_API int iodine_plan_last_elbo_image0(IodinePlan* plan, float* pred0, floa
   Plan* p = reinterpret_cast<Plan*>(plan);
   if (check_ready(p)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t HW = p->HW, K = p->s.K;
+  const size_t HW = p->HW, K = p->K_total;
   if (pred0) IOD_CHECK_CUDA(cudaMemcpyAsync(pred0, p->log_pred, 3 * HW * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (mask0) IOD_CHECK_CUDA(cudaMemcpyAsync(mask0, p->log_mask, K * HW * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (mean0) IOD_CHECK_CUDA(cudaMemcpyAsync(mean0, p->log_mean, K * 3 * HW * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -570,8 +617,9 @@ IODINE_API int iodine_reconstruct_host_async(IodinePlan* plan, const float* x_ho
                 mean_host ? p->hmean : nullptr, st))
     return 1;
   if (pred_host) IOD_CHECK_CUDA(cudaMemcpyAsync(pred_host, p->hpred, (size_t)s.B * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (mask_host) IOD_CHECK_CUDA(cudaMemcpyAsync(mask_host, p->hmask, BK * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (mean_host) IOD_CHECK_CUDA(cudaMemcpyAsync(mean_host, p->hmean, BK * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
+  const size_t BKt = (size_t)s.B * p->K_total;
+  if (mask_host) IOD_CHECK_CUDA(cudaMemcpyAsync(mask_host, p->hmask, BKt * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (mean_host) IOD_CHECK_CUDA(cudaMemcpyAsync(mean_host, p->hmean, BKt * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (z_host) IOD_CHECK_CUDA(cudaMemcpyAsync(z_host, p->st_z, BK * s.L * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (elbo_terms_host) IOD_CHECK_CUDA(cudaMemcpyAsync(elbo_terms_host, p->st_terms, (size_t)s.T * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
   return 0;

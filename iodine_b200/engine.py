@@ -20,9 +20,9 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def shape_from_arch(arch, B, precision='fp32'):
+def shape_from_arch(arch, B, precision='fp32', slot_split=None):
     """IodineShape from a ``cfg.ARCH``-like object (fields read at reference
-    lib/modeling/iodine.py:10-32)."""
+    lib/modeling/iodine.py:10-32).  ``slot_split = (rank, nranks)``: K-split plan (this rank owns K/nranks slots)."""
     s = _cabi.IodineShape()
     s.B, s.K, s.L = int(B), int(arch.SLOTS), int(arch.DIM_LATENT)
     s.H = s.W = int(arch.IMG_SIZE)
@@ -37,21 +37,28 @@ def shape_from_arch(arch, B, precision='fp32'):
     s.layernorm = 1 if arch.LAYERNORM else 0
     s.sigma = float(arch.SIGMA)
     s.precision = _cabi.PRECISIONS[precision]
+    if slot_split is not None and int(slot_split[1]) > 1:
+        s.slot_rank, s.slot_ranks = int(slot_split[0]), int(slot_split[1])
     return s
 
 
 class RefinementEngine:
     """One plan = one (architecture, per-call batch B, precision, device)."""
 
-    def __init__(self, arch, B, device, precision='fp32'):
+    def __init__(self, arch, B, device, precision='fp32', slot_split=None):
+        """``slot_split = (rank, nranks)``: K-split (include/iodine_b200.h, IodineShape.slot_ranks) -- this engine
+        owns K/nranks slots of every image: eps / z / posterior / LSTM state carry ``self.K`` = K/nranks slots,
+        decode()/reconstruct() return all ``self.K_total`` slots.  Needs ``set_comm`` before the first step."""
         self.lib = _cabi.load()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _cabi.IodineError('the refinement engine runs on CUDA devices only (got %s); '
                                     'there is no CPU fallback' % self.device)
         self.arch, self.B, self.precision = arch, int(B), precision
-        self.shape = shape_from_arch(arch, B, precision)
-        self.K, self.L, self.T = self.shape.K, self.shape.L, self.shape.T
+        self.shape = shape_from_arch(arch, B, precision, slot_split)
+        self.K_total = self.shape.K
+        self.K = self.shape.K // max(1, self.shape.slot_ranks)
+        self.L, self.T = self.shape.L, self.shape.T
         self.H, self.W, self.M = self.shape.H, self.shape.W, self.shape.mlp_units
         self._plan = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -174,16 +181,16 @@ class RefinementEngine:
             return self._z.clone(), self._terms[:T].clone(), self._post.clone()
 
     def decode(self, z):
-        B, K = self.B, self.K
+        B, K, Kt = self.B, self.K, self.K_total
         z = self._f32(z, (B, K, self.L))
-        pred, mask, mean = (self._new(B, 3, self.H, self.W), self._new(B, K, 1, self.H, self.W),
-                            self._new(B, K, 3, self.H, self.W))
+        pred, mask, mean = (self._new(B, 3, self.H, self.W), self._new(B, Kt, 1, self.H, self.W),
+                            self._new(B, Kt, 3, self.H, self.W))
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.iodine_decode(self._plan, _ptr(z), _ptr(pred), _ptr(mask), _ptr(mean), _stream()))
         return pred, mask, mean
 
     def reconstruct(self, x, eps):
-        B, K, T = self.B, self.K, self.T
+        B, K, T = self.B, self.K_total, self.T
         pred, mask, mean = (self._new(B, 3, self.H, self.W), self._new(B, K, 1, self.H, self.W),
                             self._new(B, K, 3, self.H, self.W))
         with torch.cuda.device(self.device):
@@ -203,8 +210,9 @@ class RefinementEngine:
         if out is None:
             pin = torch.cuda.is_available()
             mk = lambda *s: torch.empty(*s, dtype=torch.float32, pin_memory=pin)
-            out = dict(pred=mk(B, 3, self.H, self.W), mask=mk(B, K, 1, self.H, self.W),
-                       mean=mk(B, K, 3, self.H, self.W), z=mk(B, K, L), terms=mk(max(T, 1), 2))
+            Kt = self.K_total
+            out = dict(pred=mk(B, 3, self.H, self.W), mask=mk(B, Kt, 1, self.H, self.W),
+                       mean=mk(B, Kt, 3, self.H, self.W), z=mk(B, K, L), terms=mk(max(T, 1), 2))
         with torch.cuda.device(self.device):
             fn = self.lib.iodine_reconstruct_host if sync else self.lib.iodine_reconstruct_host_async
             _cabi.check(fn(
@@ -234,7 +242,7 @@ class RefinementEngine:
     def last_elbo_image0(self):
         """(pred[3,H,W], mask[K,H,W], mean[K,3,H,W]) of image 0 as the LAST elbo() evaluation of this plan produced
         them -- what the reference hands its logger (iodine.py:225-239)."""
-        K, H, W = self.K, self.H, self.W
+        K, H, W = self.K_total, self.H, self.W
         pred, mask, mean = self._new(3, H, W), self._new(K, H, W), self._new(K, 3, H, W)
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.iodine_plan_last_elbo_image0(self._plan, _ptr(pred), _ptr(mask), _ptr(mean), _stream()))

@@ -132,6 +132,7 @@ class IODINE(nn.Module):
         self.elbo_terms = None      # [T,2]: (sum_b log-lik, sum_b KL) per refinement step
         self._engines = {}
         self._comm = None           # (NcclComm, rank, nranks) installed by set_comm()
+        self._slot_split = None     # (rank, nranks) installed by set_slot_split(): this replica owns K/nranks slots
         self._weights_sig = {}
         self._weights_epoch = 0
         self.max_images_per_call = None   # None = automatic (fit the workspace in free HBM)
@@ -190,14 +191,14 @@ class IODINE(nn.Module):
 
     def _engine(self, B):
         dev = self._device()
-        key = (int(B), str(dev), self.precision)
+        key = (int(B), str(dev), self.precision, self._slot_split)
         eng = self._engines.get(key)
         if eng is None:
             if len(self._engines) >= 3:          # a few plans (full chunk, tail chunk, a second batch size)
                 old = next(iter(self._engines))
                 self._engines.pop(old).close()
                 self._weights_sig.pop(old, None)
-            eng = RefinementEngine(self.arch, B, dev, self.precision)
+            eng = RefinementEngine(self.arch, B, dev, self.precision, slot_split=self._slot_split)
             if self._comm is not None:
                 eng.set_comm(*self._comm)
             self._engines[key] = eng
@@ -216,6 +217,23 @@ class IODINE(nn.Module):
         for eng in self._engines.values():
             eng.set_comm(comm, rank, nranks)
 
+    def set_slot_split(self, comm, rank, nranks):
+        """K-split (SURVEY.md 8e fallback, for a batch smaller than the number of GPUs): this replica owns the slots
+        ``[rank*K/nranks, (rank+1)*K/nranks)`` of every image.  ``eps`` passed to encode()/reconstruct() and the
+        ``z`` / posterior they leave then carry K/nranks slots; ``pred, mask, mean`` are complete on every rank;
+        the library all-gathers the decoder's 4-channel output once per elbo() evaluation (``iodine_plan_set_comm``
+        on a K-split plan).  ``iodine_b200.parallel.KSplit`` drives this from a global batch."""
+        if self.K % int(nranks):
+            raise ValueError('K-split: SLOTS=%d is not a multiple of %d ranks' % (self.K, nranks))
+        for eng in self._engines.values():
+            eng.close()
+        self._engines, self._weights_sig = {}, {}
+        self._slot_split = (int(rank), int(nranks)) if int(nranks) > 1 else None
+        self._comm = None if comm is None else (comm, int(rank), int(nranks))
+
+    def _local_slots(self):
+        return self.K // (self._slot_split[1] if self._slot_split else 1)
+
     def _chunk(self, B):
         if self.max_images_per_call:
             return min(B, int(self.max_images_per_call))
@@ -230,7 +248,7 @@ class IODINE(nn.Module):
         return max(1, min(B, int(0.8 * (free + cached) // max(per_img, 1))))
 
     def _noise(self, B, eps):
-        T, K, L = self.n_iters, self.K, self.dim_latent
+        T, K, L = self.n_iters, self._local_slots(), self.dim_latent
         if eps is None:
             # reference: torch.randn_like on the model's device, T+1 draws (iodine.py:632)
             return torch.randn(T + 1, B, K, L, device=self._device(), dtype=torch.float32)
@@ -303,7 +321,7 @@ class IODINE(nn.Module):
         """reference iodine.py:161-241: single-pass ELBO (mean over batch) for the current
         posterior (``self.posterior.mean/logvar``; the learnt initial posterior if unset)."""
         x = self._require_cuda(x)
-        B, K, L = x.shape[0], self.K, self.dim_latent
+        B, K, L = x.shape[0], self._local_slots(), self.dim_latent
         mu, lv = self.posterior.mean, self.posterior.logvar
         if mu is None or mu.shape[0] != B:
             mu = self.posterior.init_mean.detach()[None, None].repeat(B, K, 1)

@@ -129,8 +129,9 @@ class SlotShard:
         self._set_global_batch(B)
         b0, b1 = shard_bounds(B, self.world, self.rank)
         if b1 <= b0:
-            raise ValueError('rank %d of %d has no image: global batch %d is smaller than the '
-                             'world size (K-split mode is not implemented)' % (self.rank, self.world, B))
+            raise ValueError('rank %d of %d has no image: global batch %d is smaller than the world size -- '
+                             'use iodine_b200.parallel.KSplit (ranks own slots instead of images)'
+                             % (self.rank, self.world, B))
         return x[b0:b1], (None if eps is None else eps[:, b0:b1])
 
     def _set_global_batch(self, n):
@@ -213,5 +214,65 @@ class SlotShard:
 
     def elbo_per_step(self):
         """Global ELBO of every refinement step (mean over the GLOBAL batch), identical on all ranks."""
+        t = self.elbo_terms
+        return (t[:, 0] - t[:, 1]) / self.global_batch
+
+
+class KSplit:
+    """K-split: the fallback partition for a batch SMALLER than the number of GPUs (e.g. one image
+    with K = 16 on 2-8 GPUs), again replacing ``torch.nn.DataParallel`` (``lib/modeling/build.py:11-12``), which can
+    only scatter the batch axis.  Every rank holds ALL images and ``K / world`` of their slots: decoder, data-gradient,
+    refinement network and posterior state are per slot, so they split; the K-way reductions of ``IODINE.elbo``
+    (``iodine.py:185, 213-216, 292, 324``) need every slot's decoder output, which the library all-gathers once per
+    elbo() evaluation (``ncclAllGather`` of ``[B,K,H,W,4]`` fp32 on the stream of the call, ``iodine_plan_set_comm`` on
+    a K-split plan).  ``pred / mask / mean`` come back complete on every rank, ``z`` as this rank's slots (or all of
+    them with ``gather=True``); the ``[T,2]`` ELBO table is all-reduced by the library as in ``SlotShard``.
+
+    NCCL only (the exchange sits between two kernels of a step): needs a CUDA model and an initialised
+    ``torch.distributed`` NCCL group to carry the communicator's unique id.
+    """
+
+    def __init__(self, model, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError('KSplit needs torch.distributed (one process per GPU)')
+        self.model, self.group = model, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if model.K % self.world:
+            raise ValueError('K-split: SLOTS=%d is not a multiple of the world size %d' % (model.K, self.world))
+        self.k_local = model.K // self.world
+        self.k0 = self.rank * self.k_local
+        self._comm = NcclComm(group=group)
+        model.set_slot_split(self._comm, self.rank, self.world)
+        self.elbo_terms = None
+        self.global_batch = None
+
+    def slots(self):
+        """this rank's slot range [k0, k1)"""
+        return self.k0, self.k0 + self.k_local
+
+    def _eps(self, eps):
+        return None if eps is None else eps[:, :, self.k0:self.k0 + self.k_local].contiguous()
+
+    def _gather_slots(self, t):
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t.contiguous(), group=self.group)
+        return torch.cat(out, dim=1)
+
+    def _finish(self, B):
+        self.global_batch = B
+        self.elbo_terms = self.model.elbo_terms.clone()            # already summed over the ranks by the library
+
+    def encode(self, x, eps=None, gather=False):
+        """x[B,3,H,W] (the same on every rank); eps[T+1,B,K,L] for ALL slots (each rank slices its own)."""
+        z = self.model.encode(x, eps=self._eps(eps))
+        self._finish(x.shape[0])
+        return self._gather_slots(z) if gather else z
+
+    def reconstruct(self, x, eps=None):
+        pred, mask, mean = self.model.reconstruct(x, eps=self._eps(eps))
+        self._finish(x.shape[0])
+        return pred, mask, mean
+
+    def elbo_per_step(self):
         t = self.elbo_terms
         return (t[:, 0] - t[:, 1]) / self.global_batch

@@ -26,12 +26,12 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), 'missing export %s' % n
     assert sorted(_cabi.EXPORTS) == names
-    assert _cabi.load().iodine_abi_version() == 1
+    assert _cabi.load().iodine_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     from iodine_b200 import _cabi
-    assert ctypes.sizeof(_cabi.IodineShape) == 18 * 4
+    assert ctypes.sizeof(_cabi.IodineShape) == 20 * 4
     assert ctypes.sizeof(_cabi.IodineWeights) == (4 * _cabi.MAX_LAYERS + 14) * 8
 
 
