@@ -99,6 +99,29 @@ typedef struct IodineWeights {
   const float* init_logvar;               /* posterior.init_logvar [L]                   */
 } IodineWeights;
 
+/* One pointer per state_dict key, as IodineWeights: where iodine_train_step writes the gradient of the loss with
+ * respect to that parameter (same shape and layout as the parameter, fp32, DEVICE memory; NULL = not wanted). */
+typedef struct IodineGrads {
+  float* dec_w[IODINE_MAX_LAYERS];
+  float* dec_b[IODINE_MAX_LAYERS];
+  float* dec_out_w;
+  float* dec_out_b;
+  float* ref_w[IODINE_MAX_LAYERS];        /* layer 0: the full 17-channel layout [Cr,17,k,k] */
+  float* ref_b[IODINE_MAX_LAYERS];
+  float* mlp_w;
+  float* mlp_b;
+  float* lstm_w_ih;
+  float* lstm_w_hh;
+  float* lstm_b_ih;
+  float* lstm_b_hh;
+  float* mean_w;
+  float* mean_b;
+  float* logvar_w;
+  float* logvar_b;
+  float* init_mean;
+  float* init_logvar;
+} IodineGrads;
+
 typedef struct IodinePlan IodinePlan;
 
 IODINE_API int         iodine_abi_version(void);
@@ -185,6 +208,23 @@ IODINE_API int iodine_evaluate_host_async(IodinePlan* plan, const float* x_host,
  * this plan (the last refinement step of encode()/reconstruct(), or iodine_elbo): pred0[3,H,W], mask0[K,H,W],
  * mean0[K,3,H,W], device memory, any may be NULL. */
 IODINE_API int iodine_plan_last_elbo_image0(IodinePlan* plan, float* pred0, float* mask0, float* mean0, void* stream);
+
+/* TRAINING: IODINE.forward (iodine.py:115-158) + what lib/engine/train.py:60-65 does with its
+ * result -- loss.mean(), optimizer.zero_grad(), loss.backward() -- in one call: the T+1 ELBO evaluations with the
+ * refinement deltas kept attached, loss = -sum_i (i+1)/(T+1) elbo_i, and the gradient of the loss with respect to
+ * every parameter, by hand-written kernels (csrc/train.cu: decoder weight gradients accumulated inside each step
+ * next to the data-gradient chain, one backward sweep over a tape of the T refiner calls incl. the LSTM state
+ * chain).  The tape lives in a second caller-supplied workspace, needed for training only.
+ *   x[B,3,H,W]; eps[T+1,B,K,L] (the T+1 torch.randn_like draws, iodine.py:632);
+ *   global_batch: images behind the batch means (0 = this plan's B).  With a communicator installed the ranks hold
+ *     different images of one global batch: pass the global size; gradients, loss and ELBO table are then summed
+ *     over the ranks with ONE ncclAllReduce of the flat gradient buffer (replaces DataParallel's gradient reduction);
+ *   grads_out: overwritten (the reference zeroes the gradients before backward); loss_out[1];
+ *   elbo_terms_out[T+1,2] = { sum_b log-likelihood, sum_b KL } of every ELBO evaluation (nullable). */
+IODINE_API int iodine_plan_train_workspace_bytes(IodinePlan* plan, size_t* bytes_out);
+IODINE_API int iodine_plan_set_train_workspace(IodinePlan* plan, void* workspace, size_t bytes);
+IODINE_API int iodine_train_step(IodinePlan* plan, const float* x, const float* eps, int32_t global_batch,
+                      const IodineGrads* grads_out, float* loss_out, float* elbo_terms_out, void* stream);
 
 /* Multi-GPU (replaces torch.nn.DataParallel, lib/modeling/build.py:11-12, and the replica-mean of
  * lib/engine/train.py:61).  The path shards by whole images, one process and one plan per GPU; every K-way reduction

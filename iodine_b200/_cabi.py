@@ -21,6 +21,7 @@ EXPORTS = [
     'iodine_reconstruct', 'iodine_reconstruct_host', 'iodine_reconstruct_host_async', 'iodine_debug_read',
     'iodine_plan_launch_count', 'iodine_plan_profile', 'iodine_plan_profile_read', 'iodine_ari',
     'iodine_plan_set_comm', 'iodine_plan_last_elbo_image0', 'iodine_evaluate_host', 'iodine_evaluate_host_async',
+    'iodine_plan_train_workspace_bytes', 'iodine_plan_set_train_workspace', 'iodine_train_step',
 ]
 
 
@@ -44,6 +45,11 @@ class IodineWeights(C.Structure):
         ('mean_w', _FP), ('mean_b', _FP), ('logvar_w', _FP), ('logvar_b', _FP),
         ('init_mean', _FP), ('init_logvar', _FP),
     ]
+
+
+class IodineGrads(C.Structure):
+    """gradient outputs of iodine_train_step: the same fields as IodineWeights"""
+    _fields_ = list(IodineWeights._fields_)
 
 
 class IodineError(RuntimeError):
@@ -89,6 +95,9 @@ def load():
         'iodine_plan_last_elbo_image0': [vp] * 5,
         'iodine_evaluate_host': [vp] * 8,
         'iodine_evaluate_host_async': [vp] * 8,
+        'iodine_plan_train_workspace_bytes': [vp, C.POINTER(sz)],
+        'iodine_plan_set_train_workspace': [vp, vp, sz],
+        'iodine_train_step': [vp, vp, vp, i32, C.POINTER(IodineGrads), vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -120,6 +120,9 @@ struct Plan {
   float *w_ih = nullptr, *w_hh = nullptr, *b_ih = nullptr, *b_hh = nullptr;
   float *head_w = nullptr, *head_b = nullptr;   // [2L, M] (mean rows then logvar rows), [2L]
   float *init_mean = nullptr, *init_logvar = nullptr;
+  void* train = nullptr;      // training state (train.cu: TrainState)
+  float* tape_u = nullptr;    // training tape hooks of launch_head: the MLP's inner ELU [BK,M] ...
+  float* tape_gates = nullptr;  // ... and the summed LSTM gate pre-activations [BK,4M]
   void* tc = nullptr;         // tensor-core path state (conv_tc.cu: TcState), IODINE_BF16 / IODINE_FP16
   void* rtc = nullptr;        // refinement-encoder tensor-core state (refine_tc.cu: RtcState)
 
@@ -198,8 +201,8 @@ int launch_conv_cc(Plan* p, const float* in, const float* wpack, const float* bi
                    const float* act_prev, float* out, float* G, int mode, cudaStream_t st);
 int launch_conv_out4(Plan* p, const float* in, float* out4, cudaStream_t st);
 int launch_dgrad_in4(Plan* p, const float* seed4, const float* act_prev, float* gout,
-                     cudaStream_t st);
-int launch_refine_convs(Plan* p, const float* x, cudaStream_t st);
+                     cudaStream_t st, bool store = false);
+int launch_refine_convs(Plan* p, const float* x, cudaStream_t st, float* const* outs = nullptr);
 
 // ------------------------------------------------------------------ launchers (mixture.cu)
 int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st);
@@ -220,7 +223,16 @@ int launch_sample_l1(Plan* p, const float* mu, const float* logvar, const float*
 int launch_post_grads(Plan* p, const float* mu, const float* logvar, const float* eps,
                       float* latent_out, cudaStream_t st);
 int launch_head(Plan* p, float* mu, float* logvar, float* h, float* c, cudaStream_t st);
+int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st);
 int launch_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st);
+
+// ------------------------------------------------------------------ plan.cu pieces the training step reuses
+int plan_check_ready(Plan* p);
+int plan_decoder_forward(Plan* p, const float* mu, const float* lv, const float* eps, const float* z_in, cudaStream_t st);
+int plan_allreduce_sum(Plan* p, float* buf, size_t count, cudaStream_t st);   // no-op without a communicator
+int launch_assemble(Plan* p, const float* x, cudaStream_t st);
+int launch_init_state(Plan* p, float* mu, float* lv, float* h, float* c, cudaStream_t st);
+void train_free(Plan* p);
 
 // ------------------------------------------------------------------ conv_tc.cu (tcgen05 path)
 int tc_supported(const Plan* p);      // 1 if the bf16 tensor-core path can run this shape

@@ -248,10 +248,11 @@ int launch_conv_cc(Plan* p, const float* in, const float* wpack, const float* bi
 }
 
 // 4 -> C data-gradient of decoder.conv: g = convT(seed4, Wout) * ELU'(act_last)
+// store: always write the gradient (the training step reduces it itself), also for a one-layer decoder
 int launch_dgrad_in4(Plan* p, const float* seed4, const float* act_prev, float* gout,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool store) {
   const int C = p->C, KS = p->s.dec_k;
-  const int mode = (p->s.dec_layers == 1) ? 2 : 1;
+  const int mode = (p->s.dec_layers == 1 && !store) ? 2 : 1;
 #define IOD_CASE(c, k)                                                                     \
   if (C == c && KS == k) {                                                                 \
     if (mode == 1) return launch_cc_t<4, c, k, 1>(p, seed4, p->out_wt, nullptr, act_prev, gout, nullptr, st); \
@@ -523,11 +524,12 @@ __global__ void avgpool_kernel(const float* __restrict__ in, float* __restrict__
 
 // All refine conv layers.  Layer 0 reads the assembled 20-channel (17 + 3 zero pad) input
 // that mixture.cu::assemble wrote into rbuf[1]'s tail region (p->enc20).
-int launch_refine_convs(Plan* p, const float* enc20, cudaStream_t st) {
+// outs: optional per-layer output buffers (the training tape keeps every activation); default = ping-pong
+int launch_refine_convs(Plan* p, const float* enc20, cudaStream_t st, float* const* outs) {
   const float* cur = enc20;
   int cin = 20;
   for (int l = 0; l < p->s.ref_layers; ++l) {
-    float* dst = p->rbuf[l & 1];
+    float* dst = outs ? outs[l] : p->rbuf[l & 1];
     const float* w = (l == 0) ? p->ref_w0 : p->ref_wp[l];
     if (launch_strided(p, cur, w, p->ref_b[l], dst, cin, p->ref_h[l], p->ref_w[l], p->ref_h[l + 1],
                        p->ref_w[l + 1], st))

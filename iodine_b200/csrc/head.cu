@@ -247,7 +247,7 @@ post_grads_kernel(const float* __restrict__ G, const float* __restrict__ wsum,
                   const float* __restrict__ mu, const float* __restrict__ logvar,
                   const float* __restrict__ eps, float* __restrict__ dz_out,
                   float* __restrict__ xin, double* __restrict__ accum,
-                  int L, int NCC, int M, int layernorm) {
+                  int L, int NCC, int M, int layernorm, float* __restrict__ raw_out /* [N][2L] or null */) {
   extern __shared__ float sm[];
   float* sG = sm;            // [NCC]
   float* sa = sm + NCC;      // [L] dmu
@@ -283,6 +283,10 @@ post_grads_kernel(const float* __restrict__ G, const float* __restrict__ wsum,
     dz_out[(size_t)n * L + ci] = d;
     sa[ci] = d - m;
     sb[ci] = d * 0.5f * expf(0.5f * lv) * e - 0.5f * (expf(lv) - 1.f);
+    if (raw_out) {                                     // training tape: dJ/d(posterior) before the layer-norm
+      raw_out[(size_t)n * 2 * L + ci] = sa[ci];
+      raw_out[(size_t)n * 2 * L + L + ci] = sb[ci];
+    }
     klp += 0.5f * (expf(lv) + m * m - 1.f - lv);                       // iodine.py:657-658
   }
   klp = warp_sum(klp);
@@ -316,14 +320,14 @@ post_grads_kernel(const float* __restrict__ G, const float* __restrict__ wsum,
   }
 }
 
+// latent_out: optional [BK][2L] copy of the raw posterior gradients (dmu | dlogvar), kept by the training tape
 int launch_post_grads(Plan* p, const float* mu, const float* logvar, const float* eps,
                       float* latent_out, cudaStream_t st) {
-  (void)latent_out;
   const int ncc = p->n_class * p->C, L = p->s.L;
   const int parts = 256 / L > 0 ? 256 / L : 1;
   const size_t smem = (size_t)(ncc + 2 * L + parts * L) * sizeof(float);
   post_grads_kernel<<<p->BK, 256, smem, st>>>(p->G, p->wsum, mu, logvar, eps, p->dz, p->xin, p->accum,
-                                              L, ncc, p->M, p->s.layernorm);
+                                              L, ncc, p->M, p->s.layernorm, latent_out);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(256)
 linear_kernel(const float* __restrict__ X, int ldx, int I, const float* __restrict__ Wt,
               const float* __restrict__ b, const float* __restrict__ X2, int ldx2, int I2,
               const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ Y,
-              int ldy, int N, int O, int kchunk, size_t zstride) {
+              int ldy, int N, int O, int kchunk, size_t zstride, float* __restrict__ Y_inner = nullptr) {
   constexpr int TM = 16 * RM, TN = 64, TK = 16;
   __shared__ float sx[TK][TM + 4];
   __shared__ float sw[TK][TN + 4];
@@ -415,7 +419,11 @@ linear_kernel(const float* __restrict__ X, int ldx, int I, const float* __restri
       const int c = c0 + tx * 4 + j;
       if (c >= O) continue;
       float v = acc[i][j] + (blockIdx.z == 0 ? b[c] + (b2 ? b2[c] : 0.f) : 0.f);
-      if (ACT == 1) v = elu_f(elu_f(v));
+      if (ACT == 1) {
+        v = elu_f(v);
+        if (Y_inner) Y_inner[(size_t)r * O + c] = v;     // training tape: the MLP's own ELU, before the extra one
+        v = elu_f(v);
+      }
       Y[(size_t)r * ldy + c] = v;
     }
   }
@@ -424,13 +432,18 @@ linear_kernel(const float* __restrict__ X, int ldx, int I, const float* __restri
 // LSTMCell pointwise (torch gate order i,f,g,o): c' = s(f) c + s(i) tanh(g), h' = s(o) tanh(c')
 // gates arrive as `parts` split-K partial sums [parts][N][4M]
 __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __restrict__ h,
-                                      float* __restrict__ c, int N, int M, int parts) {
+                                      float* __restrict__ c, int N, int M, int parts,
+                                      float* __restrict__ gsum_out /* [N][4M] summed gates or null */) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * M; i += gridDim.x * blockDim.x) {
     const int n = i / M, j = i % M;
     float gs[4] = {0.f, 0.f, 0.f, 0.f};
     for (int q = 0; q < parts; ++q) {
       const float* g = gates + ((size_t)q * N + n) * 4 * M;
       gs[0] += g[j]; gs[1] += g[M + j]; gs[2] += g[2 * M + j]; gs[3] += g[3 * M + j];
+    }
+    if (gsum_out) {
+      float* go = gsum_out + (size_t)n * 4 * M;
+      go[j] = gs[0]; go[M + j] = gs[1]; go[2 * M + j] = gs[2]; go[3 * M + j] = gs[3];
     }
     const float ig = sigmoid_f(gs[0]), fg = sigmoid_f(gs[1]), gg = tanhf(gs[2]), og = sigmoid_f(gs[3]);
     const float cn = fg * c[i] + ig * gg;
@@ -462,7 +475,7 @@ int launch_head(Plan* p, float* mu, float* logvar, float* h, float* c, cudaStrea
   {
     dim3 grid((M + 63) / 64, (N + 15) / 16);
     linear_kernel<1, 1><<<grid, 256, 0, st>>>(p->pool, Cr, Cr, p->mlp_w, p->mlp_b, nullptr, 0, 0, nullptr,
-                                              nullptr, p->xin, I, N, M, Cr, 0);
+                                              nullptr, p->xin, I, N, M, Cr, 0, p->tape_u);
     IOD_LAUNCH_CHECK(p);
   }
   {
@@ -472,7 +485,7 @@ int launch_head(Plan* p, float* mu, float* logvar, float* h, float* c, cudaStrea
                                               p->gates, 4 * M, N, 4 * M, kchunk, (size_t)N * 4 * M);
     IOD_LAUNCH_CHECK(p);
   }
-  lstm_pointwise_kernel<<<(N * M + 255) / 256, 256, 0, st>>>(p->gates, h, c, N, M, LSTM_KSPLIT);
+  lstm_pointwise_kernel<<<(N * M + 255) / 256, 256, 0, st>>>(p->gates, h, c, N, M, LSTM_KSPLIT, p->tape_gates);
   IOD_LAUNCH_CHECK(p);
   {  // both heads read the CELL state (iodine.py:488-492); delta reuses the gates buffer
     const int hk = ((M + LSTM_KSPLIT - 1) / LSTM_KSPLIT + 15) / 16 * 16;

@@ -18,9 +18,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int launch_assemble(Plan* p, const float* x, cudaStream_t st);
 int launch_kl(Plan* p, const float* mu, const float* logvar, cudaStream_t st);
-int launch_init_state(Plan* p, float* mu, float* lv, float* h, float* c, cudaStream_t st);
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -37,7 +35,7 @@ static size_t carve(Plan* p, char* base) {
   const size_t eb = act_elem_bytes(p);
   for (int l = 0; l < s.dec_layers; ++l) p->act[l] = take(BK * HW * C * eb);
   for (int i = 0; i < 2; ++i) {
-    const bool need = s.dec_layers > 1 || (i == 0 && tc_mode(p));
+    const bool need = s.dec_layers > 1 || i == 0;      // (gbuf[0] also holds dJ/d(pre-activation 0) of a training step)
     p->gbuf[i] = take(need ? BK * HW * C * eb : 1024);
   }
   // K-split: one buffer for all ranks' slots, rank-major as ncclAllGather fills it; this rank's decoder writes its
@@ -350,6 +348,12 @@ static int reduce_terms(Plan* p, float* terms, size_t count, cudaStream_t st) {
   return 0;
 }
 
+int plan_check_ready(Plan* p) { return check_ready(p); }
+int plan_decoder_forward(Plan* p, const float* mu, const float* lv, const float* eps, const float* z_in, cudaStream_t st) {
+  return decoder_forward(p, mu, lv, eps, z_in, st);
+}
+int plan_allreduce_sum(Plan* p, float* buf, size_t count, cudaStream_t st) { return reduce_terms(p, buf, count, st); }
+
 static int do_decode(Plan* p, const float* z, float* pred, float* mask, float* mean, cudaStream_t st,
                      uint8_t* amax = nullptr) {
   if (decoder_forward(p, nullptr, nullptr, nullptr, z, st)) return 1;
@@ -466,6 +470,7 @@ IODINE_API int iodine_plan_destroy(IodinePlan* plan) {
   cudaFree(p->init_logvar);
   tc_free(p);
   rtc_free(p);
+  train_free(p);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   for (int i = 0; i < Plan::N_GRAPHS; ++i)
     if (p->graph[i].exec) cudaGraphExecDestroy(p->graph[i].exec);

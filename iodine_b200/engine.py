@@ -120,6 +120,47 @@ class RefinementEngine:
             torch.cuda.current_stream().synchronize()   # sources may be freed afterwards
         self._keep = None
 
+    # ------------------------------------------------------------------ training
+    GRAD_KEYS = None
+
+    def _grad_struct(self, grads):
+        """IodineGrads over ``grads``: state_dict key -> fp32 CUDA tensor of the parameter's (engine) shape"""
+        g = _cabi.IodineGrads()
+        p = lambda k: grads[k].data_ptr()
+        for i in range(self.shape.dec_layers):
+            g.dec_w[i], g.dec_b[i] = p('decoder.mlc.layers.%d.weight' % i), p('decoder.mlc.layers.%d.bias' % i)
+        g.dec_out_w, g.dec_out_b = p('decoder.conv.weight'), p('decoder.conv.bias')
+        for i in range(self.shape.ref_layers):
+            g.ref_w[i], g.ref_b[i] = p('refine.mlc.layers.%d.weight' % i), p('refine.mlc.layers.%d.bias' % i)
+        g.mlp_w, g.mlp_b = p('refine.mlp.layers.0.weight'), p('refine.mlp.layers.0.bias')
+        g.lstm_w_ih, g.lstm_w_hh = p('refine.lstm.weight_ih'), p('refine.lstm.weight_hh')
+        g.lstm_b_ih, g.lstm_b_hh = p('refine.lstm.bias_ih'), p('refine.lstm.bias_hh')
+        g.mean_w, g.mean_b = p('refine.mean_update.weight'), p('refine.mean_update.bias')
+        g.logvar_w, g.logvar_b = p('refine.logvar_update.weight'), p('refine.logvar_update.bias')
+        g.init_mean, g.init_logvar = p('posterior.init_mean'), p('posterior.init_logvar')
+        return g
+
+    def train_step(self, x, eps, grads, global_batch=0):
+        """IODINE.forward + loss.backward() (reference iodine.py:115-158, lib/engine/train.py:60-65) in one library
+        call.  ``grads``: state_dict key -> preallocated fp32 CUDA tensor (engine shapes: refine layer 0 with all 17
+        input channels), overwritten with dLoss/dParameter.  Returns (loss 0-dim, elbo_terms [T+1,2])."""
+        B, K, L, T = self.B, self.K, self.L, self.T
+        x = self._f32(x, (B, 3, self.H, self.W))
+        eps = self._f32(eps, (T + 1, B, K, L))
+        with torch.cuda.device(self.device):
+            if getattr(self, '_train_ws', None) is None:
+                need = C.c_size_t()
+                _cabi.check(self.lib.iodine_plan_train_workspace_bytes(self._plan, C.byref(need)))
+                self._train_ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
+                base = (self._train_ws.data_ptr() + 1023) // 1024 * 1024
+                _cabi.check(self.lib.iodine_plan_set_train_workspace(self._plan, C.c_void_p(base), need.value))
+                self.train_workspace_bytes = need.value
+            loss, terms = self._new(1), self._new(T + 1, 2)
+            gs = self._grad_struct(grads)
+            _cabi.check(self.lib.iodine_train_step(self._plan, _ptr(x), _ptr(eps), int(global_batch), C.byref(gs),
+                                                   _ptr(loss), _ptr(terms), _stream()))
+        return loss[0], terms
+
     # ------------------------------------------------------------------ helpers
     def _f32(self, t, shape=None):
         t = t.to(device=self.device, dtype=torch.float32).contiguous()

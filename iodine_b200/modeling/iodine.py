@@ -83,6 +83,21 @@ ALL_ENCODINGS = ('posterior', 'grad_post', 'image', 'means', 'mask', 'mask_logit
                  'leave_one_out_likelihood', 'coordinate')
 
 
+class _TrainStep(torch.autograd.Function):
+    """Graph node of ``IODINE.forward``: the library has already produced dLoss/dParameter for every parameter when
+    the loss is returned; backward scales them by the incoming gradient (``loss.mean()`` of a 0-dim loss: 1)."""
+
+    @staticmethod
+    def forward(ctx, model, x, eps, names, *params):
+        loss, grads = model._train_step(x, eps)
+        ctx.grads = [grads[k] for k in names]
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        return (None, None, None, None) + tuple(gout * g for g in ctx.grads)
+
+
 class IODINE(nn.Module):
     def __init__(self, ARCH, precision='fp32'):
         nn.Module.__init__(self)
@@ -345,36 +360,71 @@ class IODINE(nn.Module):
         B = self._mean_batch(B or self.z.shape[0])
         return (t[:, 0] - t[:, 1]) / B
 
-    @torch.no_grad()
     def forward(self, x, eps=None):
-        """Training objective VALUE (reference iodine.py:115-158): ``-sum_i (i+1)/(T+1) * elbo_i`` over the T
-        in-loop ELBOs and the final one (151-153, 158), as a 0-dim tensor.
+        """Training objective (reference iodine.py:115-158): ``-sum_i (i+1)/(T+1) * elbo_i`` over the T in-loop ELBOs
+        and the final one (151-153, 158), as a 0-dim tensor.
 
-        The value comes from the native inference kernels; it carries NO autograd graph -- back-propagation
-        through the refinement loop (decoder / refiner weight gradients, LSTM backward) is SURVEY.md 8f rank 1 and
-        not implemented, so ``loss.backward()`` raises torch's usual "does not require grad" error instead of
-        silently training nothing."""
+        With autograd enabled the tensor carries a graph node whose backward hands every parameter its gradient, so
+        the reference's training loop (``lib/engine/train.py:60-65``: ``loss = model(data); loss = loss.mean();
+        optimizer.zero_grad(); loss.backward(); optimizer.step()``) runs unchanged.  Loss AND gradients are computed
+        inside this call by the library's training step (``iodine_train_step``, csrc/train.cu: hand-written
+        weight-gradient / LSTM-backward kernels, no autograd through the loop); ``backward()`` only scales and
+        delivers them.  Under ``torch.no_grad()`` the value comes from the inference kernels alone."""
         x = self._require_cuda(x)
         B, T = x.shape[0], self.n_iters
         eps = self._noise(B, eps)
-        self.encode(x, eps=eps)                                   # T in-loop ELBOs + final posterior
-        elbos = list(self.elbo_per_step(B))
-        final = 0
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self._slot_split is not None:
+                raise _cabi.IodineError('training is not available on a K-split replica')
+            names = [k for k, _ in self.named_parameters()]
+            return _TrainStep.apply(self, x, eps, names, *[p for _, p in self.named_parameters()])
+        with torch.no_grad():
+            self.encode(x, eps=eps)                                   # T in-loop ELBOs + final posterior
+            elbos = list(self.elbo_per_step(B))
+            final = 0
+            for b0, b1 in self._spans(B):
+                eng = self._engine(b1 - b0)
+                final = final + eng.elbo_terms(x[b0:b1], eps[T, b0:b1], self.posterior.mean[b0:b1],
+                                               self.posterior.logvar[b0:b1])
+                if b0 == 0:
+                    self._log_last_elbo(x, eng)
+            nb = self._mean_batch(B)
+            elbos.append((final[0] - final[1]) / nb)
+            logger.update(kl=final[1] / nb, likelihood=final[0] / nb)          # the last elbo() call is the final one
+            loss = 0
+            for i, e in enumerate(elbos):
+                loss = loss + (i + 1) / len(elbos) * e
+            logger.update(init_mean=self.posterior.init_mean.detach().mean(),
+                          init_logvar=self.posterior.init_logvar.detach().mean())
+            return -loss
+
+    @torch.no_grad()
+    def _train_step(self, x, eps):
+        """loss (0-dim) and {state_dict key: dLoss/dParameter} through ``iodine_train_step``; the batch is chunked like
+        the inference calls (gradients and loss are additive over images once every mean divides by the full batch)."""
+        B = x.shape[0]
+        nb = self._mean_batch(B)
+        sd = self._engine_state_dict()
+        total, loss, terms = None, 0, 0
         for b0, b1 in self._spans(B):
             eng = self._engine(b1 - b0)
-            final = final + eng.elbo_terms(x[b0:b1], eps[T, b0:b1], self.posterior.mean[b0:b1],
-                                           self.posterior.logvar[b0:b1])
+            grads = {k: torch.empty_like(v, dtype=torch.float32, device=self._device()) for k, v in sd.items()}
+            l, t = eng.train_step(x[b0:b1], eps[:, b0:b1], grads, global_batch=nb)
             if b0 == 0:
                 self._log_last_elbo(x, eng)
-        nb = self._mean_batch(B)
-        elbos.append((final[0] - final[1]) / nb)
-        logger.update(kl=final[1] / nb, likelihood=final[0] / nb)          # the last elbo() call is the final one
-        loss = 0
-        for i, e in enumerate(elbos):
-            loss = loss + (i + 1) / len(elbos) * e
+            loss, terms = loss + l, terms + t
+            if total is None:
+                total = grads
+            else:
+                for k in total:
+                    total[k] += grads[k]
+        if len(self._enc_channels) != 17:                             # partial ARCH.ENCODING: the selected channels
+            total['refine.mlc.layers.0.weight'] = total['refine.mlc.layers.0.weight'][:, self._enc_channels].contiguous()
+        self.elbo_terms = terms
+        logger.update(kl=terms[-1, 1] / nb, likelihood=terms[-1, 0] / nb)       # the last elbo() call is the final one
         logger.update(init_mean=self.posterior.init_mean.detach().mean(),
                       init_logvar=self.posterior.init_logvar.detach().mean())
-        return -loss
+        return loss, total
 
     # ------------------------------------------------------------------ side channel (A9)
     # The reference writes to the logger inside EVERY elbo() call (iodine.py:225-239), each write replacing the
