@@ -579,12 +579,99 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+# =========================================================================== training mode
+def run_train(args):
+    """`--mode train`: wall time per training batch -- the loop body of lib/engine/train.py:58-65 (`data.to(device)`,
+    `loss = model(data)`, `loss.mean()`, `optimizer.zero_grad()`, `loss.backward()`, `optimizer.step()`) -- beside the
+    only throughput figure the reference publishes: 1.7 s/batch at this configuration on 4 GPUs (log.md:3)."""
+    out_stream = _quiet_stdout()
+    import torch.distributed as dist
+    from iodine_b200.modeling.iodine import IODINE
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=dev)
+    cfg, arch, B, precision = resolve_config(args)
+    K, T, L, S = arch.SLOTS, arch.ITERS, arch.DIM_LATENT, arch.IMG_SIZE
+    torch.manual_seed(0)
+    model = IODINE(arch, precision=precision).to(dev)
+    model.max_images_per_call = B
+    if world > 1:
+        from iodine_b200.parallel import SlotShard
+        shard = SlotShard(model)                       # installs the communicator: gradients are all-reduced in the library
+        model.global_batch = B * world
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)                 # configs/clevr6_prop.yaml:19
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.rand(B, 3, S, S, generator=g).pin_memory()
+    eps = torch.randn(T + 1, B, K, L, generator=torch.Generator().manual_seed(123 + rank)).to(dev)
+
+    def step():
+        data = x_host.to(dev, non_blocking=True)
+        loss = model(data, eps=eps)
+        loss = loss.mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(2, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    eng = model.state_for_debug(B)
+    n0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    losses = [step() for _ in range(args.steps)]
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([wall, dev_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        wall, dev_s = tt.tolist()
+    if rank == 0:
+        f_dec, _ = flops_per_unit(arch)
+        # forward + data-gradient + weight-gradient of the decoder for the T+1 ELBO evaluations, refiner fwd + bwd
+        flop = B * K * ((T + 1) * 3 * f_dec + T * 3 * refine_flops_per_unit(arch))
+        line = {
+            'mode': 'train', 'metric': 'training wall time per batch (forward + backward + Adam), CLEVR6 128x128 K=7 T=5',
+            'value': wall / args.steps, 'unit': 's/batch', 'n_gpus': world, 'steps': args.steps, 'warmup': max(2, args.warmup),
+            'ms_per_step': 1e3 * wall / args.steps, 'device_ms_per_step': 1e3 * dev_s / args.steps,
+            'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': (wall / args.steps) / 1.7,
+            'baseline_note': 'BASELINE.md: 1.7 s/batch, batch 32, "4 GPUs" of unstated model, nn.DataParallel (log.md:3); here batch '
+                             '%d per GPU x %d GPU(s)' % (B, world),
+            'dtype': {'fp32': 'f32', 'tf32': 'f32 storage, tf32 tensor-core operands (decoder fwd/dgrad); weight gradients fp32 FFMA'}.get(
+                precision, '%s operands (decoder fwd/dgrad); weight gradients fp32 FFMA' % precision),
+            'data': 'synthetic',
+            'config': config_block(cfg, arch, B, world, precision),
+            'refinement_steps_per_s_training': world * B * K * T * args.steps / wall,
+            'gpu_launches': int(eng.launch_count() - n0),
+            'tflops_necessary': flop * args.steps / dev_s / 1e12,
+            'loss_first_last': [float(losses[0]), float(losses[-1])],
+            'train_workspace_gb': getattr(eng, 'train_workspace_bytes', 0) / 1e9,
+        }
+        out_stream.write(json.dumps(line) + '\n')
+        out_stream.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help='infer (default): the refinement loop, BASELINE.json\'s metric; train: s/batch of the training step')
     ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS),
                     help='BASELINE.json configuration, 1-based (default 2 = configs[1], the one the metric is quoted on)')
     ap.add_argument('--batch', type=int, default=0, help='images per GPU (default: the configuration\'s)')
@@ -614,6 +701,8 @@ def main():
                '--nproc-per-node', str(args.gpus), '--master-addr', '127.0.0.1',
                '--master-port', os.environ.get('MASTER_PORT', '29517'), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.mode == 'train':
+        return run_train(args)
     run_native(args)
 
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT_DIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(OUT_DIR, 'libiodine_b200.so')
-SOURCES = ['plan.cu', 'conv_f32.cu', 'mixture.cu', 'head.cu', 'conv_tc.cu', 'refine_tc.cu', 'ari.cu', 'train.cu']
+SOURCES = ['plan.cu', 'conv_f32.cu', 'mixture.cu', 'head.cu', 'conv_tc.cu', 'refine_tc.cu', 'ari.cu', 'train.cu', 'wgrad_tc.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']

@@ -698,8 +698,10 @@ static int decoder_backward_train(Plan* p, TrainState* ts, float coef, cudaStrea
   for (int l = n - 1; l >= 1; --l) {
     // gbuf[cur] = dJ/d(pre-activation l)
     const TView gv = dec_view(p, p->gbuf[cur]);
-    if (launch_conv_wgrad(p, dec_view(p, p->act[l - 1]), gv, ts->gflat + ts->o_dec_w[l], coef, p->BK, s.H, s.W, s.H, s.W, C, C, KS,
-                          1, st))
+    if (wgrad_tc_supported(p)) {
+      if (launch_wgrad_tc(p, p->act[l - 1], p->gbuf[cur], ts->gflat + ts->o_dec_w[l], coef, st)) return 1;
+    } else if (launch_conv_wgrad(p, dec_view(p, p->act[l - 1]), gv, ts->gflat + ts->o_dec_w[l], coef, p->BK, s.H, s.W, s.H, s.W, C,
+                                 C, KS, 1, st))
       return 1;
     if (launch_chan_sum(p, gv, ts->gflat + ts->o_dec_b[l], coef, p->BK, p->HW, st)) return 1;
     if (tc_mode(p)) {

@@ -112,3 +112,47 @@ def test_two_rank_nccl_in_library_allreduce_matches_single_process(B, tmp_path):
         assert rel_err(o['elbo'], elbo) < 1e-5, r
         assert rel_err(o['elbo_local'], elbo) < 1e-5, r
     assert torch.equal(outs[0]['terms'], outs[1]['terms'])      # all-reduced: identical everywhere
+
+
+# --------------------------------------------------------------------------- training: ONE flat gradient all-reduce
+def _train_worker(rank, world, port, B, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        arch = A.arch_by_name('tiny')
+        model = seeded_model(arch, 3.0).to(dev)
+        x, eps = _inputs(arch, B)
+        sh = SlotShard(model)                       # installs the communicator on the model's engines
+        b0, b1 = shard_bounds(B, world, rank)
+        model.global_batch = B
+        loss = model(x[b0:b1].to(dev), eps=eps[:, b0:b1].to(dev))
+        loss.mean().backward()
+        torch.cuda.synchronize()
+        res = {'loss': loss.detach().cpu(), 'grads': {k: p.grad.cpu() for k, p in model.named_parameters()}}
+        torch.save(res, os.path.join(out_dir, 'r%d.pt' % rank))
+        del sh
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('B', [4, 3])
+def test_two_rank_training_step_all_reduces_the_gradients(B, tmp_path):
+    """slot-shard training (SURVEY.md 8e "Training"): every rank ends with the FULL-batch loss and gradients -- what
+    DataParallel's gather + reduce-to-GPU-0 gives the reference (lib/engine/train.py:60-65)"""
+    world = 2
+    mp.spawn(_train_worker, args=(world, _free_port(), B, str(tmp_path)), nprocs=world, join=True)
+    arch = A.arch_by_name('tiny')
+    model = seeded_model(arch, 3.0).to(DEV)
+    x, eps = _inputs(arch, B)
+    loss = model(x.to(DEV), eps=eps.to(DEV))
+    loss.mean().backward()
+    outs = [torch.load(os.path.join(str(tmp_path), 'r%d.pt' % r)) for r in range(world)]
+    for r, o in enumerate(outs):
+        assert rel_err(o['loss'], loss.detach().cpu()) < 1e-5, r
+        for k, p in model.named_parameters():
+            assert rel_err(o['grads'][k], p.grad.cpu()) < 2e-4, (r, k)
+    for k in outs[0]['grads']:
+        assert torch.equal(outs[0]['grads'][k], outs[1]['grads'][k]), k      # all-reduced: identical everywhere

@@ -225,8 +225,11 @@ def test_forward_loss_value_against_oracle(name):
     g, arch, B, sd, model = golden_state_dict(name)
     model.to(DEV)
     x, eps = t(g['x']), t(g['eps'])
-    loss = model(x.to(DEV), eps=eps.to(DEV))
+    with torch.no_grad():                             # the value-only path (inference kernels)
+        loss = model(x.to(DEV), eps=eps.to(DEV))
     assert loss.dim() == 0 and not loss.requires_grad
+    loss_t = model(x.to(DEV), eps=eps.to(DEV))        # the training step (tests/test_gpu_train.py checks its gradients)
+    assert loss_t.dim() == 0 and loss_t.requires_grad and abs(loss_t.item() - loss.item()) < 1e-5 * abs(loss.item())
     tr = S.encode_trace(sd, arch, x, eps)
     elbos = [s['elbo'] for s in tr['steps']]
     mean, logits, _, _ = S.decoder_forward(sd, tr['z'], arch.IMG_SIZE)       # final elbo(x): z = sample(eps[T])

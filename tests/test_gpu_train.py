@@ -110,3 +110,34 @@ def test_no_grad_forward_still_returns_the_value():
     loss = model(x, eps=eps)
     assert not v.requires_grad and loss.requires_grad
     assert abs(v.item() - loss.item()) <= 1e-5 * abs(v.item())
+
+
+# --------------------------------------------------------------------------- CLEVR6 layer sizes (128x128, C = 64)
+@pytest.mark.parametrize('prec', ['fp32', 'tf32', 'fp16', 'bf16'])
+def test_training_step_at_clevr6_size_against_reference_golden(prec):
+    """the shapes bench.py --mode train times; 16-bit modes run the tcgen05 weight-gradient kernel (csrc/wgrad_tc.cu)
+    for the C -> C layers.  Fixture: sampled entries + sums of the unmodified reference's gradients
+    (oracle/make_train_golden_size.py)."""
+    from oracle import make_golden as MG
+    from oracle import make_golden_size as MS
+    from oracle import make_train_golden_size as TS
+    g = dict(np.load(os.path.join(GOLDEN, TS.NAME + '.npz')))
+    arch, x, eps = TS.case_inputs()
+    assert abs(x.double().sum().item() - float(g['x_checksum'])) <= 1e-9 * abs(float(g['x_checksum']))
+    model = seeded_model(arch, TS.SHARPEN, precision=prec)
+    cs = MG.weights_checksum(model.state_dict())
+    assert abs(cs - float(g['weights_checksum'])) <= 1e-9 * abs(cs)
+    loss, grads = _step(model, x, eps)
+    bar = {'fp32': 2e-3, 'tf32': 2e-2, 'fp16': 2e-2, 'bf16': 6e-2}[prec]
+    assert abs(loss.item() - float(g['loss'])) <= (1e-4 if prec == 'fp32' else 3e-3) * abs(float(g['loss']))
+    errs = {}
+    for k in model.state_dict():
+        flat = grads[k].detach().reshape(-1).double().cpu()
+        want = torch.from_numpy(g['grad_s/' + k]).double()
+        gmax = float(g['grad_max/' + k])
+        e_s = ((flat[MS.sample_index(flat.numel(), TS.NS)] - want).abs().max() / gmax).item()
+        e_sum = abs(flat.sum().item() - float(g['grad_sum/' + k])) / float(g['grad_abs/' + k])
+        errs[k] = max(e_s, e_sum)
+    print(prec, {k: '%.1e' % v for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < bar}
+    assert not bad, bad
