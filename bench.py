@@ -628,7 +628,7 @@ def run_train(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    losses = [step() for _ in range(args.steps)]
+    losses = [step().detach() for _ in range(args.steps)]
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -648,14 +648,16 @@ def run_train(args):
             'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': (wall / args.steps) / 1.7,
             'baseline_note': 'BASELINE.md: 1.7 s/batch, batch 32, "4 GPUs" of unstated model, nn.DataParallel (log.md:3); here batch '
                              '%d per GPU x %d GPU(s)' % (B, world),
-            'dtype': {'fp32': 'f32', 'tf32': 'f32 storage, tf32 tensor-core operands (decoder fwd/dgrad); weight gradients fp32 FFMA'}.get(
-                precision, '%s operands (decoder fwd/dgrad); weight gradients fp32 FFMA' % precision),
+            'dtype': {'fp32': 'f32 (FFMA kernels throughout)',
+                      'tf32': 'f32 storage; decoder fwd/dgrad tcgen05 kind::tf32, decoder weight gradients tcgen05 kind::f16 on fp16 '
+                              'copies of the operands (MN-major), refiner fwd/bwd fp32 FFMA; f32 accumulate everywhere'}.get(
+                precision, '%s operands for the decoder fwd/dgrad/wgrad (tcgen05), refiner fwd/bwd fp32 FFMA; f32 accumulate' % precision),
             'data': 'synthetic',
             'config': config_block(cfg, arch, B, world, precision),
             'refinement_steps_per_s_training': world * B * K * T * args.steps / wall,
             'gpu_launches': int(eng.launch_count() - n0),
             'tflops_necessary': flop * args.steps / dev_s / 1e12,
-            'loss_first_last': [float(losses[0]), float(losses[-1])],
+            'loss_first_last': [losses[0].item(), losses[-1].item()],
             'train_workspace_gb': getattr(eng, 'train_workspace_bytes', 0) / 1e9,
         }
         out_stream.write(json.dumps(line) + '\n')

@@ -252,10 +252,12 @@ int tc_export_seed(Plan* p, const void* seed8, float* dst, cudaStream_t st);
 // sums of the last data-gradient (its inverse)
 int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st);
 int tc_launch_class_sum(Plan* p, const void* g, cudaStream_t st);
-int tc_rs_worklist(const Plan* p, const int4** itab, const int32_t** coff, int* grid, const void** zero_row);
-// wgrad_tc.cu: tcgen05 weight gradient of a C -> C 3x3 layer (16-bit modes, C = 64, W = 128)
+int tc_rs_worklist(const Plan* p, int which, const int4** itab, const int32_t** coff, int* grid, const void** zero_row);
+// wgrad_tc.cu: tcgen05 weight gradients of the decoder's 3x3 layers (tensor-core modes, C = 64, W = 128)
 int wgrad_tc_supported(const Plan* p);
+int wgrad_to_h16(Plan* p, const void* src, void* dst, int channels, cudaStream_t st);   // tf32 planes -> fp16 planes
 int launch_wgrad_tc(Plan* p, const void* act_prev, const void* g, float* dw, float coef, cudaStream_t st);
+int launch_wgrad_tc_out4(Plan* p, const void* act_last, const void* seed8, float* dw, float coef, cudaStream_t st);
 int tc_dsum_fused(const Plan* p);   // 1: tc_launch_conv(..., G) of the last data-gradient layer produces the class sums itself
 
 // ------------------------------------------------------------------ refine_tc.cu (tcgen05 refinement encoder)

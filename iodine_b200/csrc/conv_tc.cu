@@ -1519,14 +1519,14 @@ int tc_launch_dgrad_in4(Plan* p, const float* seed8, const void* act_prev, void*
   return tc_launch_i4(p, q, st->g_in4.smem, st_);
 }
 
-// the row-streaming work list [0] (one CTA per range, cut at image boundaries) for other row-streaming kernels
+// the row-streaming work lists ([0]: one CTA per range, [1]: nsplit_cc CTAs per range; cut at image boundaries) for other row-streaming kernels
 // (wgrad_tc.cu); returns 0 when this plan has none
-int tc_rs_worklist(const Plan* p, const int4** itab, const int32_t** coff, int* grid, const void** zero_row) {
+int tc_rs_worklist(const Plan* p, int which, const int4** itab, const int32_t** coff, int* grid, const void** zero_row) {
   const TcState* st = reinterpret_cast<const TcState*>(p->tc);
-  if (!st || !st->rs || !st->itab[0] || p->s.W != 128) return 0;
-  if (itab) *itab = st->itab[0];
-  if (coff) *coff = st->coff[0];
-  if (grid) *grid = st->rs_grid[0];
+  if (!st || !st->rs || !st->itab[which] || p->s.W != 128) return 0;
+  if (itab) *itab = st->itab[which];
+  if (coff) *coff = st->coff[which];
+  if (grid) *grid = st->rs_grid[which];
   if (zero_row) *zero_row = st->zero_row;
   return 1;
 }

@@ -39,6 +39,7 @@ struct TrainState {
   float* dh[2] = {nullptr, nullptr};
   float* dc[2] = {nullptr, nullptr};
   float* rg[2] = {nullptr, nullptr};               // refiner conv gradients, ping-pong
+  void *h16_act = nullptr, *h16_g = nullptr;       // IODINE_TF32: fp16 copies of the weight-gradient operands
   float* gflat = nullptr;                          // every parameter gradient + loss + ELBO table
   size_t n_flat = 0;
   // offsets (floats) into gflat, state_dict order
@@ -91,6 +92,10 @@ static size_t train_carve(Plan* p, TrainState* ts, char* base) {
   ts->dx = take(BK * M);
   ts->dpool = take(BK * Cr);
   for (int i = 0; i < 2; ++i) { ts->dh[i] = take(BK * M); ts->dc[i] = take(BK * M); ts->rg[i] = take(biggest); }
+  if (tf_mode(p) && wgrad_tc_supported(p)) {
+    ts->h16_act = take(BK * HW * C / 2);
+    ts->h16_g = take(BK * HW * C / 2);
+  }
   // flat gradient buffer
   size_t o = 0;
   const size_t kk = (size_t)s.dec_k * s.dec_k, rkk = (size_t)s.ref_k * s.ref_k;
@@ -126,7 +131,7 @@ struct TView {
   int lay;        // Lay
   int f16;        // LAY_P16: 1 = IEEE half, 0 = bfloat16
   int C;          // channels (LAY_NHWC: valid channels)
-  int pitch;      // LAY_NHWC: floats per pixel (multiple of 4, >= C; padding holds zeros)
+  int pitch;      // LAY_NHWC: floats per pixel (multiple of 4, >= C; padding holds zeros); planar: the REAL channels (<= C)
 };
 // four channels c0..c0+3 (c0 % 4 == 0) of pixel `pix` of slot-image n; channels >= C read as zero
 __device__ __forceinline__ float4 load4(const TView& v, int n, int HW, int pix, int c0) {
@@ -355,7 +360,52 @@ chan_sum_kernel(TView g, float* __restrict__ db, float coef, int N, int HW, int 
   }
 }
 
+// the same for chunk-planar tensors: block = (pixel share, plane); a thread reads whole 16-byte plane values
+// (consecutive threads = consecutive pixels), 8 (16-bit) or 4 (tf32) running sums
+__global__ void __launch_bounds__(256)
+plane_sum_kernel(TView g, float* __restrict__ db, float coef, int N, int HW, int px_per_block, int cmax) {
+  __shared__ float red[8][8];
+  const int PW = g.lay == LAY_PTF ? 4 : 8, planes = g.C / PW, k = blockIdx.y;
+  const long long total = (long long)N * HW;
+  const long long p_lo = (long long)blockIdx.x * px_per_block;
+  const long long p_hi = (p_lo + px_per_block < total) ? p_lo + px_per_block : total;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const uint4* base = reinterpret_cast<const uint4*>(g.base);
+  for (long long ip = p_lo + threadIdx.x; ip < p_hi; ip += 256) {
+    const long long n = ip / HW;
+    const uint4 v = __ldg(base + (n * planes + k) * HW + (ip - n * HW));
+    if (g.lay == LAY_PTF) {
+      s[0] += __uint_as_float(v.x); s[1] += __uint_as_float(v.y); s[2] += __uint_as_float(v.z); s[3] += __uint_as_float(v.w);
+    } else {
+      const float2 a = unpack_h2(v.x, g.f16), b = unpack_h2(v.y, g.f16), c = unpack_h2(v.z, g.f16), d = unpack_h2(v.w, g.f16);
+      s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y; s[6] += d.x; s[7] += d.y;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = warp_sum(s[e]);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x >> 5][e] = s[e];
+  __syncthreads();
+  if (threadIdx.x < PW && k * PW + threadIdx.x < cmax) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(db + k * PW + threadIdx.x, coef * t);
+  }
+}
+
 static int launch_chan_sum(Plan* p, const TView& g, float* db, float coef, int N, int HW, cudaStream_t st) {
+  if (g.lay != LAY_NHWC) {
+    const int planes = g.C / (g.lay == LAY_PTF ? 4 : 8);
+    const long long total = (long long)N * HW;
+    long long nb = (4LL * p->num_sms + planes - 1) / planes;
+    long long per = (total + nb - 1) / nb;
+    if (per < 1024) per = 1024;
+    dim3 grid((unsigned)((total + per - 1) / per), planes);
+    plane_sum_kernel<<<grid, 256, 0, st>>>(g, db, coef, N, HW, (int)per, g.pitch);
+    IOD_LAUNCH_CHECK(p);
+    return 0;
+  }
   const long long total = (long long)N * HW;
   long long per = (total + 2LL * p->num_sms - 1) / (2LL * p->num_sms);
   if (per < 64) per = 64;
@@ -648,6 +698,84 @@ refine_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ wp, c
   }
 }
 
+// The same as an implicit GEMM (the gather kernel above runs at ~5 TFLOP/s).  Input pixels are split into the S*S
+// parity classes of (iy, ix): within a class every pixel receives the same taps, so a class is a dense GEMM
+// [pixels of the class] x [taps * co] x [ci].  Block = 64 pixels x 64 ci, 4 x 4 register tiles, 16 co per round.
+__global__ void __launch_bounds__(256)
+refine_dgrad_gemm_kernel(const float* __restrict__ g, const float* __restrict__ wp, const float* __restrict__ actp,
+                         float* __restrict__ gin, int N, int Hin, int Win, int Hout, int Wout, int C, int KS, int S) {
+  __shared__ __align__(16) float sa[16][64 + 4];
+  __shared__ __align__(16) float sw[16][64 + 4];
+  const int P = KS / 2;
+  const int cls = blockIdx.y, py = cls / S, px = cls - py * S;
+  const int Hc = (Hin - py + S - 1) / S, Wc = (Win - px + S - 1) / S;
+  const long long total = (long long)N * Hc * Wc;
+  const long long m0 = (long long)blockIdx.x * 64;
+  if (m0 >= total) return;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // loader role: pixel lm of the tile, 4 consecutive co of the 16-wide round
+  const int lm = threadIdx.x >> 2, lsub = (threadIdx.x & 3) * 4;
+  const long long lpix = m0 + lm;
+  int ln = 0, liy = 0, lix = 0;
+  const bool lvalid = lpix < total;
+  if (lvalid) {
+    ln = (int)(lpix / ((long long)Hc * Wc));
+    const int r = (int)(lpix - (long long)ln * Hc * Wc);
+    liy = (r / Wc) * S + py;
+    lix = (r % Wc) * S + px;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int dy = 0; dy < KS; ++dy) {
+    if ((py + P - dy) % S != 0) continue;              // (py + P - dy may be negative: C++ % keeps the sign, 0 stays 0)
+    for (int dx = 0; dx < KS; ++dx) {
+      if ((px + P - dx) % S != 0) continue;
+      const int ty_ = liy + P - dy, tx_ = lix + P - dx;
+      const int oy = ty_ / S, ox = tx_ / S;
+      const bool inside = lvalid && ty_ >= 0 && tx_ >= 0 && oy < Hout && ox < Wout;
+      const float* grow = g + (((size_t)ln * Hout + (inside ? oy : 0)) * Wout + (inside ? ox : 0)) * C;
+      const float* wrow = wp + ((size_t)(dy * KS + dx) * C + lm) * C;      // W[tap][ci = lm][co]
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        const float4 av = inside ? __ldg(reinterpret_cast<const float4*>(grow + c0 + lsub)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 wv = (lm < C) ? __ldg(reinterpret_cast<const float4*>(wrow + c0 + lsub)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        sa[lsub + 0][lm] = av.x; sa[lsub + 1][lm] = av.y; sa[lsub + 2][lm] = av.z; sa[lsub + 3][lm] = av.w;
+        sw[lsub + 0][lm] = wv.x; sw[lsub + 1][lm] = wv.y; sw[lsub + 2][lm] = wv.z; sw[lsub + 3][lm] = wv.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          const float4 a = *reinterpret_cast<const float4*>(&sa[kk][ty * 4]);
+          const float4 b = *reinterpret_cast<const float4*>(&sw[kk][tx * 4]);
+          const float av4[4] = {a.x, a.y, a.z, a.w}, bv4[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av4[i], bv4[j], acc[i][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long pix = m0 + ty * 4 + i;
+    if (pix >= total) continue;
+    const int n = (int)(pix / ((long long)Hc * Wc));
+    const int r = (int)(pix - (long long)n * Hc * Wc);
+    const int iy = (r / Wc) * S + py, ix = (r % Wc) * S + px;
+    const size_t o = (((size_t)n * Hin + iy) * Win + ix) * C + tx * 4;
+    if (tx * 4 < C) {
+      const float4 a = *reinterpret_cast<const float4*>(actp + o);
+      float4 out;
+      out.x = acc[i][0] * elu_grad_from_act(a.x); out.y = acc[i][1] * elu_grad_from_act(a.y);
+      out.z = acc[i][2] * elu_grad_from_act(a.z); out.w = acc[i][3] * elu_grad_from_act(a.w);
+      *reinterpret_cast<float4*>(gin + o) = out;
+    }
+  }
+}
+
 // loss = -sum_i (i+1)/(T+1) * (ll_i - kl_i) / Bg   (iodine.py:149-158), from the [T+1][2] table of batch sums
 __global__ void loss_kernel(const float* __restrict__ terms, float* __restrict__ loss, int T, float inv_bg) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -686,8 +814,19 @@ static int decoder_backward_train(Plan* p, TrainState* ts, float coef, cudaStrea
   IOD_CHECK_CUDA(cudaMemsetAsync(ts->Gy, 0, gsz, st));
   const int seed_half = (tc_mode(p) && !tf_mode(p)) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0;
   // decoder.conv (C -> 4): weight + bias gradient from the seeds, then its data-gradient
-  if (launch_out4_wgrad(p, dec_view(p, p->act[n - 1]), p->seed4, seed_half, ts->gflat + ts->o_out_w, ts->gflat + ts->o_out_b,
-                        coef, st))
+  const bool wtc = wgrad_tc_supported(p) != 0, tf = tf_mode(p);
+  if (wtc) {
+    const void *a16 = p->act[n - 1], *s16 = p->seed4;
+    if (tf) {                                        // fp16 copies of the operands (wgrad_tc.cu)
+      if (wgrad_to_h16(p, p->act[n - 1], ts->h16_act, C, st) || wgrad_to_h16(p, p->seed4, ts->h16_g, 4, st)) return 1;
+      a16 = ts->h16_act; s16 = ts->h16_g;
+    }
+    if (launch_wgrad_tc_out4(p, a16, s16, ts->gflat + ts->o_out_w, coef, st)) return 1;
+    TView sv;                                        // the seed: one 16-bit plane of 8 channels, 4 of them real
+    sv.base = s16; sv.lay = LAY_P16; sv.f16 = s.precision != IODINE_BF16; sv.C = 8; sv.pitch = 4;
+    if (launch_chan_sum(p, sv, ts->gflat + ts->o_out_b, coef, p->BK, p->HW, st)) return 1;
+  } else if (launch_out4_wgrad(p, dec_view(p, p->act[n - 1]), p->seed4, seed_half, ts->gflat + ts->o_out_w,
+                               ts->gflat + ts->o_out_b, coef, st))
     return 1;
   if (tc_mode(p)) {
     if (tc_launch_dgrad_in4(p, p->seed4, p->act[n - 1], p->gbuf[0], st)) return 1;
@@ -698,8 +837,13 @@ static int decoder_backward_train(Plan* p, TrainState* ts, float coef, cudaStrea
   for (int l = n - 1; l >= 1; --l) {
     // gbuf[cur] = dJ/d(pre-activation l)
     const TView gv = dec_view(p, p->gbuf[cur]);
-    if (wgrad_tc_supported(p)) {
-      if (launch_wgrad_tc(p, p->act[l - 1], p->gbuf[cur], ts->gflat + ts->o_dec_w[l], coef, st)) return 1;
+    if (wtc) {
+      const void *a16 = p->act[l - 1], *g16 = p->gbuf[cur];
+      if (tf) {
+        if (wgrad_to_h16(p, p->act[l - 1], ts->h16_act, C, st) || wgrad_to_h16(p, p->gbuf[cur], ts->h16_g, C, st)) return 1;
+        a16 = ts->h16_act; g16 = ts->h16_g;
+      }
+      if (launch_wgrad_tc(p, a16, g16, ts->gflat + ts->o_dec_w[l], coef, st)) return 1;
     } else if (launch_conv_wgrad(p, dec_view(p, p->act[l - 1]), gv, ts->gflat + ts->o_dec_w[l], coef, p->BK, s.H, s.W, s.H, s.W, C,
                                  C, KS, 1, st))
       return 1;
@@ -779,10 +923,19 @@ static int refiner_backward(Plan* p, TrainState* ts, int t, float alpha, int cur
       return 1;
     if (launch_chan_sum(p, gv, gf + ts->o_ref_b[l], 1.f, N, Hout * Wout, st)) return 1;
     if (l > 0) {
-      const size_t total = (size_t)N * Hin * Win * Cr;
-      const unsigned blocks = (unsigned)((total + 255) / 256 < 65535 * 8 ? (total + 255) / 256 : 65535 * 8);
-      refine_dgrad_kernel<<<blocks, 256, 0, st>>>(ts->rg[rc], p->ref_wp[l], ts->ract[t][l - 1], ts->rg[rc ^ 1], N, Hin, Win,
-                                                   Hout, Wout, Cr, s.ref_k, s.ref_stride);
+      static const bool gather = getenv("IODINE_REFINE_DGRAD_GATHER") != nullptr;
+      if (gather) {
+        const size_t total = (size_t)N * Hin * Win * Cr;
+        const unsigned blocks = (unsigned)((total + 255) / 256 < 65535 * 8 ? (total + 255) / 256 : 65535 * 8);
+        refine_dgrad_kernel<<<blocks, 256, 0, st>>>(ts->rg[rc], p->ref_wp[l], ts->ract[t][l - 1], ts->rg[rc ^ 1], N, Hin, Win,
+                                                     Hout, Wout, Cr, s.ref_k, s.ref_stride);
+      } else {
+        const int S = s.ref_stride;
+        const long long per_class = (long long)N * ((Hin + S - 1) / S) * ((Win + S - 1) / S);
+        dim3 grid((unsigned)((per_class + 63) / 64), S * S);
+        refine_dgrad_gemm_kernel<<<grid, 256, 0, st>>>(ts->rg[rc], p->ref_wp[l], ts->ract[t][l - 1], ts->rg[rc ^ 1], N, Hin, Win,
+                                                        Hout, Wout, Cr, s.ref_k, S);
+      }
       IOD_LAUNCH_CHECK(p);
       rc ^= 1;
     }
