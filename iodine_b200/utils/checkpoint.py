@@ -32,7 +32,12 @@ def _match_prefix(state, model):
 
 
 class Checkpointer:
-    def __init__(self, model, optimizer=None, scheduler=None, args=None, max_checkpoints=10, save_dir=''):
+    def __init__(self, model, optimizer=None, scheduler=None, args=None, max_checkpoints=10, save_dir='',
+                 trust_pickle=False):
+        """``trust_pickle``: allow ``torch.load(weights_only=False)`` for checkpoint files whose extra ``args`` hold
+        arbitrary pickled objects (the reference's loader always does, lib/utils/checkpoint.py:64).  Unpickling runs
+        code from the file, so it is OFF unless the caller vouches for the file."""
+        self.trust_pickle = bool(trust_pickle)
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.args = {} if args is None else args
         self.max_checkpoints = max_checkpoints
@@ -82,8 +87,14 @@ class Checkpointer:
     def _load_file(self, f):
         try:
             return torch.load(f, map_location=torch.device('cpu'), weights_only=True)
-        except pickle.UnpicklingError:
-            return torch.load(f, map_location=torch.device('cpu'), weights_only=False)   # args may hold arbitrary objects
+        except pickle.UnpicklingError as e:
+            if not self.trust_pickle:
+                raise pickle.UnpicklingError(
+                    '%s holds objects that torch.load(weights_only=True) refuses (%s). Pass trust_pickle=True to '
+                    'Checkpointer only for files from a trusted source: full unpickling executes code.' % (f, e))
+            import warnings
+            warnings.warn('loading %s with full unpickling (trust_pickle=True)' % f)
+            return torch.load(f, map_location=torch.device('cpu'), weights_only=False)
 
     def load(self, f=None):
         if self.has_checkpoint():
