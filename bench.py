@@ -239,7 +239,7 @@ def workload_string(cfg, S, K, T, B, precision):
             % (cfg['arch'], S, S, K, T, B, 'in total' if cfg.get('total') else 'per GPU', label))
 
 
-def config_block(cfg, arch, B, world, precision):
+def config_block(cfg, arch, B, world, precision, ksplit=0):
     """the line's `config`: identical on the native and the reference arm of one invocation"""
     S, K, T = arch.IMG_SIZE, arch.SLOTS, arch.ITERS
     eb = 2 if precision in ('fp16', 'bf16') else 4          # bytes per stored activation element
@@ -249,7 +249,9 @@ def config_block(cfg, arch, B, world, precision):
             'l2': ('activations (%.2f GB/layer) exceed the 126 MB L2; no flush needed' if layer_bytes > 252e6
                    else 'activations are %.3f GB/layer: the working set of a step FITS the 126 MB L2 (no flush; this '
                         'configuration is launch-latency bound, not a bandwidth measurement)') % (layer_bytes / 1e9),
-            'parallelism': 'slot-shard x%d (whole images per rank)' % world}
+            'parallelism': ('K-split x%d (every rank holds all images and K/%d of their slots; one ncclAllGather of the '
+                            "decoder's 4-channel output per elbo())" % (ksplit, ksplit)) if ksplit
+            else 'slot-shard x%d (whole images per rank)' % world}
 
 
 def resolve_config(args):
@@ -332,13 +334,25 @@ def run_native(args):
     torch.manual_seed(0)
     model = IODINE(arch, precision=args.precision).to(dev)
     model.max_images_per_call = B
-    g = torch.Generator().manual_seed(1 + rank)
+    ksplit = bool(args.k_split) and world > 1
+    comms = []
+    if ksplit:
+        # K-split (SURVEY.md 8e fallback, B < #GPUs): every rank holds ALL B images and K/world of their slots; the
+        # library all-gathers the decoder's 4-channel output once per elbo() evaluation (iodine_plan_set_comm on a
+        # K-split plan).  Strong scaling: the units of a step do not grow with the ranks.
+        from iodine_b200.parallel import NcclComm
+        assert K % world == 0, 'K-split needs SLOTS to be a multiple of the ranks'
+        comms.append(NcclComm())
+        model.set_slot_split(comms[0], rank, world)
+    Kl = K // world if ksplit else K                       # slots held by this rank
+    seed_rank = 0 if ksplit else rank                      # K-split: the same images everywhere
+    g = torch.Generator().manual_seed(1 + seed_rank)
     x_host = torch.rand(B, 3, S, S, generator=g).pin_memory()
-    eps_host = torch.randn(T + 1, B, K, L, generator=torch.Generator().manual_seed(123 + rank)).pin_memory()
+    eps_all = torch.randn(T + 1, B, K, L, generator=torch.Generator().manual_seed(123 + seed_rank))
+    eps_host = (eps_all[:, :, rank * Kl:(rank + 1) * Kl].contiguous() if ksplit else eps_all).pin_memory()
     x, eps = x_host.to(dev), eps_host.to(dev)
     eng = model.state_for_debug(B)
-    comms = []
-    if world > 1:
+    if world > 1 and not ksplit:
         # the path's only exchange -- the [T,2] ELBO partial sums -- is one ncclAllReduce issued by the library on
         # the stream of the call (iodine_plan_set_comm); one communicator per plan / stream
         from iodine_b200.parallel import NcclComm
@@ -346,10 +360,10 @@ def run_native(args):
         eng.set_comm(comms[0], rank, world)
     pin = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
     host_out = dict(pred=pin(B, 3, S, S), mask=pin(B, K, 1, S, S), mean=pin(B, K, 3, S, S),
-                    z=pin(B, K, L), terms=pin(T, 2))
+                    z=pin(B, Kl, L), terms=pin(T, 2))
     # what the evaluator keeps (lib/eval/ari_eval.py:32-39): the argmax of the masks, 1 byte per pixel
     eval_out = dict(pred=pin(B, 3, S, S), argmax=torch.empty(B, S, S, dtype=torch.uint8).pin_memory(),
-                    z=pin(B, K, L), terms=pin(T, 2))
+                    z=pin(B, Kl, L), terms=pin(T, 2))
 
     def barrier():
         torch.cuda.synchronize()
@@ -414,8 +428,11 @@ def run_native(args):
     model_b = IODINE(arch, precision=args.precision).to(dev)
     model_b.load_state_dict(model.state_dict())
     model_b.max_images_per_call = B
+    if ksplit:
+        comms.append(NcclComm())
+        model_b.set_slot_split(comms[1], rank, world)
     engs = [eng, model_b.state_for_debug(B)]
-    if world > 1:
+    if world > 1 and not ksplit:
         comms.append(NcclComm())
         engs[1].set_comm(comms[1], rank, world)
     streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
@@ -498,7 +515,7 @@ def run_native(args):
             del m2, e2
             torch.cuda.empty_cache()
 
-    units_per_step = world * B * K * T
+    units_per_step = (1 if ksplit else world) * B * K * T
     value = units_per_step * args.steps / (dev_ms * 1e-3)
     e2e_value = units_per_step * host_steps / e2e_s
     h2d = x_host.numel() * 4 + eps_host.numel() * 4
@@ -518,16 +535,16 @@ def run_native(args):
             peak_tf = max(tf32_live, peak_tf / 2)
         f_unit = 2 * f_dec + refine_flops_per_unit(arch)
         f_l1 = 2 * S * S * arch.DEC.KERNEL_SIZE ** 2 * (L + 2) * arch.DEC.CONV_CHAN      # collapsed first layer: not executed
-        per_launch_flop = B * K * f_cc                     # one C->C layer over the rank's slots
+        per_launch_flop = B * Kl * f_cc                    # one C->C layer over the rank's slots
         achieved_tf = per_launch_flop * conv_n / (conv_ms * 1e-3) / 1e12 if conv_n else None
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'strong' if cfg.get('total') else 'weak', 'vs_baseline': None,
+            'scaling': 'strong' if (cfg.get('total') or ksplit) else 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'tf32': 'f32 storage, tf32 tensor-core operands / f32 accumulate'}.get(
                 args.precision, '%s operands / f32 accumulate' % args.precision),
             'data': 'synthetic',
-            'config': config_block(cfg, arch, B, world, args.precision),
+            'config': config_block(cfg, arch, B, 1 if ksplit else world, args.precision, world if ksplit else 0),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h,
                     'call': 'iodine_evaluate_host_async (encode + decode, pinned host buffers; results = pred fp32, '
@@ -681,6 +698,9 @@ def main():
                     help='tf32 (default for configs[1]: fp32 storage, tcgen05 kind::tf32), fp16 / bf16 (tcgen05 kind::f16; bf16 is '
                          'outside the 1e-3 parity bar), fp32 (exact FFMA path)')
     ap.add_argument('--no-variants', action='store_true', help='skip the short fp32 / bf16 side measurements')
+    ap.add_argument('--k-split', action='store_true',
+                    help='N > 1: shard the SLOTS of the same images over the GPUs (for a batch smaller than the GPU count), '
+                         'e.g. --batch 1 --slots 16 --gpus 2; strong scaling')
     ap.add_argument('--slots', type=int, default=0, help='override K (BASELINE config #4: 11)')
     ap.add_argument('--iters', type=int, default=0, help='override T (BASELINE config #4: 7)')
     ap.add_argument('--img-size', type=int, default=0, help='override the image size (BASELINE config #5: 256)')
