@@ -433,10 +433,11 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       }
       __syncwarp();
     }
-  } else if (warp == 0) {
-    // =============================================================== TMA producer
+  } else if (!RS && warp == 0) {
+    // =============================================================== TMA producer (generic kernels only)
     // lane 0 owns the barriers; the copies of one halo row (planes x mirror copies x boxes) are
     // issued by as many lanes in parallel
+    if constexpr (!RS) {
     if (lane == 0) {  // weights: one shot, resident for the whole kernel
       const uint32_t wbar = smem_u32(&sb->wbar);
       mbar_expect_tx(wbar, p.w_bytes);
@@ -487,6 +488,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       }
     }
     __syncwarp();
+    }
   } else if (RS && warp == 1) {
     // =============================================================== MMA issuer, row-streaming
     // One thread: input rows are consumed strictly in order, each exactly once.
@@ -556,10 +558,12 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         }
       }
     }
-  } else if (warp <= TC_ISSUERS) {
-    // =============================================================== MMA issuers
+  } else if (!RS && warp <= TC_ISSUERS) {
+    // =============================================================== MMA issuers (generic kernels only: the row-
+    // streaming instantiations must not carry these 2*KS*KS*NKS MMAs and their per-MMA issue loops as dead code)
     // All lanes walk the tile sequence (so the per-tile bases are warp-uniform values); one elected
     // lane issues the MMAs and commits.  Issuer w = warp-1 owns tiles w, w+TC_ISSUERS, ...
+    if constexpr (!RS) {
     const int w = warp - 1;
     // lane 0 rather than elect.sync on purpose: behind a plain lane test ptxas wraps every UTCHMMA in its
     // own small issue block, which keeps descriptor arithmetic next to its MMA; with elect.sync it hoists
@@ -648,6 +652,7 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       }
     }
     __syncwarp();
+    }
   } else {
     // =============================================================== epilogue warps
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
@@ -1272,6 +1277,10 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, int n
   q->strips = (s.H + g.TH - 1) / g.TH;
   q->rs_segs = 0;
   q->rs_unit = g.R >= 7 ? TC_RS_UNIT : (g.R / 2 > 0 ? g.R / 2 : 1);
+  if (getenv("IODINE_TC_RS_UNIT")) {                       // experiment: rows per issue unit (must stay below the ring depth)
+    const int u = atoi(getenv("IODINE_TC_RS_UNIT"));
+    if (u >= 1 && u < g.R && u <= 16) q->rs_unit = u;
+  }
   q->rev = 0;
   q->itab = nullptr;
   q->coff = nullptr;
