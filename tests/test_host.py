@@ -85,3 +85,34 @@ def test_make_model_contract():
     bad.ENCODING = ['posterior', 'grad_post', 'not_an_encoding']
     with pytest.raises(ValueError):
         IODINE(bad)
+
+
+def test_bench_configs_follow_baseline_json():
+    """bench.py --config N: the five BASELINE.json configurations, with the per-unit FLOP figures of SURVEY.md 8(d)"""
+    import argparse
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    base = json.load(open(os.path.join(root, 'BASELINE.json')))
+    assert sorted(bench.CONFIGS) == list(range(1, len(base['configs']) + 1))
+    want = {1: (64, 6, 3, 4), 2: (128, 7, 5, 32), 3: (128, 7, 5, 256), 4: (128, 11, 7, 32), 5: (256, 16, 8, 64)}
+    for n, (S_, K, T, B) in want.items():
+        args = argparse.Namespace(config=n, slots=0, iters=0, img_size=0, batch=0, precision='')
+        cfg, arch, b, prec = bench.resolve_config(args)
+        assert (arch.IMG_SIZE, arch.SLOTS, arch.ITERS, b) == (S_, K, T, B), n
+        assert prec in ('tf32', 'fp16')
+        w = bench.workload_string(cfg, S_, K, T, b, prec)
+        assert 'configs[%d]' % (n - 1) in w
+    # the default line is labelled configs[1] only for fp32-class arithmetic
+    cfg = bench.CONFIGS[2]
+    assert 'configs[1])' in bench.workload_string(cfg, 128, 7, 5, 32, 'tf32')
+    assert 'fp16 operands' in bench.workload_string(cfg, 128, 7, 5, 32, 'fp16')
+    assert 'OUTSIDE' in bench.workload_string(cfg, 128, 7, 5, 32, 'bf16')
+    a = bench.clevr6_arch()
+    f_dec, f_cc = bench.flops_per_unit(a)
+    assert abs(2 * f_dec + bench.refine_flops_per_unit(a) - 10.071e9) < 1e6          # SURVEY.md 8(d): F_unit
+    assert abs(2 * bench.flops_per_unit(bench.bench_arch('dsprites'))[0]
+               + bench.refine_flops_per_unit(bench.bench_arch('dsprites')) - 0.724e9) < 1e6

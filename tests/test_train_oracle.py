@@ -128,3 +128,28 @@ def test_training_gradients_match_committed_reference_vectors(name):
     for k in sd:
         ref = torch.from_numpy(np.asarray(g['grad/' + k])).double()
         assert _rel(grads[k], ref) < 2e-3, (k, _rel(grads[k], ref))
+
+
+def test_training_restatement_against_the_clevr6_size_fixture():
+    """tests/golden/train_clevr6_b2_t2.npz (oracle/make_train_golden_size.py): samples + sums of the reference's
+    gradients at the CLEVR6 layer sizes; the restatement must reproduce them (the GPU tests use the same fixture)."""
+    import os
+    import numpy as np
+    from oracle import make_golden as MG
+    from oracle import make_golden_size as MS
+    from oracle import make_train_golden_size as TS
+    from helpers import GOLDEN, seeded_model
+    g = dict(np.load(os.path.join(GOLDEN, TS.NAME + '.npz')))
+    arch, x, eps = TS.case_inputs()
+    assert abs(x.double().sum().item() - float(g['x_checksum'])) <= 1e-9 * abs(float(g['x_checksum']))
+    sd = S.state_dict_to(seeded_model(arch, TS.SHARPEN).state_dict(), torch.float32)
+    cs = MG.weights_checksum(sd)
+    assert abs(cs - float(g['weights_checksum'])) <= 1e-9 * abs(cs)
+    loss, grads, _ = TR.loss_and_grads(sd, arch, x, eps)
+    assert abs(loss.item() - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    for k in sd:
+        flat = grads[k].reshape(-1).double()
+        want = torch.from_numpy(g['grad_s/' + k]).double()
+        gmax = float(g['grad_max/' + k])
+        assert ((flat[MS.sample_index(flat.numel(), TS.NS)] - want).abs().max() / gmax).item() < 2e-3, k
+        assert abs(flat.sum().item() - float(g['grad_sum/' + k])) / float(g['grad_abs/' + k]) < 2e-3, k
