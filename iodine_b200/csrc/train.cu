@@ -255,6 +255,79 @@ static int launch_conv_wgrad(Plan* p, const TView& in, const TView& g, float* dw
   return 0;
 }
 
+// Weight gradient of the refiner's FIRST conv (17 input channels in a 20-float NHWC record, 3x3, stride 2, 64 output
+// channels): the generic kernel wastes half of its 64 x 32 tile on it and re-reads g once per tap (2.0 ms per call).
+// Here one block accumulates ALL nine taps: a round = 16 consecutive output pixels of one output row; the g tile
+// [16][64] and the 3 x 33-pixel input patch they touch are staged once, thread = (output channel, quarter of the 45
+// (tap, 4-channel group) pairs), 45-48 running sums in registers, 4 FMAs per shared-memory float4.
+__global__ void __launch_bounds__(256)
+refine_wgrad_l0_kernel(const float* __restrict__ enc20, const float* __restrict__ g, float* __restrict__ dw, int N, int Hin,
+                       int Win, int Hout, int Wout, int rounds_per_block) {
+  __shared__ __align__(16) float sg[16][64];
+  __shared__ __align__(16) float sp[3][33][20];
+  const int co = threadIdx.x & 63, tq = threadIdx.x >> 6;
+  const int segs = Wout / 16;
+  const long long total = (long long)N * Hout * segs;
+  const long long r_lo = (long long)blockIdx.x * rounds_per_block;
+  const long long r_hi = (r_lo + rounds_per_block < total) ? r_lo + rounds_per_block : total;
+  float acc[12][4];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  // loader roles: g tile = 256 float4 (one per thread); patch = 3 * 33 * 5 = 495 float4 (two per thread)
+  float4 gv, pv0, pv1;
+  auto fetch = [&](long long rr) {
+    const int n = (int)(rr / ((long long)Hout * segs));
+    const int r = (int)(rr - (long long)n * Hout * segs);
+    const int oy = r / segs, ox0 = (r - oy * segs) * 16;
+    gv = __ldg(reinterpret_cast<const float4*>(g + (((size_t)n * Hout + oy) * Wout + ox0 + (threadIdx.x >> 4)) * 64 + (threadIdx.x & 15) * 4));
+    auto patch = [&](int idx) -> float4 {
+      if (idx >= 495) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c4 = idx % 5, j = (idx / 5) % 33, dy = idx / 165;
+      const int iy = 2 * oy - 1 + dy, ix = 2 * ox0 - 1 + j;
+      if (iy < 0 || iy >= Hin || ix < 0 || ix >= Win) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return __ldg(reinterpret_cast<const float4*>(enc20 + (((size_t)n * Hin + iy) * Win + ix) * 20 + c4 * 4));
+    };
+    pv0 = patch(threadIdx.x);
+    pv1 = patch(threadIdx.x + 256);
+  };
+  if (r_lo < r_hi) fetch(r_lo);
+  for (long long rr = r_lo; rr < r_hi; ++rr) {
+    __syncthreads();
+    *reinterpret_cast<float4*>(&sg[threadIdx.x >> 4][(threadIdx.x & 15) * 4]) = gv;
+    reinterpret_cast<float4*>(&sp[0][0][0])[threadIdx.x] = pv0;
+    if (threadIdx.x + 256 < 495) reinterpret_cast<float4*>(&sp[0][0][0])[threadIdx.x + 256] = pv1;
+    __syncthreads();
+    if (rr + 1 < r_hi) fetch(rr + 1);              // the next round's loads fly under this round's FMAs
+#pragma unroll 4
+    for (int kk = 0; kk < 16; ++kk) {
+      const float gval = sg[kk][co];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const int q = tq + 4 * i;                  // (tap, 4-channel group) pair of this thread
+        if (q < 45) {
+          const int tap = q / 5, c4 = q - tap * 5, dy = tap / 3, dx = tap - dy * 3;
+          const float4 v = *reinterpret_cast<const float4*>(&sp[dy][2 * kk + dx][c4 * 4]);
+          acc[i][0] = fmaf(gval, v.x, acc[i][0]);
+          acc[i][1] = fmaf(gval, v.y, acc[i][1]);
+          acc[i][2] = fmaf(gval, v.z, acc[i][2]);
+          acc[i][3] = fmaf(gval, v.w, acc[i][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int q = tq + 4 * i;
+    if (q >= 45) continue;
+    const int tap = q / 5, c4 = q - tap * 5;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ci = c4 * 4 + e;
+      if (ci < 17) atomicAdd(dw + ((size_t)co * 17 + ci) * 9 + tap, acc[i][e]);
+    }
+  }
+}
+
 // decoder.conv (C -> 4) weight and bias gradient: dW[o][ci][dy][dx] += coef * sum g4[n,oy,ox,o] * act[n,oy+dy-P,ox+dx-P,ci].
 // Thread = (ci, phase); it walks the INPUT pixels of its phase, reads act once and the KS*KS seed pixels around it
 // (the same address for all ci threads: broadcast loads), KS*KS*4 running sums in registers.
@@ -918,8 +991,15 @@ static int refiner_backward(Plan* p, TrainState* ts, int t, float alpha, int cur
     const int Hin = p->ref_h[l], Win = p->ref_w[l], Hout = p->ref_h[l + 1], Wout = p->ref_w[l + 1];
     const TView gv = nhwc_view(ts->rg[rc], Cr, Cr);
     const TView iv = (l == 0) ? nhwc_view(ts->enc[t], 17, 20) : nhwc_view(ts->ract[t][l - 1], Cr, Cr);
-    if (launch_conv_wgrad(p, iv, gv, gf + ts->o_ref_w[l], 1.f, N, Hin, Win, Hout, Wout, l == 0 ? 17 : Cr, Cr, s.ref_k,
-                          s.ref_stride, st))
+    if (l == 0 && Cr == 64 && s.ref_k == 3 && s.ref_stride == 2 && Wout % 16 == 0 && !getenv("IODINE_REFINE_WGRAD_GENERIC")) {
+      const long long rounds = (long long)N * Hout * (Wout / 16);
+      long long per = (rounds + 2LL * p->num_sms - 1) / (2LL * p->num_sms);
+      if (per < 8) per = 8;
+      refine_wgrad_l0_kernel<<<(unsigned)((rounds + per - 1) / per), 256, 0, st>>>(ts->enc[t], ts->rg[rc], gf + ts->o_ref_w[0], N,
+                                                                                    Hin, Win, Hout, Wout, (int)per);
+      IOD_LAUNCH_CHECK(p);
+    } else if (launch_conv_wgrad(p, iv, gv, gf + ts->o_ref_w[l], 1.f, N, Hin, Win, Hout, Wout, l == 0 ? 17 : Cr, Cr, s.ref_k,
+                                 s.ref_stride, st))
       return 1;
     if (launch_chan_sum(p, gv, gf + ts->o_ref_b[l], 1.f, N, Hout * Wout, st)) return 1;
     if (l > 0) {
