@@ -168,11 +168,13 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
   return 0;
 }
 
+// log_image0: keep image 0 of this elbo() evaluation for the logger side channel (every write replaces the previous
+// one, iodine.py:226-239, so inside a loop only the LAST step's needs to be produced)
 static int refine_step(Plan* p, const float* x, const float* eps_t, float* mu, float* lv, float* h,
-                       float* c, float* terms_out, float* aux_out, cudaStream_t st) {
+                       float* c, float* terms_out, float* aux_out, cudaStream_t st, bool log_image0 = true) {
   if (decoder_forward(p, mu, lv, eps_t, nullptr, st)) return 1;
   if (launch_mixture(p, x, true, st)) return 1;
-  if (launch_recombine(p, p->log_pred, p->log_mask, p->log_mean, 1, st)) return 1;   // what elbo() hands the logger
+  if (log_image0 && launch_recombine(p, p->log_pred, p->log_mask, p->log_mean, 1, st)) return 1;   // what elbo() hands the logger
   if (decoder_dgrad(p, st)) return 1;
   if (launch_post_grads(p, mu, lv, eps_t, nullptr, st)) return 1;
   if (rtc_enabled(p)) {
@@ -205,7 +207,7 @@ static int do_encode(Plan* p, const float* x, const float* eps, float* z_out, fl
   if (launch_init_state(p, p->st_mean, p->st_logvar, p->st_h, p->st_c, st)) return 1;
   for (int t = 0; t < s.T; ++t) {
     if (refine_step(p, x, eps + t * nl, p->st_mean, p->st_logvar, p->st_h, p->st_c,
-                    terms ? terms + 2 * t : nullptr, nullptr, st))
+                    terms ? terms + 2 * t : nullptr, nullptr, st, /*log_image0=*/t == s.T - 1))
       return 1;
   }
   sample_kernel<<<64, 256, 0, st>>>(p->st_mean, p->st_logvar, eps + (size_t)s.T * nl, z_out, (int)nl);

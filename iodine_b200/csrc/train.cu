@@ -1078,7 +1078,7 @@ IODINE_API int iodine_train_step(IodinePlan* plan, const float* x, const float* 
     else { p->xin = sv_xin; p->pool = sv_pool; p->enc20 = sv_enc20; }
     rc = plan_decoder_forward(p, ts->mu, ts->lv, eps_i, nullptr, st);
     if (!rc) rc = launch_mixture(p, x, true, st);
-    if (!rc) rc = launch_recombine(p, p->log_pred, p->log_mask, p->log_mean, 1, st);      // logger side channel
+    if (!rc && i == T) rc = launch_recombine(p, p->log_pred, p->log_mask, p->log_mean, 1, st);   // logger side channel: the last elbo()
     if (!rc) rc = decoder_backward_train(p, ts, coef, st);
     float* pg_i = ts->pg + (size_t)i * N * 2 * L;
     if (!rc) rc = launch_post_grads(p, ts->mu, ts->lv, eps_i, pg_i, st);
