@@ -146,6 +146,7 @@ struct Plan {
   float* G = nullptr;             // [BK,n_class,C] class-wise pixel sums of dJ/d(pre-act 1)
   float* dz = nullptr;            // [BK,L]
   double* stats = nullptr;        // [BK,4,2] (sum, sumsq) for grad_means/grad_mask/lik/loo
+  float* lnp = nullptr;           // [BK,8] their layer-norm parameters: 4 means, 4 x 1/(std + 1e-5) (post_grads_kernel)
   double* accum = nullptr;        // [2] (sum ll, sum kl) of the step
   float* pool = nullptr;          // [BK,Cr]
   float* xin = nullptr;           // [BK, M+4L]
@@ -205,7 +206,8 @@ int launch_dgrad_in4(Plan* p, const float* seed4, const float* act_prev, float* 
 int launch_refine_convs(Plan* p, const float* x, cudaStream_t st, float* const* outs = nullptr);
 
 // ------------------------------------------------------------------ launchers (mixture.cu)
-int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st);
+// fused_aux: write the refinement input in the form refine_l0f_kernel consumes (refine_tc.cu) instead of raw fp32 auxs
+int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st, bool fused_aux = false);
 int launch_recombine(Plan* p, float* pred, float* mask, float* mean, int n_images, cudaStream_t st,
                      uint8_t* amax = nullptr);   // amax[B,H,W]: argmax over the K masks (evaluator tail)
 // slot (b, k) of an image, k in [0, K_total), inside out4_all [ks_ranks][B][Kl][HW] (float4 units): rank-major, as
@@ -223,7 +225,6 @@ int launch_sample_l1(Plan* p, const float* mu, const float* logvar, const float*
 int launch_post_grads(Plan* p, const float* mu, const float* logvar, const float* eps,
                       float* latent_out, cudaStream_t st);
 int launch_head(Plan* p, float* mu, float* logvar, float* h, float* c, cudaStream_t st);
-int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st);
 int launch_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st);
 
 // ------------------------------------------------------------------ plan.cu pieces the training step reuses
@@ -265,6 +266,7 @@ int rtc_supported(const Plan* p);
 int rtc_alloc(Plan* p);
 void rtc_free(Plan* p);
 bool rtc_enabled(const Plan* p);       // 16-bit mode and every refine layer fits the tensor-core kernel
+bool rtc_fused_aux(const Plan* p);     // layer 0 normalises / packs the aux stack itself (no assemble16 pass, no enc16)
 int rtc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st);
 int rtc_launch_refine_convs(Plan* p, cudaStream_t st);   // p->enc16 -> p->pool
 

@@ -247,7 +247,8 @@ post_grads_kernel(const float* __restrict__ G, const float* __restrict__ wsum,
                   const float* __restrict__ mu, const float* __restrict__ logvar,
                   const float* __restrict__ eps, float* __restrict__ dz_out,
                   float* __restrict__ xin, double* __restrict__ accum,
-                  int L, int NCC, int M, int layernorm, float* __restrict__ raw_out /* [N][2L] or null */) {
+                  int L, int NCC, int M, int layernorm, float* __restrict__ raw_out /* [N][2L] or null */,
+                  const double* __restrict__ stats, float* __restrict__ lnp, int HW) {
   extern __shared__ float sm[];
   float* sG = sm;            // [NCC]
   float* sa = sm + NCC;      // [L] dmu
@@ -310,6 +311,23 @@ post_grads_kernel(const float* __restrict__ G, const float* __restrict__ wsum,
     st[threadIdx.x * 2] = layernorm ? m : 0.f;
     st[threadIdx.x * 2 + 1] = layernorm ? 1.f / (sd + 1e-5f) : 1.f;
   }
+  // (mean, 1 / (std + 1e-5)) of the four image-shaped layer-norms of get_input_encoding (iodine.py:376-395, biased std
+  // over C,H,W) from the sums mixture_kernel accumulated: finalised once per slot here, so that the fused first
+  // refinement layer (refine_tc.cu) reads eight floats instead of redoing the f64 arithmetic per work item
+  if (lnp && threadIdx.x >= 32 && threadIdx.x < 36) {
+    const int g = threadIdx.x - 32;
+    float m_f = 0.f, is_f = 1.f;
+    if (layernorm) {
+      const double cnt = (g == 0) ? 3.0 * HW : (double)HW;
+      const double m = stats[((size_t)n * 4 + g) * 2] / cnt;
+      double var = stats[((size_t)n * 4 + g) * 2 + 1] / cnt - m * m;
+      if (var < 0.0) var = 0.0;
+      m_f = (float)m;
+      is_f = 1.f / ((float)sqrt(var) + 1e-5f);
+    }
+    lnp[(size_t)n * 8 + g] = m_f;
+    lnp[(size_t)n * 8 + 4 + g] = is_f;
+  }
   __syncthreads();
   float* row = xin + (size_t)n * (M + 4 * L) + M;
   for (int ci = threadIdx.x; ci < L; ci += blockDim.x) {
@@ -327,7 +345,7 @@ int launch_post_grads(Plan* p, const float* mu, const float* logvar, const float
   const int parts = 256 / L > 0 ? 256 / L : 1;
   const size_t smem = (size_t)(ncc + 2 * L + parts * L) * sizeof(float);
   post_grads_kernel<<<p->BK, 256, smem, st>>>(p->G, p->wsum, mu, logvar, eps, p->dz, p->xin, p->accum,
-                                              L, ncc, p->M, p->s.layernorm, latent_out);
+                                              L, ncc, p->M, p->s.layernorm, latent_out, p->stats, p->lnp, p->HW);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

@@ -9,20 +9,59 @@
 // mask_posterior (289-292), pixel likelihood (309-312) and leave-one-out likelihood
 // (321-328), plus the sums the parameter-free layer-norm (376-395) needs.  No [B,K,C,H,W]
 // intermediate of the reference (K_log_likelihood, log(mask), r, ...) touches HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace iod {
 
+// Hardware exponential / logarithm for the tensor-core precision modes (FAST): MUFU.EX2 / MUFU.LG2 with the
+// argument product split exactly (x * log2(e) = t + r, r from one FMA), so the result keeps ~2 ulp over the
+// whole range, and WITHOUT flush-to-zero: the reference's un-stabilised exp(sum ll) (iodine.py:290) lives in the
+// subnormals for pixels no slot explains.  The exact fp32 mode keeps libm.
+template <bool FAST>
+__device__ __forceinline__ float mix_exp(float x) {
+  if constexpr (!FAST) return expf(x);
+  const float t = x * 1.4426950408889634f;
+  float r = fmaf(x, 1.4426950408889634f, -t);
+  r = fmaf(x, 1.9259629911266175e-8f, r);
+  float e;
+  asm("ex2.approx.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return e * fmaf(r, 0.6931471805599453f, 1.f);
+}
+template <bool FAST>
+__device__ __forceinline__ float mix_log(float x) {
+  if constexpr (!FAST) return logf(x);
+  float l;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(l) : "f"(x));
+  return l * 0.6931471805599453f;
+}
+template <bool FAST>
+__device__ __forceinline__ float mix_rcp(float x) {
+  if constexpr (!FAST) return 1.f / x;
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <bool FAST>
+__device__ __forceinline__ float mix_sigmoid(float v) { return mix_rcp<FAST>(1.f + mix_exp<FAST>(-v)); }
+
 // auxs layout per slot-pixel (12 floats): 0-2 mean rgb | 3 mask | 4 logit | 5 mask_post |
 // 6-8 dJ/dmean rgb | 9 dJ/dmask | 10 leave-one-out | 11 unused
-template <int KMAX>
+// FUSED (tensor-core refinement encoder, refine_tc.cu: refine_l0f_kernel): the same 48 bytes per slot-pixel hold the
+// refinement network's input stack in the form its first layer consumes -- no separate assembly pass:
+//   pl0  uint4  [n][HW]  channels 0-7 of the stack, FINAL 16-bit values: image rgb | mean rgb | mask | logit
+//   raw4 float4 [n][HW]  mask_posterior | dJ/dmean rgb         (fp32: the last three still lack their layer-norm,
+//   raw2 float2 [n][HW]  dJ/dmask | leave-one-out               whose statistics only exist once this grid finishes)
+// (pl0 at auxs, raw4 at auxs + 4 BK HW floats, raw2 at auxs + 8 BK HW floats)
+template <int KMAX, bool FUSED, bool FAST>
 __global__ void __launch_bounds__(128)
 mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
                float* __restrict__ seed4, float* __restrict__ auxs, float* __restrict__ lik,
                double* __restrict__ stats, double* __restrict__ accum,
                int K, int HW, float inv_2s2, float inv_s2, float ll_const, int want_grads,
                int seed_half /* 0: fp32 float4, 1: bf16 x8, 2: fp16 x8 */,
-               int Kl, int k_off, int ll_on) {
+               int Kl, int k_off, int ll_on, int f16, size_t n_slot_pix) {
   // K-split: out4 holds all K slots of every image (out4_slot), this rank keeps the outputs of slots
   // [k_off, k_off + Kl) under LOCAL slot numbers; whole images: Kl == K, k_off == 0.  ll_on: this rank adds the
   // image log-likelihood to the step's sum (K-split: exactly one rank does).
@@ -45,7 +84,7 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
     lg[k] = -INFINITY; mr[k] = mg[k] = mb[k] = 0.f;
     if (k < K && live) {
       const float4 v = reinterpret_cast<const float4*>(out4)[out4_slot(b, k, B, Kl, HW) + pix];
-      mr[k] = sigmoid_f(v.x); mg[k] = sigmoid_f(v.y); mb[k] = sigmoid_f(v.z);
+      mr[k] = mix_sigmoid<FAST>(v.x); mg[k] = mix_sigmoid<FAST>(v.y); mb[k] = mix_sigmoid<FAST>(v.z);
       lg[k] = v.w;
       lmax = fmaxf(lmax, v.w);
     }
@@ -56,9 +95,9 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     logit_raw[k] = lg[k];
-    if (k < K && live) { lg[k] = expf(lg[k] - lmax); den += lg[k]; }
+    if (k < K && live) { lg[k] = mix_exp<FAST>(lg[k] - lmax); den += lg[k]; }
   }
-  const float inv_den = live ? 1.f / den : 0.f;
+  const float inv_den = live ? mix_rcp<FAST>(den) : 0.f;
   // ---- per-channel a_kc = log(mask+1e-12) + ll_kc ; s_c = logsumexp_k  (210-216)
   float amax_r = -INFINITY, amax_g = -INFINITY, amax_b = -INFINITY;
   float lm[KMAX];
@@ -67,7 +106,7 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
     lm[k] = 0.f;
     if (k < K && live) {
       lg[k] *= inv_den;                              // lg now holds the mask
-      lm[k] = logf(lg[k] + 1e-12f);
+      lm[k] = mix_log<FAST>(lg[k] + 1e-12f);
       const float dr = xr - mr[k], dg = xg - mg[k], db = xb - mb[k];
       amax_r = fmaxf(amax_r, lm[k] - dr * dr * inv_2s2 + ll_const);
       amax_g = fmaxf(amax_g, lm[k] - dg * dg * inv_2s2 + ll_const);
@@ -82,16 +121,16 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
       const float dr = xr - mr[k], dg = xg - mg[k], db = xb - mb[k];
       const float llr = -dr * dr * inv_2s2 + ll_const, llg = -dg * dg * inv_2s2 + ll_const,
                   llb = -db * db * inv_2s2 + ll_const;
-      sr += expf(lm[k] + llr - amax_r);
-      sg += expf(lm[k] + llg - amax_g);
-      sb += expf(lm[k] + llb - amax_b);
-      const float Lk = expf(llr + llg + llb);        // un-stabilised, as the reference (290)
+      sr += mix_exp<FAST>(lm[k] + llr - amax_r);
+      sg += mix_exp<FAST>(lm[k] + llg - amax_g);
+      sb += mix_exp<FAST>(lm[k] + llb - amax_b);
+      const float Lk = mix_exp<FAST>(llr + llg + llb);        // un-stabilised, as the reference (290)
       kl_tot += Lk;
       mkl_tot += lg[k] * Lk;
     }
   }
   float s_r = 0.f, s_g = 0.f, s_b = 0.f;
-  if (live) { s_r = amax_r + logf(sr); s_g = amax_g + logf(sg); s_b = amax_b + logf(sb); }
+  if (live) { s_r = amax_r + mix_log<FAST>(sr); s_g = amax_g + mix_log<FAST>(sg); s_b = amax_b + mix_log<FAST>(sb); }
   const float ll_pix = s_r + s_g + s_b;              // summed over channels (220)
 
   // ---- block reduction of the log-likelihood
@@ -109,7 +148,7 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
   if (!want_grads) return;
 
   // ---- gradients + aux channels
-  const float likv = live ? expf(ll_pix) : 0.f;      // exp(sum_c s_c)           (309-310)
+  const float likv = live ? mix_exp<FAST>(ll_pix) : 0.f;      // exp(sum_c s_c)           (309-310)
   if (live) lik[(size_t)b * HW + pix] = likv;
   float gm[KMAX];                                     // dJ/dmask_k
   float mgsum = 0.f;
@@ -119,9 +158,9 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
     if (k < K && live) {
       const float dr = xr - mr[k], dg = xg - mg[k], db = xb - mb[k];
       // exp(ll_kc - s_c) = r_kc / (mask_k + 1e-12)
-      const float er = expf(-dr * dr * inv_2s2 + ll_const - s_r);
-      const float eg = expf(-dg * dg * inv_2s2 + ll_const - s_g);
-      const float eb = expf(-db * db * inv_2s2 + ll_const - s_b);
+      const float er = mix_exp<FAST>(-dr * dr * inv_2s2 + ll_const - s_r);
+      const float eg = mix_exp<FAST>(-dg * dg * inv_2s2 + ll_const - s_g);
+      const float eb = mix_exp<FAST>(-db * db * inv_2s2 + ll_const - s_b);
       gm[k] = er + eg + eb;
       mgsum += lg[k] * gm[k];
     }
@@ -152,17 +191,24 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
           const float llr = -dr * dr * inv_2s2 + ll_const, llg = -dg * dg * inv_2s2 + ll_const,
                       llb = -db * db * inv_2s2 + ll_const;
           const float me = mk + 1e-12f;
-          const float er = expf(llr - s_r), eg = expf(llg - s_g), eb = expf(llb - s_b);
+          const float er = mix_exp<FAST>(llr - s_r), eg = mix_exp<FAST>(llg - s_g), eb = mix_exp<FAST>(llb - s_b);
           // dJ/dmean_kc = r_kc (x_c - mean_kc)/sigma^2 with r_kc = (mask+1e-12) * exp(ll - s)
           const float gr = me * er * dr * inv_s2, gg = me * eg * dg * inv_s2, gb = me * eb * db * inv_s2;
-          const float Lk = expf(llr + llg + llb);
+          const float Lk = mix_exp<FAST>(llr + llg + llb);
           const float mpost = Lk / kl_tot;                                   // (292) 0/0 -> NaN as ref
           const float loo = (mkl_tot - mk * Lk) / (1.f - mk + 1e-5f);        // (326-328)
           const size_t sp = ((size_t)(b * Kl + (k - k_off))) * HW + pix;
-          float4* ax = reinterpret_cast<float4*>(auxs) + sp * 3;
-          ax[0] = make_float4(m_r, m_g, m_b, mk);
-          ax[1] = make_float4(lgr, mpost, gr, gg);
-          ax[2] = make_float4(gb, gmk, loo, 0.f);
+          if constexpr (FUSED) {
+            reinterpret_cast<uint4*>(auxs)[sp] = make_uint4(pack_h2(xr, xg, f16), pack_h2(xb, m_r, f16),
+                                                            pack_h2(m_g, m_b, f16), pack_h2(mk, lgr, f16));
+            reinterpret_cast<float4*>(auxs)[n_slot_pix + sp] = make_float4(mpost, gr, gg, gb);
+            reinterpret_cast<float2*>(auxs)[4 * n_slot_pix + sp] = make_float2(gmk, loo);
+          } else {
+            float4* ax = reinterpret_cast<float4*>(auxs) + sp * 3;
+            ax[0] = make_float4(m_r, m_g, m_b, mk);
+            ax[1] = make_float4(lgr, mpost, gr, gg);
+            ax[2] = make_float4(gb, gmk, loo, 0.f);
+          }
           // chain to the decoder's raw outputs: sigmoid' and softmax'
           const float4 sd = make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g),
                                         gb * m_b * (1.f - m_b), mk * (gmk - mgsum));
@@ -213,7 +259,207 @@ mixture_kernel(const float* __restrict__ out4, const float* __restrict__ x,
   }
 }
 
-int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st) {
+// ------------------------------------------------------------------------------------------------
+// The same pass for the tensor-core precision modes: identical outputs up to ~1e-6 relative, a third of the
+// instructions (mixture_kernel is instruction-issue bound: ~490 per slot-pixel, most of them in 15 libm exponentials
+// and their range handling).  What changes:
+//   * every slot's p_kc = exp(a_kc - max_k a_kc) is computed ONCE and kept in registers: the responsibilities are
+//     r_kc = p_kc / sum_k p_kc and exp(ll_kc - s_c) = r_kc / (mask_k + 1e-12), so the second and third evaluation of
+//     the three per-channel exponentials (dJ/dmask, dJ/dmean) become two multiplications; L_k = exp(sum_c ll_kc) is
+//     kept as well;
+//   * exponentials / logarithms / reciprocals are MUFU.EX2 / LG2 / RCP.  Flush-to-zero forms where a flushed result is
+//     indistinguishable (softmax terms next to the +1e-12, sigmoid, p_kc <= 1); the un-stabilised L_k and the pixel
+//     likelihood (iodine.py:290, 309) keep the exact-product, subnormal-preserving form mix_exp<true>;
+//   * mask_posterior = L_k / sum_k L_k with ONE reciprocal per pixel, the operands pre-scaled by 2^100 when the sum is
+//     below 2^-100 (so that a sum in the subnormals still divides; 0 / 0 stays NaN as in the reference).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_ftz(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
+__device__ __forceinline__ float lg2_fast(float x) { float l; asm("lg2.approx.f32 %0, %1;" : "=f"(l) : "f"(x)); return l; }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_sub(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+template <int KMAX, bool FUSED>
+__global__ void __launch_bounds__(128)
+mixture_fast_kernel(const float* __restrict__ out4, const float* __restrict__ x,
+                    float* __restrict__ seed4, float* __restrict__ auxs, float* __restrict__ lik,
+                    double* __restrict__ stats, double* __restrict__ accum,
+                    int K, int HW, float inv_2s2, float inv_s2, float ll_const, int want_grads,
+                    int seed_half, int Kl, int k_off, int ll_on, int f16, size_t n_slot_pix) {
+  constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const int b = blockIdx.y, B = gridDim.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = pix < HW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = 4;
+
+  float mk[KMAX], mr[KMAX], mg[KMAX], mb[KMAX];     // mask, mean rgb
+  float pr[KMAX], pg[KMAX], pb[KMAX];               // a_kc, then p_kc = exp(a_kc - max)
+  float Lk[KMAX];                                   // exp(sum_c ll_kc), un-stabilised
+  float xr = 0.f, xg = 0.f, xb = 0.f;
+  if (live) {
+    xr = x[((size_t)b * 3 + 0) * HW + pix];
+    xg = x[((size_t)b * 3 + 1) * HW + pix];
+    xb = x[((size_t)b * 3 + 2) * HW + pix];
+  }
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    mk[k] = -INFINITY; mr[k] = mg[k] = mb[k] = 0.f; pr[k] = pg[k] = pb[k] = 0.f; Lk[k] = 0.f;
+    if (k < K && live) {
+      const float4 v = reinterpret_cast<const float4*>(out4)[out4_slot(b, k, B, Kl, HW) + pix];
+      mr[k] = rcp_fast(1.f + ex2_ftz(-v.x * L2E));
+      mg[k] = rcp_fast(1.f + ex2_ftz(-v.y * L2E));
+      mb[k] = rcp_fast(1.f + ex2_ftz(-v.z * L2E));
+      mk[k] = v.w;
+      lmax = fmaxf(lmax, v.w);
+    }
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K && live) { mk[k] = ex2_ftz((mk[k] - lmax) * L2E); den += mk[k]; }
+  const float inv_den = live ? rcp_fast(den) : 0.f;
+  float amax_r = -INFINITY, amax_g = -INFINITY, amax_b = -INFINITY;
+  float kl_tot = 0.f, mkl_tot = 0.f;                 // sum_k L_k ; sum_k mask_k L_k
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K && live) {
+      mk[k] *= inv_den;                              // mask = softmax_K(logits)            (iodine.py:185)
+      const float lm = lg2_fast(mk[k] + 1e-12f) * LN2;
+      const float dr = xr - mr[k], dg = xg - mg[k], db = xb - mb[k];
+      const float llr = fmaf(-dr * dr, inv_2s2, ll_const), llg = fmaf(-dg * dg, inv_2s2, ll_const),
+                  llb = fmaf(-db * db, inv_2s2, ll_const);
+      pr[k] = lm + llr; pg[k] = lm + llg; pb[k] = lm + llb;       // a_kc                     (210-216)
+      amax_r = fmaxf(amax_r, pr[k]); amax_g = fmaxf(amax_g, pg[k]); amax_b = fmaxf(amax_b, pb[k]);
+      Lk[k] = mix_exp<true>(llr + llg + llb);                     // un-stabilised, as the reference (290)
+      kl_tot += Lk[k];
+      mkl_tot = fmaf(mk[k], Lk[k], mkl_tot);
+    }
+  }
+  float sr = 0.f, sg = 0.f, sb = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K && live) {
+      pr[k] = ex2_ftz((pr[k] - amax_r) * L2E); sr += pr[k];
+      pg[k] = ex2_ftz((pg[k] - amax_g) * L2E); sg += pg[k];
+      pb[k] = ex2_ftz((pb[k] - amax_b) * L2E); sb += pb[k];
+    }
+  }
+  float ll_pix = 0.f;                                // sum_c logsumexp_k a_kc            (213-220)
+  if (live) ll_pix = (amax_r + lg2_fast(sr) * LN2) + (amax_g + lg2_fast(sg) * LN2) + (amax_b + lg2_fast(sb) * LN2);
+
+  __shared__ double red[NW];
+  {
+    float v = warp_sum(live ? ll_pix : 0.f);
+    if (lane == 0) red[warp] = (double)v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < NW; ++w) t += red[w];
+      if (ll_on) atomicAdd(&accum[0], t);
+    }
+  }
+  if (!want_grads) return;
+
+  const float likv = live ? mix_exp<true>(ll_pix) : 0.f;       // exp(sum_c s_c)           (309-310)
+  if (live) lik[(size_t)b * HW + pix] = likv;
+  const float isr = live ? rcp_fast(sr) : 0.f, isg = live ? rcp_fast(sg) : 0.f, isb = live ? rcp_fast(sb) : 0.f;
+  float gm[KMAX];                                     // dJ/dmask_k = sum_c exp(ll_kc - s_c) = sum_c r_kc / (mask + 1e-12)
+  float mgsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    gm[k] = 0.f;
+    if (k < K && live) {
+      pr[k] *= isr; pg[k] *= isg; pb[k] *= isb;       // p now holds the responsibilities r_kc
+      gm[k] = (pr[k] + pg[k] + pb[k]) * rcp_fast(mk[k] + 1e-12f);
+      mgsum = fmaf(mk[k], gm[k], mgsum);
+    }
+  }
+  // mask_posterior denominators: one reciprocal, operands pre-scaled out of the subnormals
+  const float kscale = (kl_tot < 7.8886090522101181e-31f) ? 1.2676506002282294e30f : 1.f;   // 2^-100, 2^100
+  const float inv_kl = rcp_sub(kl_tot * kscale);
+
+  constexpr int MIX_KB = 5;
+  constexpr int NBATCH = (KMAX + MIX_KB - 1) / MIX_KB;
+  __shared__ double s_stat[NBATCH][32];
+  for (int i = threadIdx.x; i < NBATCH * 32; i += blockDim.x) (&s_stat[0][0])[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int bt = 0; bt < NBATCH; ++bt) {
+    if (bt * MIX_KB < K) {                          // block-uniform
+      float vb[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) vb[i] = 0.f;
+      if (bt == 0) { vb[30] = likv; vb[31] = likv * likv; }
+#pragma unroll
+      for (int kk = 0; kk < MIX_KB; ++kk) {
+        const int k = bt * MIX_KB + kk;             // compile-time
+        if (k < KMAX && k < K && live && k >= k_off && k < k_off + Kl) {
+          const float m_k = mk[k], m_r = mr[k], m_g = mg[k], m_b = mb[k], gmk = gm[k];
+          const float dr = xr - m_r, dg = xg - m_g, db = xb - m_b;
+          // dJ/dmean_kc = r_kc (x_c - mean_kc) / sigma^2
+          const float gr = pr[k] * dr * inv_s2, gg = pg[k] * dg * inv_s2, gb = pb[k] * db * inv_s2;
+          const float mpost = (Lk[k] * kscale) * inv_kl;                             // (292) 0/0 -> NaN as ref
+          const float loo = (mkl_tot - m_k * Lk[k]) * rcp_fast(1.f - m_k + 1e-5f);   // (326-328)
+          const size_t sp = ((size_t)(b * Kl + (k - k_off))) * HW + pix;
+          const float lgr = __ldg(out4 + (out4_slot(b, k, B, Kl, HW) + pix) * 4 + 3);   // raw logit (L1 hit)
+          if constexpr (FUSED) {
+            reinterpret_cast<uint4*>(auxs)[sp] = make_uint4(pack_h2(xr, xg, f16), pack_h2(xb, m_r, f16),
+                                                            pack_h2(m_g, m_b, f16), pack_h2(m_k, lgr, f16));
+            reinterpret_cast<float4*>(auxs)[n_slot_pix + sp] = make_float4(mpost, gr, gg, gb);
+            reinterpret_cast<float2*>(auxs)[4 * n_slot_pix + sp] = make_float2(gmk, loo);
+          } else {
+            float4* ax = reinterpret_cast<float4*>(auxs) + sp * 3;
+            ax[0] = make_float4(m_r, m_g, m_b, m_k);
+            ax[1] = make_float4(lgr, mpost, gr, gg);
+            ax[2] = make_float4(gb, gmk, loo, 0.f);
+          }
+          const float4 sd = make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g),
+                                        gb * m_b * (1.f - m_b), m_k * (gmk - mgsum));
+          if (seed_half) {
+            reinterpret_cast<uint4*>(seed4)[sp] = make_uint4(pack_h2(sd.x, sd.y, seed_half == 2),
+                                                             pack_h2(sd.z, sd.w, seed_half == 2), 0u, 0u);
+          } else {
+            reinterpret_cast<float4*>(seed4)[sp] = sd;
+          }
+          vb[6 * kk + 0] = gr + gg + gb;
+          vb[6 * kk + 1] = gr * gr + gg * gg + gb * gb;
+          vb[6 * kk + 2] = gmk;
+          vb[6 * kk + 3] = gmk * gmk;
+          vb[6 * kk + 4] = loo;
+          vb[6 * kk + 5] = loo * loo;
+        }
+      }
+#pragma unroll
+      for (int m = 16, n = 32; m >= 1; m >>= 1, n >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+          const float send = up ? vb[i] : vb[i + n / 2];
+          const float keep = up ? vb[i + n / 2] : vb[i];
+          vb[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+      atomicAdd(&s_stat[bt][lane], (double)vb[0]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NBATCH * 32; i += blockDim.x) {
+    const int bt = i >> 5, l = i & 31;
+    const double v = s_stat[bt][l];
+    if (l < 30) {
+      const int k = bt * MIX_KB + l / 6, j = l % 6;
+      if (k >= k_off && k < k_off + Kl) {
+        const int grp = j >> 1, g = (grp == 2) ? 3 : grp;
+        atomicAdd(&stats[((size_t)(b * Kl + (k - k_off)) * 4 + g) * 2 + (j & 1)], v);
+      }
+    } else if (bt == 0) {
+      for (int k = 0; k < Kl; ++k) atomicAdd(&stats[((size_t)(b * Kl + k) * 4 + 2) * 2 + (l - 30)], v);
+    }
+  }
+}
+
+int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st, bool fused_aux) {
   const IodineShape& s = p->s;
   const float sg = s.sigma;
   const float inv_2s2 = 1.f / (2.f * sg * sg), inv_s2 = 1.f / (sg * sg);
@@ -224,12 +470,23 @@ int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st) {
   dim3 grid((p->HW + 127) / 128, s.B);
   const int seed_half = (tc_mode(p) && !tf_mode(p)) ? (s.precision == IODINE_FP16 ? 2 : 1) : 0;
   const int k_off = p->ks_rank * s.K, ll_on = p->ks_rank == 0;
-  if (p->K_total <= 8)
-    mixture_kernel<8><<<grid, 128, 0, st>>>(p->out4_all, x, p->seed4, p->auxs, p->lik, p->stats, p->accum, p->K_total,
-                                            p->HW, inv_2s2, inv_s2, ll_const, want_grads, seed_half, s.K, k_off, ll_on);
-  else
-    mixture_kernel<16><<<grid, 128, 0, st>>>(p->out4_all, x, p->seed4, p->auxs, p->lik, p->stats, p->accum, p->K_total,
-                                             p->HW, inv_2s2, inv_s2, ll_const, want_grads, seed_half, s.K, k_off, ll_on);
+  // hardware exp / log in the tensor-core modes (the exact fp32 mode keeps libm; IODINE_MIX_EXACT=1 keeps it everywhere)
+  static const bool exact_env = getenv("IODINE_MIX_EXACT") != nullptr;
+  const bool fast = tc_mode(p) && !exact_env;
+  const bool fused = fused_aux && want_grads;
+  const size_t nsp = (size_t)p->BK * p->HW;
+#define IOD_MIX_ARGS                                                                                               \
+  p->out4_all, x, p->seed4, p->auxs, p->lik, p->stats, p->accum, p->K_total, p->HW, inv_2s2, inv_s2, ll_const,       \
+      want_grads, seed_half, s.K, k_off, ll_on, half_is_f16(p), nsp
+#define IOD_MIX(KM, FU)                                                                  \
+  do {                                                                                   \
+    if (fast) mixture_fast_kernel<KM, FU><<<grid, 128, 0, st>>>(IOD_MIX_ARGS);            \
+    else mixture_kernel<KM, FU, false><<<grid, 128, 0, st>>>(IOD_MIX_ARGS);               \
+  } while (0)
+  if (p->K_total <= 8) { if (fused) IOD_MIX(8, true); else IOD_MIX(8, false); }
+  else { if (fused) IOD_MIX(16, true); else IOD_MIX(16, false); }
+#undef IOD_MIX
+#undef IOD_MIX_ARGS
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -375,9 +632,69 @@ __global__ void export_aux_kernel(const float* __restrict__ enc20, const uint16_
   }
 }
 
+// tests only, fused aux path: the 17 channels as refine_l0f_kernel's producers build them (same arithmetic, same
+// 16-bit rounding) from mixture_kernel<FUSED>'s output
+__global__ void export_aux_fused_kernel(const uint4* __restrict__ pl0, const float4* __restrict__ raw4,
+                                        const float2* __restrict__ raw2, const float* __restrict__ lik,
+                                        const double* __restrict__ stats, const float* __restrict__ xin,
+                                        float* __restrict__ aux_out, int BK, int K, int H, int W, int M, int L4,
+                                        int layernorm, int f16) {
+  const int HW = H * W;
+  const size_t total = (size_t)BK * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pix = i % HW, n = i / HW;
+    float mu[4], is[4];
+    for (int g = 0; g < 4; ++g) {
+      mu[g] = 0.f; is[g] = 1.f;
+      if (layernorm) {
+        const double cnt = (g == 0) ? 3.0 * HW : (double)HW;
+        const double m = stats[((size_t)n * 4 + g) * 2] / cnt;
+        double var = stats[((size_t)n * 4 + g) * 2 + 1] / cnt - m * m;
+        if (var < 0.0) var = 0.0;
+        mu[g] = (float)m;
+        is[g] = 1.f / ((float)sqrt(var) + 1e-5f);
+      }
+    }
+    const uint4 a = pl0[i];
+    const float4 r4 = raw4[i];
+    const float2 r2 = raw2[i];
+    const float lk = lik[(size_t)(n / K) * HW + pix];
+    uint4 o1;
+    o1.x = pack_h2(r4.x, (r4.y - mu[0]) * is[0], f16);
+    o1.y = pack_h2((r4.z - mu[0]) * is[0], (r4.w - mu[0]) * is[0], f16);
+    o1.z = pack_h2((r2.x - mu[1]) * is[1], (lk - mu[2]) * is[2], f16);
+    o1.w = pack_h2((r2.y - mu[3]) * is[3], 0.f, f16);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, o1.x, o1.y, o1.z, o1.w};
+    float* o = aux_out + (size_t)n * 17 * HW + pix;
+    for (int q = 0; q < 8; ++q) {
+      const float2 v = unpack_h2(w[q], f16);
+      o[(size_t)(2 * q) * HW] = v.x;
+      if (2 * q + 1 < 15) o[(size_t)(2 * q + 1) * HW] = v.y;
+    }
+    const int yy = pix / W, xx = pix % W;
+    o[(size_t)15 * HW] = (W > 1) ? -1.f + 2.f * (float)xx / (float)(W - 1) : -1.f;
+    o[(size_t)16 * HW] = (H > 1) ? -1.f + 2.f * (float)yy / (float)(H - 1) : -1.f;
+  }
+  const size_t base = (size_t)BK * 17 * HW;
+  const size_t tl = (size_t)BK * L4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tl; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = i / L4, j = i % L4;
+    aux_out[base + i] = xin[(size_t)n * (M + L4) + M + j];
+  }
+}
+
 int launch_export_aux(Plan* p, const float* x, float* aux_out, cudaStream_t st) {
   (void)x;
   const bool rtc = rtc_enabled(p);
+  if (rtc_fused_aux(p)) {
+    const size_t nsp = (size_t)p->BK * p->HW;
+    export_aux_fused_kernel<<<p->num_sms * 4, 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(p->auxs), reinterpret_cast<const float4*>(p->auxs) + nsp,
+        reinterpret_cast<const float2*>(p->auxs) + 4 * nsp, p->lik, p->stats, p->xin, aux_out, p->BK, p->s.K, p->s.H,
+        p->s.W, p->M, 4 * p->s.L, p->s.layernorm, half_is_f16(p));
+    IOD_LAUNCH_CHECK(p);
+    return 0;
+  }
   export_aux_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->enc20, rtc ? reinterpret_cast<const uint16_t*>(p->enc16) : nullptr,
                                                     p->xin, aux_out, p->BK, p->s.H, p->s.W, p->M, 4 * p->s.L,
                                                     half_is_f16(p));

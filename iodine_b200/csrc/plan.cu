@@ -46,7 +46,7 @@ static size_t carve(Plan* p, char* base) {
   p->auxs = (float*)take(BK * HW * 12 * sizeof(float));
   const bool rtc = rtc_enabled(p);
   p->enc20 = (float*)take(rtc ? 1024 : BK * HW * 20 * sizeof(float));
-  p->enc16 = take(rtc ? BK * HW * 32 : 1024);
+  p->enc16 = take(rtc && !rtc_fused_aux(p) ? BK * HW * 32 : 1024);
   p->lik = (float*)take((size_t)s.B * HW * sizeof(float));
   size_t r0 = (size_t)p->ref_h[1] * p->ref_w[1] * Cr;
   size_t r1 = s.ref_layers > 1 ? (size_t)p->ref_h[2] * p->ref_w[2] * Cr : 256;
@@ -59,6 +59,7 @@ static size_t carve(Plan* p, char* base) {
   p->G = (float*)take(BK * p->n_class * C * sizeof(float));
   p->dz = (float*)take(BK * L * sizeof(float));
   p->stats = (double*)take(BK * 8 * sizeof(double));
+  p->lnp = (float*)take(BK * 8 * sizeof(float));
   p->accum = (double*)take(2 * sizeof(double));
   p->pool = (float*)take(BK * Cr * sizeof(float));
   p->xin = (float*)take(BK * (M + 4 * L) * sizeof(float));
@@ -173,12 +174,12 @@ static int decoder_dgrad(Plan* p, cudaStream_t st) {
 static int refine_step(Plan* p, const float* x, const float* eps_t, float* mu, float* lv, float* h,
                        float* c, float* terms_out, float* aux_out, cudaStream_t st, bool log_image0 = true) {
   if (decoder_forward(p, mu, lv, eps_t, nullptr, st)) return 1;
-  if (launch_mixture(p, x, true, st)) return 1;
+  if (launch_mixture(p, x, true, st, rtc_fused_aux(p))) return 1;
   if (log_image0 && launch_recombine(p, p->log_pred, p->log_mask, p->log_mean, 1, st)) return 1;   // what elbo() hands the logger
   if (decoder_dgrad(p, st)) return 1;
   if (launch_post_grads(p, mu, lv, eps_t, nullptr, st)) return 1;
   if (rtc_enabled(p)) {
-    if (launch_assemble16(p, x, st)) return 1;
+    if (!rtc_fused_aux(p) && launch_assemble16(p, x, st)) return 1;   // fused: layer 0 assembles its own operand
     if (rtc_launch_refine_convs(p, st)) return 1;
   } else {
     if (launch_assemble(p, x, st)) return 1;

@@ -283,6 +283,341 @@ __global__ void __launch_bounds__(rtc_threads(N), 1) refine_tc_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Layer 0 with the aux-input assembly fused into its operand load (stride 2, 3x3, even image sizes).
+//
+// mixture_kernel<.., FUSED> leaves the refinement input as it can know it while its grid is still running: channels
+// 0-7 final (16-bit plane `pl0`), mask-posterior and the five layer-normalised channels raw in fp32 (`raw4`, `raw2`,
+// per-image `lik`) next to the f64 sums of their layer-norms (get_input_encoding, iodine.py:277-340; layernorm
+// 376-395; post_grads_kernel turns the sums into (mean, 1 / (std + 1e-5)) per slot).  This kernel finishes the assembly on the way into shared memory -- there is no assembled tensor in HBM
+// and no separate pass -- and replaces the 16-byte gather of refine_tc_kernel for this layer:
+//   * a work item is TR output rows x Wseg output columns of one slot-image.  One producer warp per input row copies
+//     the item's (2 TR + 1) x (2 Wseg + 1) input pixels ONCE, coalesced, with cp.async into a staging buffer (the
+//     gather read every pixel 2.25 times), one whole item ahead of its use; the same threads then apply
+//     (v - mean) / (std + 1e-5) from the slot's sums, pack to 16 bits and store each pixel into one of four PHASE
+//     planes (row parity x column parity) of the item's operand buffer, pitch P = Wseg + 8 positions, one zero halo
+//     position on the left;
+//   * in phase space a stride-2 tap is a unit-stride run: tap (dy, dx) of output (r, c) is position (r + [dy == 2]) P
+//     + c + (dx == 0 ? 7 : 8) of plane (dy != 1, dx != 1).  So, as in conv_tc.cu, 128 consecutive flat positions
+//     r P + c are directly a K-major no-swizzle UMMA operand (K = 16: channels 0-7 | 8-14 + one zero) and a tile is
+//     9 tcgen05.mma (M = 128, N = Cr); outputs at c >= Wseg are discarded; the last tile of an item starts at
+//     th P - 128 (overlapping its predecessor) so that no tile reads past the item's rows;
+//   * two operand buffers: the producers fill one while the tensor core reads the other; 8 TMEM accumulator stages;
+//     the epilogue (bias + coordinate-channel table, ELU, 16-bit chunk-planar store) is refine_tc_kernel's.
+// ------------------------------------------------------------------------------------------------
+constexpr int L0F_PROD_WARPS = 9;
+constexpr int L0F_ACC = 8;
+__host__ __device__ constexpr int l0f_threads(int N) { return 32 * (L0F_PROD_WARPS + 1 + rtc_epi_warps(N)); }
+
+struct L0fParams {
+  const uint4* pl0;      // [n][H][W] channels 0-7, final 16-bit
+  const float4* raw4;    // [n][H][W] mask_posterior | dJ/dmean rgb
+  const float2* raw2;    // [n][H][W] dJ/dmask | leave-one-out likelihood
+  const float* lik;      // [b][H][W] pixel likelihood
+  const float* lnp;      // [n][8] layer-norm parameters of grad_means, grad_mask, likelihood, leave-one-out:
+                         // 4 means, 4 x 1 / (std + 1e-5) (finalised per slot by post_grads_kernel, head.cu)
+  uint4* out;            // chunk-planar [n][N/8][Ho][Wo]
+  const void* wimg;      // [tap][k-half][n][8] 16-bit
+  const float* rowtab;   // [Ho][2][N] bias + convolution of the y-coordinate channel (index 0: output column 0, whose
+                         // left taps fall into the padding; 1: every other column)
+  uint32_t w_bytes;
+  int32_t H, W, Ho, Wo, K;
+  int32_t TR, Wseg, P, nseg, strips, items;
+  uint32_t magicP;       // 2^32 / P + 1: pos / P = umulhi(pos, magicP) for the flat positions of an item
+  float xc_step;         // 2 / (W - 1): x-coordinate channel value of image column ix = -1 + ix * xc_step
+  uint32_t lbo16;        // 16-byte units between the two channel planes of a phase
+  uint32_t buf16;        // 8 * lbo16: 16-byte units per operand buffer (4 phases x 2 channel planes)
+  uint32_t stage_bytes;  // one staging buffer: (2 TR + 1) rows x (2 Wseg + 1) pixels x 44 bytes, rounded up to 128
+  uint32_t idesc;
+};
+
+struct L0fSmem {
+  uint64_t full[2];
+  uint64_t empty[2];
+  uint64_t tfull[L0F_ACC];
+  uint64_t tempty[L0F_ACC];
+  uint64_t wbar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void cp_async_ca(uint32_t dst, const void* src, int bytes /* 4 or 8 */) {
+  if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int N, bool F16>
+__global__ void __launch_bounds__(l0f_threads(N), 1) refine_l0f_kernel(const __grid_constant__ L0fParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int TMEM_COLS = (L0F_ACC * N < 32) ? 32 : L0F_ACC * N;
+  constexpr int EW = rtc_epi_warps(N);
+  const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
+  uint8_t* s_w = smem;
+  uint8_t* s_a = smem + w_region;
+  uint8_t* s_stage = s_a + (size_t)2 * p.buf16 * 16u;
+  L0fSmem* sb = reinterpret_cast<L0fSmem*>(s_stage + (size_t)2 * p.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = p.P, TR = p.TR;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&sb->full[i]), 32 * L0F_PROD_WARPS);   // every producer thread arrives
+      mbar_init(smem_u32(&sb->empty[i]), 1);                     // tcgen05.commit
+    }
+    for (int i = 0; i < L0F_ACC; ++i) {
+      mbar_init(smem_u32(&sb->tfull[i]), 1);
+      mbar_init(smem_u32(&sb->tempty[i]), EW);
+    }
+    mbar_init(smem_u32(&sb->wbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == L0F_PROD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sb->tmem_base)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // both operand buffers start as zeros: positions no producer ever writes (halo padding left of position 7, rows of
+  // a short last strip) feed discarded outputs only, but must not hold NaN patterns next to real operands
+  {
+    uint4* a4 = reinterpret_cast<uint4*>(s_a);
+    const int n16 = 2 * (int)p.buf16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sb->tmem_base;
+  const int HWo = p.Ho * p.Wo, HW = p.H * p.W;
+  const int per_img = p.strips * p.nseg;
+
+  // item -> (slot-image n, first output row y0, rows th, first output column xoff, columns wv)
+  auto decode = [&](int item, int& n, int& y0, int& th, int& xoff, int& wv) {
+    n = item / per_img;
+    const int r = item - n * per_img;
+    const int strip = r / p.nseg, seg = r - strip * p.nseg;
+    y0 = strip * TR;
+    th = (p.Ho - y0 < TR) ? p.Ho - y0 : TR;
+    xoff = seg * p.Wseg;
+    wv = (p.Wo - xoff < p.Wseg) ? p.Wo - xoff : p.Wseg;
+  };
+  // first flat position of tile t of an item with th rows (nt tiles): the last one is pulled back inside the item
+  auto tile_pos0 = [&](int t, int nt, int th) -> int {
+    if (t + 1 < nt || nt == 1) return t * 128;
+    return th * P - 128;
+  };
+
+  if (warp < L0F_PROD_WARPS) {
+    // =============================================================== producers: copy ahead, normalise, pack, phase-split
+    const uint32_t a_base = smem_u32(s_a), st_base = smem_u32(s_stage);
+    const uint32_t lbo_b = p.lbo16 * 16u, buf_b = p.buf16 * 16u;
+    const int NCP = 2 * p.Wseg + 1;               // staged pixels per row: index 0 = the halo column 2 xoff - 1
+    const int rows_max = 2 * TR + 1;
+    const uint32_t o_pl0 = 0u, o_r4 = (uint32_t)(rows_max * NCP) * 16u, o_r2 = 2u * o_r4, o_lk = o_r2 + (uint32_t)(rows_max * NCP) * 8u;
+    // staged copy of one item: every thread copies exactly the pixels it converts later (row = warp, columns = lane + 32 u;
+    // lane 0 also the halo column), so its own cp.async.wait_group is all the synchronisation the staging needs
+    auto prefetch = [&](int item, int sbuf) {
+      int n, y0, th, xoff, wv;
+      decode(item, n, y0, th, xoff, wv);
+      const uint4* pl0 = p.pl0 + (size_t)n * HW;
+      const float4* raw4 = p.raw4 + (size_t)n * HW;
+      const float2* raw2 = p.raw2 + (size_t)n * HW;
+      const float* lik = p.lik + (size_t)(n / p.K) * HW;
+      const int nrows = 2 * th + 1, ncols = 2 * wv;
+      const uint32_t sbase = st_base + (uint32_t)sbuf * p.stage_bytes;
+      for (int lr = warp; lr < nrows; lr += L0F_PROD_WARPS) {
+        const int iy = 2 * y0 - 1 + lr;
+        if (iy < 0 || iy >= p.H) continue;
+        const size_t rofs = (size_t)iy * p.W + 2 * xoff;
+        auto stage_px = [&](int c) {              // c = input column relative to 2 xoff (-1: the halo column)
+          const uint32_t idx = (uint32_t)(lr * NCP + c + 1);
+          cp_async16(sbase + o_pl0 + idx * 16u, pl0 + rofs + c, 16u);
+          cp_async16(sbase + o_r4 + idx * 16u, raw4 + rofs + c, 16u);
+          cp_async_ca(sbase + o_r2 + idx * 8u, raw2 + rofs + c, 8);
+          cp_async_ca(sbase + o_lk + idx * 4u, lik + rofs + c, 4);
+        };
+        for (int lc = lane; lc < ncols; lc += 32) stage_px(lc);
+        if (lane == 0 && xoff > 0) stage_px(-1);
+      }
+    };
+    int buf = 0;
+    uint32_t ph = 0;
+    int sbuf = 0;
+    if ((int)blockIdx.x < p.items) prefetch(blockIdx.x, 0);
+    cp_async_commit();
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int nxt = item + (int)gridDim.x;
+      if (nxt < p.items) prefetch(nxt, sbuf ^ 1);
+      cp_async_commit();
+      int n, y0, th, xoff, wv;
+      decode(item, n, y0, th, xoff, wv);
+      const float4 mu4 = __ldg(reinterpret_cast<const float4*>(p.lnp) + (size_t)n * 2);
+      const float4 is4 = __ldg(reinterpret_cast<const float4*>(p.lnp) + (size_t)n * 2 + 1);
+      const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, is[4] = {is4.x, is4.y, is4.z, is4.w};
+      cp_async_wait<1>();                           // this item's copies (the group before the one just committed)
+      mbar_wait(smem_u32(&sb->empty[buf]), ph ^ 1u, 21);
+      const uint32_t bbase = a_base + (uint32_t)buf * buf_b;
+      const uint32_t sbase = st_base + (uint32_t)sbuf * p.stage_bytes;
+      const int nrows = 2 * th + 1, ncols = 2 * wv;
+      for (int lr = warp; lr < nrows; lr += L0F_PROD_WARPS) {
+        const int iy = 2 * y0 - 1 + lr;
+        const bool row_in = iy >= 0 && iy < p.H;
+        // local input row lr: even -> odd image row (phase py = 1, plane row lr / 2), odd -> even image row
+        const int py = (lr & 1) ^ 1, prow = lr >> 1;
+        const uint32_t rbase = bbase + (uint32_t)(py * 2) * 2u * lbo_b + (uint32_t)(prow * P) * 16u;
+        auto emit = [&](int c) {                    // c = input column relative to 2 xoff (-1: the halo column)
+          const bool inside = row_in && (c >= 0 || xoff > 0);
+          uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
+          if (inside) {
+            const uint32_t idx = (uint32_t)(lr * NCP + c + 1);
+            float4 r4; float2 r2; float lk;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o0.x), "=r"(o0.y), "=r"(o0.z), "=r"(o0.w) : "r"(sbase + o_pl0 + idx * 16u));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w) : "r"(sbase + o_r4 + idx * 16u));
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r2.x), "=f"(r2.y) : "r"(sbase + o_r2 + idx * 8u));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lk) : "r"(sbase + o_lk + idx * 4u));
+            o1.x = pack_h2(r4.x, (r4.y - mu[0]) * is[0], F16);
+            o1.y = pack_h2((r4.z - mu[0]) * is[0], (r4.w - mu[0]) * is[0], F16);
+            o1.z = pack_h2((r2.x - mu[1]) * is[1], (lk - mu[2]) * is[2], F16);
+            // channel 15: the x-coordinate plane (iodine.py:334-339) rides in the operand's spare slot; the y-coordinate
+            // plane's convolution only depends on the output row (and on whether the left taps are padding): rowtab
+            o1.w = pack_h2((r2.y - mu[3]) * is[3], fmaf((float)(2 * xoff + c), p.xc_step, -1.f), F16);
+          }
+          // even columns -> phase px = 0, odd -> px = 1; column 2 j (+1) sits at position j + 8, the halo at 7
+          const int px = c & 1, pos = ((c + 1) >> 1) + 7 + (px ^ 1);
+          const uint32_t dst = rbase + (uint32_t)px * 2u * lbo_b + (uint32_t)pos * 16u;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o0.x), "r"(o0.y), "r"(o0.z), "r"(o0.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + lbo_b), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w) : "memory");
+        };
+        for (int lc = lane; lc < ncols; lc += 32) emit(lc);
+        if (lane == 0) emit(-1);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(smem_u32(&sb->full[buf]));
+      buf ^= 1;
+      if (buf == 0) ph ^= 1u;
+      sbuf ^= 1;
+    }
+    cp_async_wait<0>();
+  } else if (warp == L0F_PROD_WARPS) {
+    // =============================================================== MMA issuer (+ weight load)
+    if (lane == 0) {
+      const uint32_t wbar = smem_u32(&sb->wbar);
+      mbar_expect_tx(wbar, p.w_bytes);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg);
+      for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
+        const uint32_t nb = (p.w_bytes - off < 16384u) ? (p.w_bytes - off) : 16384u;
+        bulk_load_1d(smem_u32(s_w + off), src + off, nb, wbar);
+      }
+      mbar_wait(wbar, 0, 22);
+      constexpr uint64_t DESC_HI = (uint64_t)(8u | (1u << 14)) << 32;      // SBO = 128 B, version 1
+      const uint32_t a16 = (smem_u32(s_a) >> 4) | (p.lbo16 << 16);         // LBO = channel-plane stride
+      const uint32_t w16 = (smem_u32(s_w) >> 4) | ((uint32_t)N << 16);     // LBO = N (16-byte units)
+      int buf = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t aph = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int n, y0, th, xoff, wv;
+        decode(item, n, y0, th, xoff, wv);
+        const int nt = (th * P + 127) >> 7;
+        mbar_wait(smem_u32(&sb->full[buf]), ph, 23);
+        tc_fence_after();
+        const uint32_t ab = a16 + (uint32_t)buf * p.buf16;
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(smem_u32(&sb->tempty[acc]), aph ^ 1u, 24);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+          const uint32_t t0 = (uint32_t)tile_pos0(t, nt, th);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+            const uint32_t phase = (uint32_t)((dy != 1) * 2 + (dx != 1));
+            const uint32_t off = phase * 2u * p.lbo16 + (uint32_t)((dy == 2) * P + (dx == 0 ? 7 : 8)) + t0;
+            tc_mma_bf16(d_tmem, DESC_HI | (ab + off), DESC_HI | (w16 + (uint32_t)(tap * 2 * N)), p.idesc, tap ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&sb->tfull[acc]));
+          if (++acc == L0F_ACC) { acc = 0; aph ^= 1u; }
+        }
+        tc_commit(smem_u32(&sb->empty[buf]));
+        buf ^= 1;
+        if (buf == 0) ph ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================================== epilogue warps
+    constexpr int NC = (EW == 8) ? N / 2 : N;      // accumulator columns per warp
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int col0 = (EW == 8) ? ((warp - (L0F_PROD_WARPS + 1)) / 4) * NC : 0;
+    int acc = 0; uint32_t aph = 0;
+    // (item, tile) walker
+    int item = blockIdx.x, t = 0, nt = 0, n = 0, y0 = 0, th = 0, xoff = 0, wv = 0;
+    auto load_item = [&]() {
+      if (item < p.items) { decode(item, n, y0, th, xoff, wv); nt = (th * P + 127) >> 7; }
+      t = 0;
+    };
+    // this thread's output of the current tile: the positions a pulled-back last tile shares with its predecessor
+    // are left to the predecessor (whole warps of the last tile then have nothing to do)
+    auto locate = [&](bool& valid, int& oy, int& ox) {
+      valid = false; oy = 0; ox = 0;
+      if (item >= p.items) return;
+      const int pos = tile_pos0(t, nt, th) + quad * 32 + lane;
+      const int r = (int)__umulhi((uint32_t)pos, p.magicP), c = pos - r * P;
+      valid = r < th && c < wv && (t == 0 || pos >= t * 128);
+      oy = y0 + r; ox = xoff + c;
+    };
+    auto advance = [&]() { if (++t >= nt) { item += gridDim.x; load_item(); } };
+    load_item();
+    while (item < p.items) {
+      bool valid; int oy, ox;
+      locate(valid, oy, ox);
+      const int on = n;
+      // bias + y-coordinate table row of this output: requested before the accumulator wait (L1-resident, the lanes
+      // of a warp share one or two rows)
+      float4 tb[NC / 4];
+      {
+        const float4* bp = reinterpret_cast<const float4*>(p.rowtab + ((size_t)(oy * 2 + (ox > 0 ? 1 : 0)) * N + col0));
+#pragma unroll
+        for (int k = 0; k < NC / 4; ++k) tb[k] = __ldg(bp + k);
+      }
+      mbar_wait(smem_u32(&sb->tfull[acc]), aph, 25);
+      tc_fence_after();
+      uint32_t v[NC];
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * N + col0) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+      for (int q = 0; q < NC / 16; ++q) IOD_TMEM_LD16((v + q * 16), taddr + q * 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[acc]));
+      if (valid) {
+        uint4* op = p.out + ((size_t)on * (N / 8) + (col0 >> 3)) * HWo + (size_t)oy * p.Wo + ox;
+#pragma unroll
+        for (int k = 0; k < NC / 8; ++k) {
+          float f[8];
+          const float4 b0 = tb[2 * k], b1 = tb[2 * k + 1];
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = elu_fast(__uint_as_float(v[k * 8 + e]) + bb[e]);
+          uint4 o;
+          o.x = pack_h2(f[0], f[1], F16);
+          o.y = pack_h2(f[2], f[3], F16);
+          o.z = pack_h2(f[4], f[5], F16);
+          o.w = pack_h2(f[6], f[7], F16);
+          op[(size_t)k * HWo] = o;
+        }
+      }
+      advance();
+      if (++acc == L0F_ACC) { acc = 0; aph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == L0F_PROD_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct RtcState {
@@ -290,7 +625,12 @@ struct RtcState {
   uint32_t w_bytes[IODINE_MAX_LAYERS];
   int cin[IODINE_MAX_LAYERS];         // contracted channels per layer (16 for layer 0, Cr after)
   float* tab0 = nullptr;              // [H1*W1][Cr] layer-0 bias + coordinate-channel table
+  float* rowtab = nullptr;            // [H1][2][Cr] fused layer 0: bias + y-coordinate-channel table
   bool ok = false;
+  bool fused = false;                 // layer 0 = refine_l0f_kernel (reads mixture_kernel<FUSED>'s output directly)
+  int f_TR = 0, f_Wseg = 0, f_P = 0, f_nseg = 0, f_strips = 0;
+  uint32_t f_lbo16 = 0, f_stage = 0;
+  size_t f_smem = 0;
 };
 
 static RtcState* rtc_state(Plan* p) { return reinterpret_cast<RtcState*>(p->rtc); }
@@ -324,12 +664,42 @@ int rtc_supported(const Plan* p) {
   return 1;
 }
 
+// Geometry of the fused layer 0 (refine_l0f_kernel): stride 2, 3x3, even image sizes.  TR output rows per work item:
+// as many as two buffers of (2 TR + 1) input rows allow, fewer when the launch would otherwise leave SMs without work.
+static bool l0f_geometry(const Plan* p, RtcState* st) {
+  const IodineShape& s = p->s;
+  if (getenv("IODINE_NO_AUX_FUSE")) return false;
+  if (s.ref_k != 3 || s.ref_stride != 2 || (s.H & 1) || (s.W & 1) || s.H < 4 || s.W < 4) return false;
+  const int Ho = p->ref_h[1], Wo = p->ref_w[1];
+  if (Ho != s.H / 2 || Wo != s.W / 2) return false;
+  const int Wseg = Wo < 64 ? Wo : 64;
+  const int nseg = (Wo + Wseg - 1) / Wseg, P = Wseg + 8;
+  const uint32_t w_bytes = 9u * 2u * (uint32_t)p->Cr * 16u;
+  for (int TR = 8; TR >= 1; TR >>= 1) {
+    if (TR > Ho && TR > 1) continue;
+    const int need = ((TR + 1) * P + 8 > P + 136) ? (TR + 1) * P + 8 : P + 136;   // see tile_pos0: no tile reads past it
+    const uint32_t lbo16 = (uint32_t)((need + 7) / 8 * 8);
+    const uint32_t stage = (uint32_t)(((2 * TR + 1) * (2 * Wseg + 1) * 44 + 127) / 128 * 128);
+    const size_t smem = (size_t)((w_bytes + 1023u) & ~1023u) + (size_t)2 * 8 * lbo16 * 16 + (size_t)2 * stage +
+                        sizeof(L0fSmem) + 64;
+    const int strips = (Ho + TR - 1) / TR;
+    const long long items = (long long)p->BK * strips * nseg;
+    if (smem > (size_t)227 * 1024 || lbo16 >= 16384u) continue;
+    if (items < 2LL * p->num_sms && TR > 1) continue;     // small problems: more, smaller items
+    st->f_TR = TR; st->f_Wseg = Wseg; st->f_P = P; st->f_nseg = nseg; st->f_strips = strips;
+    st->f_lbo16 = lbo16; st->f_stage = stage; st->f_smem = smem;
+    return true;
+  }
+  return false;
+}
+
 int rtc_alloc(Plan* p) {
   RtcState* st = new RtcState();
   p->rtc = st;
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) { st->w[l] = nullptr; st->w_bytes[l] = 0; st->cin[l] = 0; }
   st->ok = rtc_supported(p) != 0;
   if (!st->ok) return 0;
+  st->fused = l0f_geometry(p, st);
   const IodineShape& s = p->s;
   const int Cr = p->Cr, kk = s.ref_k * s.ref_k;
   for (int l = 0; l < s.ref_layers; ++l) {
@@ -338,6 +708,7 @@ int rtc_alloc(Plan* p) {
     IOD_CHECK_CUDA(cudaMalloc((void**)&st->w[l], st->w_bytes[l]));
   }
   IOD_CHECK_CUDA(cudaMalloc((void**)&st->tab0, (size_t)p->ref_h[1] * p->ref_w[1] * Cr * sizeof(float)));
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->rowtab, (size_t)p->ref_h[1] * 2 * Cr * sizeof(float)));
   return 0;
 }
 
@@ -346,6 +717,7 @@ void rtc_free(Plan* p) {
   if (!st) return;
   for (int l = 0; l < IODINE_MAX_LAYERS; ++l) cudaFree(st->w[l]);
   cudaFree(st->tab0);
+  cudaFree(st->rowtab);
   delete st;
   p->rtc = nullptr;
 }
@@ -353,6 +725,10 @@ void rtc_free(Plan* p) {
 bool rtc_enabled(const Plan* p) {
   const RtcState* st = reinterpret_cast<const RtcState*>(p->rtc);
   return st && st->ok;
+}
+bool rtc_fused_aux(const Plan* p) {
+  const RtcState* st = reinterpret_cast<const RtcState*>(p->rtc);
+  return st && st->ok && st->fused;
 }
 
 // weight image [tap][ks][k-half][n][8]; w is OIHW [Cr][CI][k][k], only input channels < cin_real are used
@@ -393,14 +769,39 @@ __global__ void rtc_tab0_kernel(const float* __restrict__ w, const float* __rest
   }
 }
 
+// fused layer 0: rowtab[y][xc][co] = bias[co] + zero-padded stride-2 conv of the y-coordinate plane (input channel 16)
+// at output row y; xc = 0: output column 0 (taps dx < pad fall into the padding), xc = 1: any other column (even image
+// sizes: no tap leaves the image on the right / bottom).  The x-coordinate plane (channel 15) is a real operand channel.
+__global__ void rtc_rowtab_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ tab,
+                                  int Cr, int KS, int S, int H, int Ho) {
+  const int P = KS / 2;
+  const int total = Ho * 2 * Cr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % Cr, xc = (i / Cr) % 2, y = i / (2 * Cr);
+    float s = b[co];
+    for (int dy = 0; dy < KS; ++dy) {
+      const int iy = y * S + dy - P;
+      if (iy < 0 || iy >= H) continue;
+      const float cyv = (H > 1) ? -1.f + 2.f * (float)iy / (float)(H - 1) : -1.f;
+      for (int dx = (xc == 0 ? P : 0); dx < KS; ++dx) s += w[(((size_t)co * 17 + 16) * KS + dy) * KS + dx] * cyv;
+    }
+    tab[i] = s;
+  }
+}
+
 int rtc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
   RtcState* st = rtc_state(p);
   if (!st || !st->ok) return 0;
   const IodineShape& s = p->s;
   const int Cr = p->Cr, f16 = half_is_f16(p);
   for (int l = 0; l < s.ref_layers; ++l) {
-    rtc_pack_kernel<<<32, 256, 0, st_>>>(w->ref_w[l], st->w[l], Cr, l == 0 ? 17 : Cr, l == 0 ? 15 : Cr, st->cin[l], s.ref_k,
-                                         f16);
+    // layer 0 contracts the 15 data channels; the fused kernel also takes the x-coordinate plane (channel 15) as data
+    rtc_pack_kernel<<<32, 256, 0, st_>>>(w->ref_w[l], st->w[l], Cr, l == 0 ? 17 : Cr, l == 0 ? (st->fused ? 16 : 15) : Cr,
+                                         st->cin[l], s.ref_k, f16);
+    IOD_LAUNCH_CHECK(p);
+  }
+  if (st->fused) {
+    rtc_rowtab_kernel<<<32, 256, 0, st_>>>(w->ref_w[0], w->ref_b[0], st->rowtab, Cr, s.ref_k, s.ref_stride, s.H, p->ref_h[1]);
     IOD_LAUNCH_CHECK(p);
   }
   rtc_tab0_kernel<<<128, 256, 0, st_>>>(w->ref_w[0], w->ref_b[0], st->tab0, Cr, s.ref_k, s.ref_stride, s.H, s.W, p->ref_h[1],
@@ -441,13 +842,65 @@ __global__ void rtc_pool_kernel(const uint4* __restrict__ in, float* __restrict_
   }
 }
 
-// All refine conv layers on the tensor cores: enc16 (assemble16, mixture.cu) -> ... -> pool[BK][Cr]
+template <int N, bool F16>
+static int l0f_launch_t(Plan* p, const L0fParams& q, size_t smem, cudaStream_t st_) {
+  auto kern = refine_l0f_kernel<N, F16>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    IOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  const int grid = q.items < p->num_sms ? q.items : p->num_sms;
+  kern<<<grid, l0f_threads(N), smem, st_>>>(q);
+  IOD_LAUNCH_CHECK(p);
+  return 0;
+}
+
+// layer 0 straight from mixture_kernel<FUSED>'s output (p->auxs holds pl0 | raw4 | raw2) -> r16[0]
+static int l0f_launch(Plan* p, cudaStream_t st_) {
+  RtcState* st = rtc_state(p);
+  const IodineShape& s = p->s;
+  const size_t nsp = (size_t)p->BK * p->HW;
+  L0fParams q;
+  q.pl0 = reinterpret_cast<const uint4*>(p->auxs);
+  q.raw4 = reinterpret_cast<const float4*>(p->auxs) + nsp;
+  q.raw2 = reinterpret_cast<const float2*>(p->auxs) + 4 * nsp;
+  q.lik = p->lik;
+  q.lnp = p->lnp;
+  q.out = reinterpret_cast<uint4*>(p->r16[0]);
+  q.wimg = st->w[0];
+  q.rowtab = st->rowtab;
+  q.w_bytes = st->w_bytes[0];
+  q.H = s.H; q.W = s.W; q.Ho = p->ref_h[1]; q.Wo = p->ref_w[1]; q.K = s.K;
+  q.TR = st->f_TR; q.Wseg = st->f_Wseg; q.P = st->f_P; q.nseg = st->f_nseg; q.strips = st->f_strips;
+  q.items = p->BK * st->f_strips * st->f_nseg;
+  q.magicP = (uint32_t)(0x100000000ull / (uint64_t)st->f_P) + 1u;
+  q.xc_step = s.W > 1 ? 2.f / (float)(s.W - 1) : 0.f;
+  const int f16 = half_is_f16(p);
+  q.lbo16 = st->f_lbo16; q.buf16 = 8u * st->f_lbo16; q.stage_bytes = st->f_stage;
+  const uint32_t fmt = f16 ? 0u : 1u;
+  q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p->Cr >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#define L0F_CASE(n) if (p->Cr == n) return f16 ? l0f_launch_t<n, true>(p, q, st->f_smem, st_) : l0f_launch_t<n, false>(p, q, st->f_smem, st_);
+  L0F_CASE(64) L0F_CASE(32) L0F_CASE(16)
+#undef L0F_CASE
+  set_error("refine_l0f: unsupported ref_chan=%d", p->Cr);
+  return 1;
+}
+
+// All refine conv layers on the tensor cores: the aux stack (fused: mixture_kernel's output; otherwise enc16 from
+// assemble16, mixture.cu) -> ... -> pool[BK][Cr]
 int rtc_launch_refine_convs(Plan* p, cudaStream_t st_) {
   RtcState* st = rtc_state(p);
   const IodineShape& s = p->s;
   const int Cr = p->Cr;
   const void* cur = p->enc16;
-  for (int l = 0; l < s.ref_layers; ++l) {
+  int l_first = 0;
+  if (st->fused) {
+    if (l0f_launch(p, st_)) return 1;
+    cur = p->r16[0];
+    l_first = 1;
+  }
+  for (int l = l_first; l < s.ref_layers; ++l) {
     RtcParams q;
     q.in = reinterpret_cast<const uint4*>(cur);
     q.out = reinterpret_cast<uint4*>(p->r16[l & 1]);
