@@ -67,7 +67,8 @@ struct alignas(64) TcParams {
   TcMaps maps;
   int32_t f16;                    // 1: IEEE half operands, 0: bfloat16
   int32_t dbg;                    // IODINE_TC_DEBUG bit mask (timing experiments only; results are wrong when set):
-                                  // 1 no TMEM reads, 2 no epilogue stores, 4 no TMA (generic producer), 8 no activation loads
+                                  // 1 no TMEM reads, 2 no epilogue stores, 4 no TMA (generic producer), 8 no activation loads,
+                                  // 16 no input rows (row-streaming producers)
   int32_t nch_in;                 // input planes
   int32_t nch_out;                // output planes of the whole layer (all channel splits)
   int32_t n_tot;                  // output channels of the whole layer
@@ -400,6 +401,11 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
               if (++slot2 == R) { slot2 = 0; phase2 ^= 1u; }
             }
             ++g_row;
+            if (p.dbg & 16) {                      // timing experiment: no input traffic at all (the ring keeps its zeros)
+              mbar_arrive(fb);
+              if (++slot == R) { slot = 0; phase ^= 1u; }
+              continue;
+            }
             mbar_expect_tx(fb, per_plane * (uint32_t)(c_hi - c_lo));              // (arrives even with no plane)
             const int y = y0 - pad + j;
             const bool inside = y >= 0 && y < p.H;

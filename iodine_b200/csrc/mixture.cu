@@ -278,52 +278,59 @@ __device__ __forceinline__ float lg2_fast(float x) { float l; asm("lg2.approx.f3
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_sub(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-template <int KMAX, bool FUSED>
+// F16: IEEE half (else bfloat16) for the 16-bit outputs (pl0; the seeds when seed_half != 0)
+template <int KMAX, bool FUSED, bool F16>
 __global__ void __launch_bounds__(128)
 mixture_fast_kernel(const float* __restrict__ out4, const float* __restrict__ x,
                     float* __restrict__ seed4, float* __restrict__ auxs, float* __restrict__ lik,
                     double* __restrict__ stats, double* __restrict__ accum,
                     int K, int HW, float inv_2s2, float inv_s2, float ll_const, int want_grads,
-                    int seed_half, int Kl, int k_off, int ll_on, int f16, size_t n_slot_pix) {
+                    int seed_half, int Kl, int k_off, int ll_on, int /*f16*/, size_t n_slot_pix) {
   constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const int b = blockIdx.y, B = gridDim.y;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = pix < HW;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;   // HW is a multiple of the block size (launch_mixture): every thread owns a pixel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = 4;
 
   float mk[KMAX], mr[KMAX], mg[KMAX], mb[KMAX];     // mask, mean rgb
   float pr[KMAX], pg[KMAX], pb[KMAX];               // a_kc, then p_kc = exp(a_kc - max)
   float Lk[KMAX];                                   // exp(sum_c ll_kc), un-stabilised
-  float xr = 0.f, xg = 0.f, xb = 0.f;
-  if (live) {
-    xr = x[((size_t)b * 3 + 0) * HW + pix];
-    xg = x[((size_t)b * 3 + 1) * HW + pix];
-    xb = x[((size_t)b * 3 + 2) * HW + pix];
-  }
+  float lgr[KMAX];                                  // raw mask logits (an aux channel)
+  const float xr = x[((size_t)b * 3 + 0) * HW + pix];
+  const float xg = x[((size_t)b * 3 + 1) * HW + pix];
+  const float xb = x[((size_t)b * 3 + 2) * HW + pix];
+  // slot k of image b inside out4_all (out4_slot), stepped without divisions: + HW inside a rank's block of Kl slots,
+  // + (B Kl - Kl + 1) HW across the rank boundary; 32-bit float4 indices (BK HW < 2^32)
+  const float4* o4 = reinterpret_cast<const float4*>(out4) + pix;
+  const uint32_t so_first = (uint32_t)b * (uint32_t)Kl * (uint32_t)HW;
+  const uint32_t so_wrap = ((uint32_t)B * (uint32_t)Kl - (uint32_t)Kl + 1u) * (uint32_t)HW;
   float lmax = -INFINITY;
+  {
+  uint32_t so = so_first; int kk = 0;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    mk[k] = -INFINITY; mr[k] = mg[k] = mb[k] = 0.f; pr[k] = pg[k] = pb[k] = 0.f; Lk[k] = 0.f;
-    if (k < K && live) {
-      const float4 v = reinterpret_cast<const float4*>(out4)[out4_slot(b, k, B, Kl, HW) + pix];
+    mk[k] = -INFINITY; lgr[k] = 0.f; mr[k] = mg[k] = mb[k] = 0.f; pr[k] = pg[k] = pb[k] = 0.f; Lk[k] = 0.f;
+    if (k < K) {
+      const float4 v = o4[so];
+      if (++kk == Kl) { kk = 0; so += so_wrap; } else so += (uint32_t)HW;
       mr[k] = rcp_fast(1.f + ex2_ftz(-v.x * L2E));
       mg[k] = rcp_fast(1.f + ex2_ftz(-v.y * L2E));
       mb[k] = rcp_fast(1.f + ex2_ftz(-v.z * L2E));
-      mk[k] = v.w;
+      mk[k] = v.w; lgr[k] = v.w;
       lmax = fmaxf(lmax, v.w);
     }
+  }
   }
   float den = 0.f;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k)
-    if (k < K && live) { mk[k] = ex2_ftz((mk[k] - lmax) * L2E); den += mk[k]; }
-  const float inv_den = live ? rcp_fast(den) : 0.f;
+    if (k < K) { mk[k] = ex2_ftz((mk[k] - lmax) * L2E); den += mk[k]; }
+  const float inv_den = rcp_fast(den);
   float amax_r = -INFINITY, amax_g = -INFINITY, amax_b = -INFINITY;
   float kl_tot = 0.f, mkl_tot = 0.f;                 // sum_k L_k ; sum_k mask_k L_k
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    if (k < K && live) {
+    if (k < K) {
       mk[k] *= inv_den;                              // mask = softmax_K(logits)            (iodine.py:185)
       const float lm = lg2_fast(mk[k] + 1e-12f) * LN2;
       const float dr = xr - mr[k], dg = xg - mg[k], db = xb - mb[k];
@@ -339,18 +346,18 @@ mixture_fast_kernel(const float* __restrict__ out4, const float* __restrict__ x,
   float sr = 0.f, sg = 0.f, sb = 0.f;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    if (k < K && live) {
+    if (k < K) {
       pr[k] = ex2_ftz((pr[k] - amax_r) * L2E); sr += pr[k];
       pg[k] = ex2_ftz((pg[k] - amax_g) * L2E); sg += pg[k];
       pb[k] = ex2_ftz((pb[k] - amax_b) * L2E); sb += pb[k];
     }
   }
-  float ll_pix = 0.f;                                // sum_c logsumexp_k a_kc            (213-220)
-  if (live) ll_pix = (amax_r + lg2_fast(sr) * LN2) + (amax_g + lg2_fast(sg) * LN2) + (amax_b + lg2_fast(sb) * LN2);
+  const float ll_pix =                               // sum_c logsumexp_k a_kc            (213-220)
+      (amax_r + lg2_fast(sr) * LN2) + (amax_g + lg2_fast(sg) * LN2) + (amax_b + lg2_fast(sb) * LN2);
 
   __shared__ double red[NW];
   {
-    float v = warp_sum(live ? ll_pix : 0.f);
+    float v = warp_sum(ll_pix);
     if (lane == 0) red[warp] = (double)v;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -361,18 +368,16 @@ mixture_fast_kernel(const float* __restrict__ out4, const float* __restrict__ x,
   }
   if (!want_grads) return;
 
-  const float likv = live ? mix_exp<true>(ll_pix) : 0.f;       // exp(sum_c s_c)           (309-310)
-  if (live) lik[(size_t)b * HW + pix] = likv;
-  const float isr = live ? rcp_fast(sr) : 0.f, isg = live ? rcp_fast(sg) : 0.f, isb = live ? rcp_fast(sb) : 0.f;
-  float gm[KMAX];                                     // dJ/dmask_k = sum_c exp(ll_kc - s_c) = sum_c r_kc / (mask + 1e-12)
+  const float likv = mix_exp<true>(ll_pix);       // exp(sum_c s_c)           (309-310)
+  lik[(size_t)b * HW + pix] = likv;
+  const float isr = rcp_fast(sr), isg = rcp_fast(sg), isb = rcp_fast(sb);
+  // dJ/dmask_k = sum_c exp(ll_kc - s_c) = sum_c r_kc / (mask + 1e-12); recomputed per slot below rather than kept
   float mgsum = 0.f;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    gm[k] = 0.f;
-    if (k < K && live) {
+    if (k < K) {
       pr[k] *= isr; pg[k] *= isg; pb[k] *= isb;       // p now holds the responsibilities r_kc
-      gm[k] = (pr[k] + pg[k] + pb[k]) * rcp_fast(mk[k] + 1e-12f);
-      mgsum = fmaf(mk[k], gm[k], mgsum);
+      mgsum = fmaf(mk[k], (pr[k] + pg[k] + pb[k]) * rcp_fast(mk[k] + 1e-12f), mgsum);
     }
   }
   // mask_posterior denominators: one reciprocal, operands pre-scaled out of the subnormals
@@ -384,6 +389,10 @@ mixture_fast_kernel(const float* __restrict__ out4, const float* __restrict__ x,
   __shared__ double s_stat[NBATCH][32];
   for (int i = threadIdx.x; i < NBATCH * 32; i += blockDim.x) (&s_stat[0][0])[i] = 0.0;
   __syncthreads();
+  const uint32_t sp0 = (uint32_t)b * (uint32_t)Kl * (uint32_t)HW + (uint32_t)pix;   // output index of local slot 0
+  uint4* const a_pl0 = reinterpret_cast<uint4*>(auxs);
+  float4* const a_r4 = reinterpret_cast<float4*>(auxs) + n_slot_pix;
+  float2* const a_r2 = reinterpret_cast<float2*>(auxs) + 4 * n_slot_pix;
 #pragma unroll
   for (int bt = 0; bt < NBATCH; ++bt) {
     if (bt * MIX_KB < K) {                          // block-uniform
@@ -394,31 +403,29 @@ mixture_fast_kernel(const float* __restrict__ out4, const float* __restrict__ x,
 #pragma unroll
       for (int kk = 0; kk < MIX_KB; ++kk) {
         const int k = bt * MIX_KB + kk;             // compile-time
-        if (k < KMAX && k < K && live && k >= k_off && k < k_off + Kl) {
-          const float m_k = mk[k], m_r = mr[k], m_g = mg[k], m_b = mb[k], gmk = gm[k];
+        if (k < KMAX && k < K && k >= k_off && k < k_off + Kl) {
+          const float m_k = mk[k], m_r = mr[k], m_g = mg[k], m_b = mb[k];
+          const float gmk = (pr[k] + pg[k] + pb[k]) * rcp_fast(m_k + 1e-12f);
           const float dr = xr - m_r, dg = xg - m_g, db = xb - m_b;
           // dJ/dmean_kc = r_kc (x_c - mean_kc) / sigma^2
           const float gr = pr[k] * dr * inv_s2, gg = pg[k] * dg * inv_s2, gb = pb[k] * db * inv_s2;
           const float mpost = (Lk[k] * kscale) * inv_kl;                             // (292) 0/0 -> NaN as ref
           const float loo = (mkl_tot - m_k * Lk[k]) * rcp_fast(1.f - m_k + 1e-5f);   // (326-328)
-          const size_t sp = ((size_t)(b * Kl + (k - k_off))) * HW + pix;
-          const float lgr = __ldg(out4 + (out4_slot(b, k, B, Kl, HW) + pix) * 4 + 3);   // raw logit (L1 hit)
+          const uint32_t sp = sp0 + (uint32_t)(k - k_off) * (uint32_t)HW;
           if constexpr (FUSED) {
-            reinterpret_cast<uint4*>(auxs)[sp] = make_uint4(pack_h2(xr, xg, f16), pack_h2(xb, m_r, f16),
-                                                            pack_h2(m_g, m_b, f16), pack_h2(m_k, lgr, f16));
-            reinterpret_cast<float4*>(auxs)[n_slot_pix + sp] = make_float4(mpost, gr, gg, gb);
-            reinterpret_cast<float2*>(auxs)[4 * n_slot_pix + sp] = make_float2(gmk, loo);
+            a_pl0[sp] = make_uint4(pack_h2(xr, xg, F16), pack_h2(xb, m_r, F16), pack_h2(m_g, m_b, F16), pack_h2(m_k, lgr[k], F16));
+            a_r4[sp] = make_float4(mpost, gr, gg, gb);
+            a_r2[sp] = make_float2(gmk, loo);
           } else {
-            float4* ax = reinterpret_cast<float4*>(auxs) + sp * 3;
+            float4* ax = reinterpret_cast<float4*>(auxs) + (size_t)sp * 3;
             ax[0] = make_float4(m_r, m_g, m_b, m_k);
-            ax[1] = make_float4(lgr, mpost, gr, gg);
+            ax[1] = make_float4(lgr[k], mpost, gr, gg);
             ax[2] = make_float4(gb, gmk, loo, 0.f);
           }
           const float4 sd = make_float4(gr * m_r * (1.f - m_r), gg * m_g * (1.f - m_g),
                                         gb * m_b * (1.f - m_b), m_k * (gmk - mgsum));
           if (seed_half) {
-            reinterpret_cast<uint4*>(seed4)[sp] = make_uint4(pack_h2(sd.x, sd.y, seed_half == 2),
-                                                             pack_h2(sd.z, sd.w, seed_half == 2), 0u, 0u);
+            reinterpret_cast<uint4*>(seed4)[sp] = make_uint4(pack_h2(sd.x, sd.y, F16), pack_h2(sd.z, sd.w, F16), 0u, 0u);
           } else {
             reinterpret_cast<float4*>(seed4)[sp] = sd;
           }
@@ -472,7 +479,7 @@ int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st, bo
   const int k_off = p->ks_rank * s.K, ll_on = p->ks_rank == 0;
   // hardware exp / log in the tensor-core modes (the exact fp32 mode keeps libm; IODINE_MIX_EXACT=1 keeps it everywhere)
   static const bool exact_env = getenv("IODINE_MIX_EXACT") != nullptr;
-  const bool fast = tc_mode(p) && !exact_env;
+  const bool fast = tc_mode(p) && !exact_env && p->HW % 128 == 0;   // (mixture_fast_kernel: no partial blocks)
   const bool fused = fused_aux && want_grads;
   const size_t nsp = (size_t)p->BK * p->HW;
 #define IOD_MIX_ARGS                                                                                               \
@@ -480,10 +487,13 @@ int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st, bo
       want_grads, seed_half, s.K, k_off, ll_on, half_is_f16(p), nsp
 #define IOD_MIX(KM, FU)                                                                  \
   do {                                                                                   \
-    if (fast) mixture_fast_kernel<KM, FU><<<grid, 128, 0, st>>>(IOD_MIX_ARGS);            \
+    if (fast && f16o) mixture_fast_kernel<KM, FU, true><<<grid, 128, 0, st>>>(IOD_MIX_ARGS);   \
+    else if (fast) mixture_fast_kernel<KM, FU, false><<<grid, 128, 0, st>>>(IOD_MIX_ARGS);     \
     else mixture_kernel<KM, FU, false><<<grid, 128, 0, st>>>(IOD_MIX_ARGS);               \
   } while (0)
+  const bool f16o = half_is_f16(p) != 0;           // (seed_half == 1, bf16 seeds, only occurs with bf16 outputs)
   if (p->K_total <= 8) { if (fused) IOD_MIX(8, true); else IOD_MIX(8, false); }
+  else if (p->K_total <= 12) { if (fused) IOD_MIX(12, true); else IOD_MIX(12, false); }
   else { if (fused) IOD_MIX(16, true); else IOD_MIX(16, false); }
 #undef IOD_MIX
 #undef IOD_MIX_ARGS

@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -5 > gpurun_out/r2q_pytest.log
+cat gpurun_out/r2q_pytest.log | cut -c1-800
+run() {
+  timeout 600 python bench.py --precision $1 --steps 6 --warmup 3 --no-cpu-baseline --no-variants 2>gpurun_out/r2q_$1_$2.err | python -c "
+import json,sys
+l=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=l['roofline']
+print('$1 $2 value=%.0f ms_per_step=%.3f e2e=%.0f conv avg_launch_ms=%.4f'%(l['value'], l['ms_per_step'], l['e2e']['value'], r['avg_launch_ms']))
+"
+}
+run fp16 prod
+run tf32 prod
+IODINE_TC_DEBUG=16 run tf32 noinput
+IODINE_TC_DEBUG=16 run fp16 noinput
+IODINE_TC_DEBUG=26 run tf32 noinput_nostore_noact
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2q_launches_fp16.csv python bench.py --precision fp16 --profile-mode --steps 1 --warmup 1 > /dev/null 2>&1
+python scripts/launch_summary.py gpurun_out/r2q_launches_fp16.csv 2>/dev/null | head -13
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mixture" -s 4 -c 1 -o gpurun_out/r2q_mix python bench.py --precision fp16 --profile-mode --steps 1 --warmup 1 > gpurun_out/r2q_ncu.log 2>&1
