@@ -49,7 +49,10 @@ constexpr int TC_MAX_RING = 32;
 // tile owns one accumulator stage, so issuers never share an accumulator.
 constexpr int TC_ISSUERS = 2;
 __host__ __device__ constexpr int tc_epi_warps(int N) { return N >= 32 ? 8 : 4; }
-__host__ __device__ constexpr int tc_threads(int N) { return 32 * (1 + TC_ISSUERS) + 32 * tc_epi_warps(N); }
+// row-streaming kernels carry one more warp behind the epilogue warps: the scout (see the issuer)
+__host__ __device__ constexpr int tc_threads(int N, bool rs = false) {
+  return 32 * (1 + TC_ISSUERS) + 32 * tc_epi_warps(N) + (rs ? 32 : 0);
+}
 constexpr int TC_ACC_STAGES = 4;
 constexpr int TC_RS_UNIT = 5;        // input rows per issue unit of the row-streaming variant (<= 16; TcParams::rs_unit < ring rows)
 constexpr int TC_RS_SLOTS = 8;       // accumulator slots of the row-streaming variant (one per output row in flight)
@@ -122,6 +125,9 @@ struct TcSmem {                    // tail of the dynamic shared memory block
   uint64_t tfull[TC_RS_SLOTS];
   uint64_t tempty[TC_RS_SLOTS];
   uint64_t wbar;
+  uint64_t plan_full[2];           // row-streaming: scout -> issuer, one issue unit of row plans is ready
+  uint64_t plan_empty[2];          // issuer -> scout
+  uint4 plan[2][16];               // per row of the unit: {A base | LBO, first accumulator, packed counts, rows of the unit | last-unit flag}
   uint32_t tmem_base;
 };
 
@@ -185,7 +191,9 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, const uint32_t (&
 // WRAP: the accumulator blocks straddle the end of the slot ring (second run from slot 0) -- a compile-time
 // flag so that the common case carries no predicated-off instructions; id0/id1/id1n/idn are the instruction
 // descriptors (N = blocks * Cout) loaded once per row, not once per MMA.
-template <int N, int KS, int NKS, int PST16, bool WRAP, bool TF>
+// HALF: -1 = the whole row; 0 / 1 = the first / second half of its (dx, K-step) sequence (experiment: the next row's
+// bookkeeping between the halves was slower, profiles/r2_issuer_experiments.md)
+template <int N, int KS, int NKS, int PST16, bool WRAP, bool TF, int HALF>
 __device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, uint32_t rb, const uint32_t (&a_off)[40],
                                              uint32_t w_base16, int c0, int c1, int boff, bool has_new, int n0, int n1,
                                              uint32_t id_c0, uint32_t id_c1, uint32_t id_n0, uint32_t id_n1, uint32_t id_1) {
@@ -201,6 +209,7 @@ __device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, ui
 #pragma unroll
     for (int ks = 0; ks < NKS; ++ks) {
       const int e = dx * NKS + ks;
+      if ((HALF == 0 && e >= (KS * NKS) / 2) || (HALF == 1 && e < (KS * NKS) / 2)) continue;
       const uint32_t off = PST16 ? (uint32_t)(dx + 2 * ks * PST16) : a_off[dx * NKS + ks];
       const uint64_t ad = DESC_HI | (rb + off);
       const uint32_t eo = (uint32_t)e * 2u * NB;
@@ -295,12 +304,12 @@ __device__ __forceinline__ void tc_transposed_sum(float* v, int lane) {
 // RS: row-streaming variant (W == 128, one tile per output row): see tc_issue_row.
 // TF: tf32 operands -- planes hold 4 fp32 channels (still 16 bytes per pixel), K = 8 per MMA = two planes, NKS = C/8.
 template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS, bool TF>
-__global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(tc_threads(N, RS), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int PW = TF ? 4 : 8;                       // channels per plane
   const int cta = (int)blockIdx.x / p.nsplit, ncta = (int)gridDim.x / p.nsplit;
   const int csplit = (int)blockIdx.x - cta * p.nsplit; // this CTA's block of N output channels
-  constexpr int NTHREADS = tc_threads(N);
+  constexpr int NTHREADS = tc_threads(N, RS);
   constexpr int EW = tc_epi_warps(N);
   constexpr int NC = (EW == 8) ? N / 2 : N;            // accumulator columns per epilogue warp
   constexpr int ACC = RS ? TC_RS_SLOTS : TC_ACC_STAGES;       // accumulator stages (TMEM)
@@ -335,6 +344,10 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
       mbar_init(smem_u32(&sb->tempty[i]), EW);     // one arrive per epilogue warp
     }
     mbar_init(smem_u32(&sb->wbar), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&sb->plan_full[i]), 1);
+      mbar_init(smem_u32(&sb->plan_empty[i]), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -504,64 +517,115 @@ __global__ void __launch_bounds__(tc_threads(N), 1) conv_tc_kernel(const __grid_
         mbar_wait(smem_u32(&sb->wbar), 0, 2);
         const uint32_t a_base16 = smem_u32(s_a) >> 4;
         const uint32_t w_base16 = smem_u32(s_w) >> 4;
-        int slot = 0; uint32_t rph = 0;            // ring slot / phase of the next input row
-        int qg = 0;                                // output rows (tiles) of all previous items of this CTA
+        const uint32_t id_step = (uint32_t)(N >> 3) << 17, id_0 = p.idesc_n[1] - id_step;   // idesc of c blocks = id_0 + c id_step
+        // The per-row bookkeeping (ring slot, accumulator blocks, weight block, which barriers to signal) and every
+        // wait on the ring / accumulator barriers are the SCOUT warp's (below): the tensor pipe's instruction queue
+        // is short, and a few hundred cycles of serial arithmetic + barrier polls per issue unit in this thread left
+        // it idle (the pure load + MMA pipeline ran ~1.4x above the back-to-back MMA time of tools/umma_probe_tf32).
+        // Per unit this warp takes ONE barrier wait and three shuffles per row.
+        int pp = 0; uint32_t pph = 0;
         for (int item = __ldg(p.coff + cta), it_end = __ldg(p.coff + cta + 1); item < it_end; ++item) {
           const int TH = __ldg(p.itab + item).z;   // rows of this item (1 .. H)
           const int nrows = TH + 2 * pad;
-          // Rows are handled in units of TC_RS_UNIT: all barrier waits of a unit first, then its MMAs back to
-          // back.  A wait costs 70-150 cycles even when the barrier has long completed, and the tensor pipe's
-          // instruction queue is short, so per-row waits left the pipe idle between rows.
           const int unit = p.rs_unit;
           for (int j0 = 0; j0 < nrows; j0 += unit) {
             const int ju = (nrows - j0 < unit) ? nrows - j0 : unit;
-            // lanes wait in parallel: lane u on the ring row of unit row u, lane 16+u on the accumulator slot
-            // that row opens (a wait costs 70-150 cycles even when the barrier completed long ago)
-            if (lane < ju) {
-              int sl = slot + lane; uint32_t ph = rph;
-              if (sl >= R) { sl -= R; ph ^= 1u; }
-              mbar_wait(smem_u32(&sb->full[sl]), ph, 3);
-            } else if (lane >= 16 && lane - 16 < ju && j0 + lane - 16 <= TH - 1) {
-              const int qn = qg + j0 + lane - 16;  // output row q = j receives its first contribution: fresh slot
-              mbar_wait(smem_u32(&sb->tempty[qn & (ACC - 1)]), (((uint32_t)qn / ACC) & 1u) ^ 1u, 4);
-            }
-            __syncwarp();
+            mbar_wait(smem_u32(&sb->plan_full[pp]), pph, 3);
             tc_fence_after();
+            const uint4 mine = sb->plan[pp][lane & 15];
             for (int u = 0; u < ju; ++u) {
-              const int j = j0 + u;
-              // output rows of this strip fed by input row j: q in [j-(KS-1), j] clipped to the strip
-              const int qa = (j - (KS - 1) > 0) ? j - (KS - 1) : 0;
-              const int qb = (j < TH - 1) ? j : TH - 1;
-              const bool has_new = j <= TH - 1;    // row q = j: overwrite on its first step
-              const int cnt = qb - qa + 1;                       // accumulator blocks written by this row
-              const int sa = (qg + qa) & (ACC - 1);              // slot of the first one
-              const int c0 = (cnt < ACC - sa) ? cnt : ACC - sa;  // blocks before the slot ring wraps
-              const int c1 = cnt - c0;
-              const int boff = qa - (j - (KS - 1));              // first weight block (block b <-> dy = KS-1-b)
-              const uint32_t rb = __shfl_sync(0xffffffffu, (a_base16 + (uint32_t)(slot * Ps)) | (plane_stride16 << 16), 0);
+              const uint32_t rb = __shfl_sync(0xffffffffu, mine.x, u);
+              const uint32_t d0 = __shfl_sync(0xffffffffu, mine.y, u);
+              const uint32_t pk = __shfl_sync(0xffffffffu, mine.z, u);
               const uint32_t wb_t = __shfl_sync(0xffffffffu, w_base16, 0);
-              const uint32_t d0 = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(sa * N), 0);
-              // blocks that already hold partial sums (step 0 accumulates into them) per run
-              const int n0 = has_new ? (c1 ? c0 : c0 - 1) : c0;
-              const int n1 = has_new ? (c1 ? c1 - 1 : 0) : c1;
-              const uint32_t id_c0 = p.idesc_n[c0], id_c1 = p.idesc_n[c1], id_n0 = p.idesc_n[n0], id_n1 = p.idesc_n[n1],
-                             id_1 = p.idesc_n[1];
               if (leader) {
+                const int c0 = (int)(pk & 7u), c1 = (int)((pk >> 3) & 7u), boff = (int)((pk >> 6) & 3u);
+                const bool has_new = ((pk >> 8) & 1u) != 0;
+                const int n0 = (int)((pk >> 9) & 7u), n1 = (int)((pk >> 12) & 7u);
+                const uint32_t tf = (pk >> 15) & 15u, sl = (pk >> 19) & 31u;
+                // instruction descriptor for c accumulator blocks: N = c * Cout sits in bits 17.. (make_idesc)
+                const uint32_t id_c0 = id_0 + (uint32_t)c0 * id_step, id_c1 = id_0 + (uint32_t)c1 * id_step,
+                               id_n0 = id_0 + (uint32_t)n0 * id_step, id_n1 = id_0 + (uint32_t)n1 * id_step,
+                               id_1 = id_0 + id_step;
                 if (c1 > 0)
-                  tc_issue_row<N, KS, NKS, PST16, true, TF>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
-                                                        id_c1, id_n0, id_n1, id_1);
+                  tc_issue_row<N, KS, NKS, PST16, true, TF, -1>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
+                                                              id_c1, id_n0, id_n1, id_1);
                 else
-                  tc_issue_row<N, KS, NKS, PST16, false, TF>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
-                                                         id_c1, id_n0, id_n1, id_1);
-                if (j >= KS - 1) tc_commit(smem_u32(&sb->tfull[(qg + j - (KS - 1)) & (ACC - 1)]));   // row complete
-                tc_commit(smem_u32(&sb->empty[slot]));                                             // ring row consumed
+                  tc_issue_row<N, KS, NKS, PST16, false, TF, -1>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
+                                                               id_c1, id_n0, id_n1, id_1);
+                if (tf != 15u) tc_commit(smem_u32(&sb->tfull[tf]));    // row complete
+                tc_commit(smem_u32(&sb->empty[sl]));                   // ring row consumed
               }
               __syncwarp();
-              if (++slot == R) { slot = 0; rph ^= 1u; }
             }
+            if (lane == 0) mbar_arrive(smem_u32(&sb->plan_empty[pp]));
+            pp ^= 1;
+            if (pp == 0) pph ^= 1u;
           }
-          qg += TH;
         }
+      }
+    }
+  } else if (RS && warp == 3 + EW) {
+    // =============================================================== scout, row-streaming
+    // Walks the same (item, unit, row) sequence one unit ahead of the issuer: lane u works out what row j0 + u of the
+    // unit needs, the lanes wait -- in parallel -- for the ring rows to land and for the accumulator slots the unit
+    // opens to be drained, then the plans go to shared memory and one arrive releases the unit to the issuer.
+    if constexpr (RS) {
+      const uint32_t a_base16 = smem_u32(s_a) >> 4;
+      int slot = 0; uint32_t rph = 0;            // ring slot / phase of the next input row
+      int qg = 0;                                // output rows (tiles) of all previous items of this CTA
+      int pp = 0; uint32_t pph = 0;
+      for (int item = __ldg(p.coff + cta), it_end = __ldg(p.coff + cta + 1); item < it_end; ++item) {
+        const int TH = __ldg(p.itab + item).z;   // rows of this item (1 .. H)
+        const int nrows = TH + 2 * pad;
+        const int unit = p.rs_unit;
+        for (int j0 = 0; j0 < nrows; j0 += unit) {
+          const int ju = (nrows - j0 < unit) ? nrows - j0 : unit;
+          uint4 plan = make_uint4(0u, 0u, 0u, 0u);
+          {
+            const int u = (lane < ju) ? lane : 0;
+            const int j = j0 + u;
+            int sl = slot + u;
+            if (sl >= R) sl -= R;
+            // output rows of this strip fed by input row j: q in [j-(KS-1), j] clipped to the strip
+            const int qa = (j - (KS - 1) > 0) ? j - (KS - 1) : 0;
+            const int qb = (j < TH - 1) ? j : TH - 1;
+            const int has_new = j <= TH - 1;                   // row q = j: overwrite on its first step
+            const int cnt = qb - qa + 1;                       // accumulator blocks written by this row
+            const int sa = (qg + qa) & (ACC - 1);              // slot of the first one
+            const int c0 = (cnt < ACC - sa) ? cnt : ACC - sa;  // blocks before the slot ring wraps
+            const int c1 = cnt - c0;
+            const int boff = qa - (j - (KS - 1));              // first weight block (block b <-> dy = KS-1-b)
+            // blocks that already hold partial sums (step 0 accumulates into them) per run
+            const int n0 = has_new ? (c1 ? c0 : c0 - 1) : c0;
+            const int n1 = has_new ? (c1 ? c1 - 1 : 0) : c1;
+            const int tf = (j >= KS - 1) ? ((qg + j - (KS - 1)) & (ACC - 1)) : 15;   // accumulator this row completes
+            plan.x = (a_base16 + (uint32_t)(sl * Ps)) | (plane_stride16 << 16);
+            plan.y = tmem_base + (uint32_t)(sa * N);
+            plan.z = (uint32_t)c0 | ((uint32_t)c1 << 3) | ((uint32_t)boff << 6) | ((uint32_t)has_new << 8) | ((uint32_t)n0 << 9) |
+                     ((uint32_t)n1 << 12) | ((uint32_t)tf << 15) | ((uint32_t)sl << 19);
+          }
+          plan.w = (uint32_t)ju | ((item + 1 == it_end && j0 + unit >= nrows) ? 256u : 0u);   // rows of the unit | the CTA's last unit
+          if (lane == 0) mbar_wait(smem_u32(&sb->plan_empty[pp]), pph ^ 1u, 6);
+          // lane u waits on the ring row of unit row u, lane 16+u on the accumulator slot that row opens
+          if (lane < ju) {
+            int sl = slot + lane; uint32_t ph = rph;
+            if (sl >= R) { sl -= R; ph ^= 1u; }
+            mbar_wait(smem_u32(&sb->full[sl]), ph, 3);
+          } else if (lane >= 16 && lane - 16 < ju && j0 + lane - 16 <= TH - 1) {
+            const int qn = qg + j0 + lane - 16;  // output row q = j receives its first contribution: fresh slot
+            mbar_wait(smem_u32(&sb->tempty[qn & (ACC - 1)]), (((uint32_t)qn / ACC) & 1u) ^ 1u, 4);
+          }
+          __syncwarp();
+          if (lane < ju) sb->plan[pp][lane] = plan;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&sb->plan_full[pp]));
+          pp ^= 1;
+          if (pp == 0) pph ^= 1u;
+          slot += ju;
+          if (slot >= R) { slot -= R; rph ^= 1u; }
+        }
+        qg += TH;
       }
     }
   } else if (!RS && warp <= TC_ISSUERS) {
@@ -1327,7 +1391,7 @@ static int tc_launch_g(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_
   }
   const int ranges_max = p->num_sms / q.nsplit;
   const int ranges = q.items < ranges_max ? q.items : ranges_max;
-  kern<<<ranges * q.nsplit, tc_threads(N), smem, st_>>>(q);
+  kern<<<ranges * q.nsplit, tc_threads(N, RS), smem, st_>>>(q);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
