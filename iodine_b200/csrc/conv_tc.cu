@@ -49,9 +49,13 @@ constexpr int TC_MAX_RING = 32;
 // tile owns one accumulator stage, so issuers never share an accumulator.
 constexpr int TC_ISSUERS = 2;
 __host__ __device__ constexpr int tc_epi_warps(int N) { return N >= 32 ? 8 : 4; }
-// row-streaming kernels carry one more warp behind the epilogue warps: the scout (see the issuer)
-__host__ __device__ constexpr int tc_threads(int N, bool rs = false) {
-  return 32 * (1 + TC_ISSUERS) + 32 * tc_epi_warps(N) + (rs ? 32 : 0);
+// row-streaming kernels carry more warps behind the epilogue warps: the scout and, where the register file allows, a
+// second MMA issuer (see the issuer).  A 13th warp caps the block at 128 registers per thread (allocation is per four
+// warps), which the forward epilogues fit and the data-gradient ones (140-168: prefetch queue of the saved
+// activation, running class sums) do not: those keep the single issuer.
+__host__ __device__ constexpr bool tc_iss2(int epi, bool rs, bool tf) { (void)tf; return rs && (epi == 0 || epi == 2); }
+__host__ __device__ constexpr int tc_threads(int N, bool rs = false, bool iss2 = false) {
+  return 32 * (1 + TC_ISSUERS) + 32 * tc_epi_warps(N) + (rs ? 32 : 0) + (iss2 ? 32 : 0);
 }
 constexpr int TC_ACC_STAGES = 4;
 constexpr int TC_RS_UNIT = 5;        // input rows per issue unit of the row-streaming variant (<= 16; TcParams::rs_unit < ring rows)
@@ -304,12 +308,13 @@ __device__ __forceinline__ void tc_transposed_sum(float* v, int lane) {
 // RS: row-streaming variant (W == 128, one tile per output row): see tc_issue_row.
 // TF: tf32 operands -- planes hold 4 fp32 channels (still 16 bytes per pixel), K = 8 per MMA = two planes, NKS = C/8.
 template <int N, int EPI, int KS, int NKS, int PS, int PST16, bool RS, bool TF>
-__global__ void __launch_bounds__(tc_threads(N, RS), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int PW = TF ? 4 : 8;                       // channels per plane
   const int cta = (int)blockIdx.x / p.nsplit, ncta = (int)gridDim.x / p.nsplit;
   const int csplit = (int)blockIdx.x - cta * p.nsplit; // this CTA's block of N output channels
-  constexpr int NTHREADS = tc_threads(N, RS);
+  constexpr bool ISS2 = tc_iss2(EPI, RS, TF);
+  constexpr int NTHREADS = tc_threads(N, RS, ISS2);
   constexpr int EW = tc_epi_warps(N);
   constexpr int NC = (EW == 8) ? N / 2 : N;            // accumulator columns per epilogue warp
   constexpr int ACC = RS ? TC_RS_SLOTS : TC_ACC_STAGES;       // accumulator stages (TMEM)
@@ -340,13 +345,13 @@ __global__ void __launch_bounds__(tc_threads(N, RS), 1) conv_tc_kernel(const __g
       mbar_init(smem_u32(&sb->empty[i]), RS ? 1 : TC_ISSUERS);   // every issuer hands every row back once
     }
     for (int i = 0; i < ACC; ++i) {
-      mbar_init(smem_u32(&sb->tfull[i]), 1);
+      mbar_init(smem_u32(&sb->tfull[i]), ISS2 ? 2 : 1);   // two issuers: the owners of the row's last two input rows commit
       mbar_init(smem_u32(&sb->tempty[i]), EW);     // one arrive per epilogue warp
     }
     mbar_init(smem_u32(&sb->wbar), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sb->plan_full[i]), 1);
-      mbar_init(smem_u32(&sb->plan_empty[i]), 1);
+      mbar_init(smem_u32(&sb->plan_empty[i]), ISS2 ? 2 : 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -508,22 +513,25 @@ __global__ void __launch_bounds__(tc_threads(N, RS), 1) conv_tc_kernel(const __g
     }
     __syncwarp();
     }
-  } else if (RS && warp == 1) {
-    // =============================================================== MMA issuer, row-streaming
-    // One thread: input rows are consumed strictly in order, each exactly once.
+  } else if (RS && (warp == 1 || (ISS2 && warp == 4 + EW))) {
+    // =============================================================== MMA issuer(s), row-streaming
+    // Input rows are consumed strictly in order, each exactly once.  The per-row bookkeeping (ring slot, accumulator
+    // blocks, weight block, which barriers to signal) and every wait on the ring / accumulator barriers are the SCOUT
+    // warp's (below): the tensor pipe's instruction queue is short, and serial arithmetic + barrier polls in the issuing
+    // thread left it idle.  What remains per row is the ~100 uniform-datapath instructions that build its descriptors
+    // (ptxas schedules them ahead of the row's MMA burst) -- with ISS2 two warps take alternate rows, so that one builds
+    // its descriptors while the other's burst runs; a token (named barriers 1 / 2) keeps the bursts in row order, which
+    // the overwrite of a fresh accumulator needs.  Completion: a thread's tcgen05.commit covers its own MMAs, so an
+    // accumulator is complete when the owners of its last TWO input rows have both committed to it.
     if constexpr (RS) {
-      if (warp == 1) {
-        const bool leader = elect_one_sync();      // 12-14 MMAs per row: few enough descriptors for ptxas to keep in uniform registers
+      {
+        const int w = (warp == 1) ? 0 : 1;         // issuer index: rows with (running row number & 1) == w
+        const bool leader = elect_one_sync();
         mbar_wait(smem_u32(&sb->wbar), 0, 2);
-        const uint32_t a_base16 = smem_u32(s_a) >> 4;
         const uint32_t w_base16 = smem_u32(s_w) >> 4;
         const uint32_t id_step = (uint32_t)(N >> 3) << 17, id_0 = p.idesc_n[1] - id_step;   // idesc of c blocks = id_0 + c id_step
-        // The per-row bookkeeping (ring slot, accumulator blocks, weight block, which barriers to signal) and every
-        // wait on the ring / accumulator barriers are the SCOUT warp's (below): the tensor pipe's instruction queue
-        // is short, and a few hundred cycles of serial arithmetic + barrier polls per issue unit in this thread left
-        // it idle (the pure load + MMA pipeline ran ~1.4x above the back-to-back MMA time of tools/umma_probe_tf32).
-        // Per unit this warp takes ONE barrier wait and three shuffles per row.
         int pp = 0; uint32_t pph = 0;
+        int g = 0;                                 // running row number of the CTA
         for (int item = __ldg(p.coff + cta), it_end = __ldg(p.coff + cta + 1); item < it_end; ++item) {
           const int TH = __ldg(p.itab + item).z;   // rows of this item (1 .. H)
           const int nrows = TH + 2 * pad;
@@ -533,30 +541,41 @@ __global__ void __launch_bounds__(tc_threads(N, RS), 1) conv_tc_kernel(const __g
             mbar_wait(smem_u32(&sb->plan_full[pp]), pph, 3);
             tc_fence_after();
             const uint4 mine = sb->plan[pp][lane & 15];
-            for (int u = 0; u < ju; ++u) {
+            const bool last_unit = item + 1 == it_end && j0 + unit >= nrows;
+            for (int u = 0; u < ju; ++u, ++g) {
+              if (ISS2 && (g & 1) != w) continue;
               const uint32_t rb = __shfl_sync(0xffffffffu, mine.x, u);
               const uint32_t d0 = __shfl_sync(0xffffffffu, mine.y, u);
               const uint32_t pk = __shfl_sync(0xffffffffu, mine.z, u);
               const uint32_t wb_t = __shfl_sync(0xffffffffu, w_base16, 0);
+              const int c0 = (int)(pk & 7u), c1 = (int)((pk >> 3) & 7u), boff = (int)((pk >> 6) & 3u);
+              const bool has_new = ((pk >> 8) & 1u) != 0;
+              const int n0 = (int)((pk >> 9) & 7u), n1 = (int)((pk >> 12) & 7u);
+              const uint32_t tf = (pk >> 15) & 15u, sl = (pk >> 19) & 31u, tf1 = (pk >> 24) & 15u;
+              // instruction descriptor for c accumulator blocks: N = c * Cout sits in bits 17.. (make_idesc)
+              const uint32_t id_c0 = id_0 + (uint32_t)c0 * id_step, id_c1 = id_0 + (uint32_t)c1 * id_step,
+                             id_n0 = id_0 + (uint32_t)n0 * id_step, id_n1 = id_0 + (uint32_t)n1 * id_step,
+                             id_1 = id_0 + id_step;
+              if (ISS2 && g > 0) {                 // the previous row's burst has been issued
+                if (w == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+                else asm volatile("bar.sync 1, 64;" ::: "memory");
+              }
               if (leader) {
-                const int c0 = (int)(pk & 7u), c1 = (int)((pk >> 3) & 7u), boff = (int)((pk >> 6) & 3u);
-                const bool has_new = ((pk >> 8) & 1u) != 0;
-                const int n0 = (int)((pk >> 9) & 7u), n1 = (int)((pk >> 12) & 7u);
-                const uint32_t tf = (pk >> 15) & 15u, sl = (pk >> 19) & 31u;
-                // instruction descriptor for c accumulator blocks: N = c * Cout sits in bits 17.. (make_idesc)
-                const uint32_t id_c0 = id_0 + (uint32_t)c0 * id_step, id_c1 = id_0 + (uint32_t)c1 * id_step,
-                               id_n0 = id_0 + (uint32_t)n0 * id_step, id_n1 = id_0 + (uint32_t)n1 * id_step,
-                               id_1 = id_0 + id_step;
                 if (c1 > 0)
                   tc_issue_row<N, KS, NKS, PST16, true, TF, -1>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
                                                               id_c1, id_n0, id_n1, id_1);
                 else
                   tc_issue_row<N, KS, NKS, PST16, false, TF, -1>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
                                                                id_c1, id_n0, id_n1, id_1);
-                if (tf != 15u) tc_commit(smem_u32(&sb->tfull[tf]));    // row complete
-                tc_commit(smem_u32(&sb->empty[sl]));                   // ring row consumed
+                if (tf != 15u) tc_commit(smem_u32(&sb->tfull[tf]));              // this row was the accumulator's last input row
+                if (ISS2 && tf1 != 15u) tc_commit(smem_u32(&sb->tfull[tf1]));    // ... its last but one
+                tc_commit(smem_u32(&sb->empty[sl]));                             // ring row consumed
               }
               __syncwarp();
+              if (ISS2 && !(last_unit && u == ju - 1)) {   // hand the token on (nobody waits for the CTA's last row)
+                if (w == 0) asm volatile("bar.arrive 1, 64;" ::: "memory");
+                else asm volatile("bar.arrive 2, 64;" ::: "memory");
+              }
             }
             if (lane == 0) mbar_arrive(smem_u32(&sb->plan_empty[pp]));
             pp ^= 1;
@@ -600,10 +619,12 @@ __global__ void __launch_bounds__(tc_threads(N, RS), 1) conv_tc_kernel(const __g
             const int n0 = has_new ? (c1 ? c0 : c0 - 1) : c0;
             const int n1 = has_new ? (c1 ? c1 - 1 : 0) : c1;
             const int tf = (j >= KS - 1) ? ((qg + j - (KS - 1)) & (ACC - 1)) : 15;   // accumulator this row completes
+            // accumulator whose last but one input row this is (two issuers: its owner commits to it as well)
+            const int tf1 = (j >= KS - 2 && j - (KS - 2) <= TH - 1) ? ((qg + j - (KS - 2)) & (ACC - 1)) : 15;
             plan.x = (a_base16 + (uint32_t)(sl * Ps)) | (plane_stride16 << 16);
             plan.y = tmem_base + (uint32_t)(sa * N);
             plan.z = (uint32_t)c0 | ((uint32_t)c1 << 3) | ((uint32_t)boff << 6) | ((uint32_t)has_new << 8) | ((uint32_t)n0 << 9) |
-                     ((uint32_t)n1 << 12) | ((uint32_t)tf << 15) | ((uint32_t)sl << 19);
+                     ((uint32_t)n1 << 12) | ((uint32_t)tf << 15) | ((uint32_t)sl << 19) | ((uint32_t)tf1 << 24);
           }
           plan.w = (uint32_t)ju | ((item + 1 == it_end && j0 + unit >= nrows) ? 256u : 0u);   // rows of the unit | the CTA's last unit
           if (lane == 0) mbar_wait(smem_u32(&sb->plan_empty[pp]), pph ^ 1u, 6);
@@ -1391,7 +1412,7 @@ static int tc_launch_g(Plan* p, const TcParams& q, size_t smem, cudaStream_t st_
   }
   const int ranges_max = p->num_sms / q.nsplit;
   const int ranges = q.items < ranges_max ? q.items : ranges_max;
-  kern<<<ranges * q.nsplit, tc_threads(N, RS), smem, st_>>>(q);
+  kern<<<ranges * q.nsplit, tc_threads(N, RS, tc_iss2(EPI, RS, TF)), smem, st_>>>(q);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
