@@ -59,7 +59,9 @@ __host__ __device__ constexpr int tc_threads(int N, bool rs = false, bool iss2 =
 }
 constexpr int TC_ACC_STAGES = 4;
 constexpr int TC_RS_UNIT = 5;        // input rows per issue unit of the row-streaming variant (<= 16; TcParams::rs_unit < ring rows)
-constexpr int TC_RS_SLOTS = 8;       // accumulator slots of the row-streaming variant (one per output row in flight)
+constexpr int TC_RS_SLOTS = 8;       // accumulator slots of the row-streaming variant (one per output row in flight) ...
+constexpr int TC_RS_SLOTS_MAX = 16;  // ... 16 where they fit the 512 TMEM columns (N <= 32): the KS-slot window of a row then
+                                     // straddles the end of the slot ring -- two MMAs per step instead of one -- half as often
 
 // EPI_DSUM: data-gradient whose output is not stored but reduced over the border classes of the collapsed first
 // layer straight from the accumulators (row-streaming kernels only; replaces EPI_DGRAD + tc_class_sum_kernel)
@@ -126,8 +128,8 @@ struct alignas(64) TcParams {
 struct TcSmem {                    // tail of the dynamic shared memory block
   uint64_t full[TC_MAX_RING];
   uint64_t empty[TC_MAX_RING];
-  uint64_t tfull[TC_RS_SLOTS];
-  uint64_t tempty[TC_RS_SLOTS];
+  uint64_t tfull[TC_RS_SLOTS_MAX];
+  uint64_t tempty[TC_RS_SLOTS_MAX];
   uint64_t wbar;
   uint64_t plan_full[2];           // row-streaming: scout -> issuer, one issue unit of row plans is ready
   uint64_t plan_empty[2];          // issuer -> scout
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
   constexpr int NTHREADS = tc_threads(N, RS, ISS2);
   constexpr int EW = tc_epi_warps(N);
   constexpr int NC = (EW == 8) ? N / 2 : N;            // accumulator columns per epilogue warp
-  constexpr int ACC = RS ? TC_RS_SLOTS : TC_ACC_STAGES;       // accumulator stages (TMEM)
+  constexpr int ACC = RS ? (N <= 32 ? TC_RS_SLOTS_MAX : TC_RS_SLOTS) : TC_ACC_STAGES;       // accumulator stages (TMEM)
   constexpr int TMEM_COLS = (ACC * N < 32) ? 32 : ACC * N;
   const uint32_t w_region = (p.w_bytes + 1023u) & ~1023u;
   uint8_t* s_w = smem;
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
               const int c0 = (int)(pk & 7u), c1 = (int)((pk >> 3) & 7u), boff = (int)((pk >> 6) & 3u);
               const bool has_new = ((pk >> 8) & 1u) != 0;
               const int n0 = (int)((pk >> 9) & 7u), n1 = (int)((pk >> 12) & 7u);
-              const uint32_t tf = (pk >> 15) & 15u, sl = (pk >> 19) & 31u, tf1 = (pk >> 24) & 15u;
+              const uint32_t tf = (pk >> 15) & 31u, sl = (pk >> 20) & 31u, tf1 = (pk >> 25) & 31u;
               // instruction descriptor for c accumulator blocks: N = c * Cout sits in bits 17.. (make_idesc)
               const uint32_t id_c0 = id_0 + (uint32_t)c0 * id_step, id_c1 = id_0 + (uint32_t)c1 * id_step,
                              id_n0 = id_0 + (uint32_t)n0 * id_step, id_n1 = id_0 + (uint32_t)n1 * id_step,
@@ -567,8 +569,8 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
                 else
                   tc_issue_row<N, KS, NKS, PST16, false, TF, -1>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
                                                                id_c1, id_n0, id_n1, id_1);
-                if (tf != 15u) tc_commit(smem_u32(&sb->tfull[tf]));              // this row was the accumulator's last input row
-                if (ISS2 && tf1 != 15u) tc_commit(smem_u32(&sb->tfull[tf1]));    // ... its last but one
+                if (tf != 31u) tc_commit(smem_u32(&sb->tfull[tf]));              // this row was the accumulator's last input row
+                if (ISS2 && tf1 != 31u) tc_commit(smem_u32(&sb->tfull[tf1]));    // ... its last but one
                 tc_commit(smem_u32(&sb->empty[sl]));                             // ring row consumed
               }
               __syncwarp();
@@ -618,13 +620,13 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
             // blocks that already hold partial sums (step 0 accumulates into them) per run
             const int n0 = has_new ? (c1 ? c0 : c0 - 1) : c0;
             const int n1 = has_new ? (c1 ? c1 - 1 : 0) : c1;
-            const int tf = (j >= KS - 1) ? ((qg + j - (KS - 1)) & (ACC - 1)) : 15;   // accumulator this row completes
+            const int tf = (j >= KS - 1) ? ((qg + j - (KS - 1)) & (ACC - 1)) : 31;   // accumulator this row completes
             // accumulator whose last but one input row this is (two issuers: its owner commits to it as well)
-            const int tf1 = (j >= KS - 2 && j - (KS - 2) <= TH - 1) ? ((qg + j - (KS - 2)) & (ACC - 1)) : 15;
+            const int tf1 = (j >= KS - 2 && j - (KS - 2) <= TH - 1) ? ((qg + j - (KS - 2)) & (ACC - 1)) : 31;
             plan.x = (a_base16 + (uint32_t)(sl * Ps)) | (plane_stride16 << 16);
             plan.y = tmem_base + (uint32_t)(sa * N);
             plan.z = (uint32_t)c0 | ((uint32_t)c1 << 3) | ((uint32_t)boff << 6) | ((uint32_t)has_new << 8) | ((uint32_t)n0 << 9) |
-                     ((uint32_t)n1 << 12) | ((uint32_t)tf << 15) | ((uint32_t)sl << 19) | ((uint32_t)tf1 << 24);
+                     ((uint32_t)n1 << 12) | ((uint32_t)tf << 15) | ((uint32_t)sl << 20) | ((uint32_t)tf1 << 25);
           }
           plan.w = (uint32_t)ju | ((item + 1 == it_end && j0 + unit >= nrows) ? 256u : 0u);   // rows of the unit | the CTA's last unit
           if (lane == 0) mbar_wait(smem_u32(&sb->plan_empty[pp]), pph ^ 1u, 6);
@@ -1087,7 +1089,8 @@ static bool tc_geometry(const Plan* p, int nch_in, int N, int n_ent, int max_lbo
   g->m = (127 + 2 * pad + max_lbo_pos + g->Ps - 1) / g->Ps;   // rows mirrored behind the ring end
   if (rs) g->m = 0;                                            // row-streaming tiles never leave their ring row
   const size_t row_bytes = (size_t)nch_in * g->Ps * 16;
-  const size_t budget = (size_t)227 * 1024 - round_up((int)g->w_bytes, 1024) - 1024 - sizeof(TcSmem);
+  // (exactly what g->smem adds up below: the fp16 C = 64 ring keeps its 9th row by ~600 bytes)
+  const size_t budget = (size_t)227 * 1024 - round_up((int)g->w_bytes, 1024) - sizeof(TcSmem) - 64;
   int rows = (int)(budget / row_bytes);
   int R = rows - g->m;
   if (R > TC_MAX_RING) R = TC_MAX_RING;

@@ -280,7 +280,7 @@ __device__ __forceinline__ float rcp_sub(float x) { float r; asm("rcp.approx.f32
 
 // F16: IEEE half (else bfloat16) for the 16-bit outputs (pl0; the seeds when seed_half != 0)
 template <int KMAX, bool FUSED, bool F16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, KMAX <= 8 ? 5 : (KMAX <= 12 ? 3 : 2))
 mixture_fast_kernel(const float* __restrict__ out4, const float* __restrict__ x,
                     float* __restrict__ seed4, float* __restrict__ auxs, float* __restrict__ lik,
                     double* __restrict__ stats, double* __restrict__ accum,
@@ -306,20 +306,28 @@ mixture_fast_kernel(const float* __restrict__ out4, const float* __restrict__ x,
   const uint32_t so_wrap = ((uint32_t)B * (uint32_t)Kl - (uint32_t)Kl + 1u) * (uint32_t)HW;
   float lmax = -INFINITY;
   {
-  uint32_t so = so_first; int kk = 0;
+    // all K loads first (one round trip to HBM instead of K), then the arithmetic
+    float4 v[KMAX];
+    uint32_t so = so_first; int kk = 0;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    mk[k] = -INFINITY; lgr[k] = 0.f; mr[k] = mg[k] = mb[k] = 0.f; pr[k] = pg[k] = pb[k] = 0.f; Lk[k] = 0.f;
-    if (k < K) {
-      const float4 v = o4[so];
-      if (++kk == Kl) { kk = 0; so += so_wrap; } else so += (uint32_t)HW;
-      mr[k] = rcp_fast(1.f + ex2_ftz(-v.x * L2E));
-      mg[k] = rcp_fast(1.f + ex2_ftz(-v.y * L2E));
-      mb[k] = rcp_fast(1.f + ex2_ftz(-v.z * L2E));
-      mk[k] = v.w; lgr[k] = v.w;
-      lmax = fmaxf(lmax, v.w);
+    for (int k = 0; k < KMAX; ++k) {
+      v[k] = make_float4(0.f, 0.f, 0.f, -INFINITY);
+      if (k < K) {
+        v[k] = o4[so];
+        if (++kk == Kl) { kk = 0; so += so_wrap; } else so += (uint32_t)HW;
+      }
     }
-  }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      mk[k] = -INFINITY; lgr[k] = 0.f; mr[k] = mg[k] = mb[k] = 0.f; pr[k] = pg[k] = pb[k] = 0.f; Lk[k] = 0.f;
+      if (k < K) {
+        mr[k] = rcp_fast(1.f + ex2_ftz(-v[k].x * L2E));
+        mg[k] = rcp_fast(1.f + ex2_ftz(-v[k].y * L2E));
+        mb[k] = rcp_fast(1.f + ex2_ftz(-v[k].z * L2E));
+        mk[k] = v[k].w; lgr[k] = v[k].w;
+        lmax = fmaxf(lmax, v[k].w);
+      }
+    }
   }
   float den = 0.f;
 #pragma unroll
