@@ -417,6 +417,11 @@ def run_native(args):
     torch.cuda.synchronize()
     prof_ms = p0.elapsed_time(p1)
     conv_ms, conv_n = eng.profile_read()
+    # ... and the same for the pixel-mixture kernel (the "aux-input fuse" of BASELINE.json's north star: HBM-bound)
+    eng.profile(2)
+    step_device()
+    torch.cuda.synchronize()
+    mix_ms, mix_n = eng.profile_read()
     eng.profile(False)
     barrier()
 
@@ -579,6 +584,17 @@ def run_native(args):
                 'step_frac_executed': value / world * (f_unit - 2 * f_l1) / 1e12 / peak_tf,
                 'note': 'launches bracketed with CUDA events in a separate %d-step eager loop (%.2f ms/step); value/ms_per_step are from the CUDA-graph loop' % (psteps, prof_ms / psteps)},
         }
+        if mix_n:
+            # algorithmic bytes per launch: per slot-pixel the decoder output (16 B) in, the seeds (16 B) and the
+            # refinement input out (tensor-core modes: 16-bit plane 16 B + fp32 raw channels 24 B; fp32 mode: 48 B),
+            # per image-pixel the image (12 B) in and the likelihood (4 B) out
+            aux_bytes = B * K * S * S * (16 + 16 + (48 if args.precision == 'fp32' else 40)) + B * S * S * 16
+            gbs = aux_bytes / (mix_ms / mix_n * 1e-3) / 1e9
+            line['aux_fuse'] = {'bound': 'hbm', 'kernel': 'pixel mixture + aux-input assembly (%s)' % (
+                                    'mixture_kernel' if args.precision == 'fp32' else 'mixture_fast_kernel'),
+                                'achieved': gbs, 'peak': peak_gbs, 'unit': 'GB/s', 'frac': gbs / peak_gbs if peak_gbs else None,
+                                'algorithmic_bytes_per_launch': aux_bytes, 'launches_timed': int(mix_n),
+                                'avg_launch_ms': mix_ms / mix_n}
         if world == 1 and not args.no_variants and not args.profile_mode:
             line['variants'] = variants
         if world == 1 and not args.no_cpu_baseline:

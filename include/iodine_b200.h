@@ -264,7 +264,8 @@ IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, 
 /* Measurement hook (bench.py's roofline): while enabled, every decoder C->C convolution
  * launch (forward and data-gradient -- the dominant kernel) is bracketed by CUDA events on
  * the launching stream.  iodine_plan_profile_read() synchronises those events, returns
- * the summed device time in milliseconds and the number of bracketed launches, and resets. */
+ * the summed device time in milliseconds and the number of bracketed launches, and resets.
+ * enable = 2 brackets the pixel-mixture (aux-input fuse) kernel of every refinement step instead. */
 IODINE_API int iodine_plan_profile(IodinePlan* plan, int enable);
 IODINE_API int iodine_plan_profile_read(IodinePlan* plan, double* ms_total_out, uint64_t* launches_out);
 

@@ -85,7 +85,7 @@ struct Plan {
   bool weights_set = false;
   void* comm = nullptr;       // ncclComm_t installed by iodine_plan_set_comm (nullptr: single rank)
   int comm_rank = 0, comm_nranks = 1;
-  bool profiling = false;
+  int profiling = 0;          // iodine_plan_profile: 0 off, 1 decoder C->C convolutions, 2 pixel-mixture kernel
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
   size_t prof_used = 0;
 
@@ -229,6 +229,7 @@ int launch_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st);
 
 // ------------------------------------------------------------------ plan.cu pieces the training step reuses
 int plan_check_ready(Plan* p);
+void plan_prof_mark(Plan* p, cudaStream_t st, int cls);   // iodine_plan_profile bracket (cls 2: the pixel-mixture kernel)
 int plan_decoder_forward(Plan* p, const float* mu, const float* lv, const float* eps, const float* z_in, cudaStream_t st);
 int plan_allreduce_sum(Plan* p, float* buf, size_t count, cudaStream_t st);   // no-op without a communicator
 int launch_assemble(Plan* p, const float* x, cudaStream_t st);

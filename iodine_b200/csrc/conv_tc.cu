@@ -57,7 +57,7 @@ __host__ __device__ constexpr bool tc_iss2(int epi, bool rs, bool tf) { (void)tf
 __host__ __device__ constexpr int tc_threads(int N, bool rs = false, bool iss2 = false) {
   return 32 * (1 + TC_ISSUERS) + 32 * tc_epi_warps(N) + (rs ? 32 : 0) + (iss2 ? 32 : 0);
 }
-constexpr int TC_ACC_STAGES = 4;
+constexpr int TC_ACC_STAGES = 4;        // accumulator stages of the generic kernels (8 measured no faster: profiles/r2_issuer_experiments.md)
 constexpr int TC_RS_UNIT = 5;        // input rows per issue unit of the row-streaming variant (<= 16; TcParams::rs_unit < ring rows)
 constexpr int TC_RS_SLOTS = 8;       // accumulator slots of the row-streaming variant (one per output row in flight) ...
 constexpr int TC_RS_SLOTS_MAX = 16;  // ... 16 where they fit the 512 TMEM columns (N <= 32): the KS-slot window of a row then

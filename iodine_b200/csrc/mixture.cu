@@ -500,11 +500,13 @@ int launch_mixture(Plan* p, const float* x, bool want_grads, cudaStream_t st, bo
     else mixture_kernel<KM, FU, false><<<grid, 128, 0, st>>>(IOD_MIX_ARGS);               \
   } while (0)
   const bool f16o = half_is_f16(p) != 0;           // (seed_half == 1, bf16 seeds, only occurs with bf16 outputs)
+  if (want_grads) plan_prof_mark(p, st, 2);
   if (p->K_total <= 8) { if (fused) IOD_MIX(8, true); else IOD_MIX(8, false); }
   else if (p->K_total <= 12) { if (fused) IOD_MIX(12, true); else IOD_MIX(12, false); }
   else { if (fused) IOD_MIX(16, true); else IOD_MIX(16, false); }
 #undef IOD_MIX
 #undef IOD_MIX_ARGS
+  if (want_grads) plan_prof_mark(p, st, 2);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

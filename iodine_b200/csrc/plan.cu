@@ -100,8 +100,9 @@ __global__ void sample_kernel(const float* __restrict__ mu, const float* __restr
 }
 
 // ---------------------------------------------------------------- profiling brackets
-static void prof_mark(Plan* p, cudaStream_t st) {
-  if (!p->profiling) return;
+// cls: 1 = decoder C->C convolutions, 2 = the pixel-mixture (aux-input fuse) kernel
+static void prof_mark(Plan* p, cudaStream_t st, int cls = 1) {
+  if (p->profiling != cls) return;
   if (p->prof_used == p->prof_events.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -109,6 +110,8 @@ static void prof_mark(Plan* p, cudaStream_t st) {
   }
   cudaEventRecord(p->prof_events[p->prof_used++], st);
 }
+
+void plan_prof_mark(Plan* p, cudaStream_t st, int cls) { prof_mark(p, st, cls); }
 
 static int gather_out4(Plan* p, cudaStream_t st);
 
@@ -718,7 +721,7 @@ IODINE_API int iodine_debug_read(IodinePlan* plan, const char* name, void* dst, 
 IODINE_API int iodine_plan_profile(IodinePlan* plan, int enable) {
   Plan* p = reinterpret_cast<Plan*>(plan);
   IOD_REQUIRE(p, "null plan");
-  p->profiling = enable != 0;
+  p->profiling = enable;
   p->prof_used = 0;
   return 0;
 }

@@ -312,7 +312,7 @@ class RefinementEngine:
         return n.value
 
     def profile(self, enable):
-        _cabi.check(self.lib.iodine_plan_profile(self._plan, 1 if enable else 0))
+        _cabi.check(self.lib.iodine_plan_profile(self._plan, int(enable)))
 
     def profile_read(self):
         """(summed device ms of the bracketed decoder-conv launches, number of launches)"""
