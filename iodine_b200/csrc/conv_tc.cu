@@ -131,8 +131,8 @@ struct TcSmem {                    // tail of the dynamic shared memory block
   uint64_t tfull[TC_RS_SLOTS_MAX];
   uint64_t tempty[TC_RS_SLOTS_MAX];
   uint64_t wbar;
-  uint64_t plan_full[2];           // row-streaming: scout -> issuer, one issue unit of row plans is ready
-  uint64_t plan_empty[2];          // issuer -> scout
+  // row-streaming: the scout hands one issue unit of row plans at a time to the issuer(s); double-buffered, guarded by
+  // named barriers (3 + pp / 7 + pp: plans of buffer pp ready for issuer 0 / 1; 5 + pp: buffer pp consumed)
   uint4 plan[2][16];               // per row of the unit: {A base | LBO, first accumulator, packed counts, rows of the unit | last-unit flag}
   uint32_t tmem_base;
 };
@@ -229,6 +229,14 @@ __device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, ui
       }
     }
   }
+}
+
+// named barriers (ids 1..15; 0 is __syncthreads): whole warps only
+__device__ __forceinline__ void tc_named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tc_named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Walks the (work item, tile) sequence of one CTA; identical in every role.  A tile starts at flat
@@ -351,10 +359,6 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
       mbar_init(smem_u32(&sb->tempty[i]), EW);     // one arrive per epilogue warp
     }
     mbar_init(smem_u32(&sb->wbar), 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&sb->plan_full[i]), 1);
-      mbar_init(smem_u32(&sb->plan_empty[i]), ISS2 ? 2 : 1);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
         mbar_wait(smem_u32(&sb->wbar), 0, 2);
         const uint32_t w_base16 = smem_u32(s_w) >> 4;
         const uint32_t id_step = (uint32_t)(N >> 3) << 17, id_0 = p.idesc_n[1] - id_step;   // idesc of c blocks = id_0 + c id_step
-        int pp = 0; uint32_t pph = 0;
+        int pp = 0;
         int g = 0;                                 // running row number of the CTA
         for (int item = __ldg(p.coff + cta), it_end = __ldg(p.coff + cta + 1); item < it_end; ++item) {
           const int TH = __ldg(p.itab + item).z;   // rows of this item (1 .. H)
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
           const int unit = p.rs_unit;
           for (int j0 = 0; j0 < nrows; j0 += unit) {
             const int ju = (nrows - j0 < unit) ? nrows - j0 : unit;
-            mbar_wait(smem_u32(&sb->plan_full[pp]), pph, 3);
+            tc_named_sync((w ? 7 : 3) + pp, 64);   // the scout has published this unit's plans
             tc_fence_after();
             const uint4 mine = sb->plan[pp][lane & 15];
             const bool last_unit = item + 1 == it_end && j0 + unit >= nrows;
@@ -558,10 +562,7 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
               const uint32_t id_c0 = id_0 + (uint32_t)c0 * id_step, id_c1 = id_0 + (uint32_t)c1 * id_step,
                              id_n0 = id_0 + (uint32_t)n0 * id_step, id_n1 = id_0 + (uint32_t)n1 * id_step,
                              id_1 = id_0 + id_step;
-              if (ISS2 && g > 0) {                 // the previous row's burst has been issued
-                if (w == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
-                else asm volatile("bar.sync 1, 64;" ::: "memory");
-              }
+              if (ISS2 && g > 0) tc_named_sync(w == 0 ? 2 : 1, 64);   // the previous row's burst has been issued
               if (leader) {
                 if (c1 > 0)
                   tc_issue_row<N, KS, NKS, PST16, true, TF, -1>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
@@ -574,14 +575,11 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
                 tc_commit(smem_u32(&sb->empty[sl]));                             // ring row consumed
               }
               __syncwarp();
-              if (ISS2 && !(last_unit && u == ju - 1)) {   // hand the token on (nobody waits for the CTA's last row)
-                if (w == 0) asm volatile("bar.arrive 1, 64;" ::: "memory");
-                else asm volatile("bar.arrive 2, 64;" ::: "memory");
-              }
+              if (ISS2 && !(last_unit && u == ju - 1)) tc_named_arrive(w == 0 ? 1 : 2, 64);   // hand the token on (nobody waits for the CTA's last row)
             }
-            if (lane == 0) mbar_arrive(smem_u32(&sb->plan_empty[pp]));
+            __syncwarp();
+            tc_named_arrive(5 + pp, ISS2 ? 96 : 64);   // plans consumed
             pp ^= 1;
-            if (pp == 0) pph ^= 1u;
           }
         }
       }
@@ -595,12 +593,12 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
       const uint32_t a_base16 = smem_u32(s_a) >> 4;
       int slot = 0; uint32_t rph = 0;            // ring slot / phase of the next input row
       int qg = 0;                                // output rows (tiles) of all previous items of this CTA
-      int pp = 0; uint32_t pph = 0;
+      int pp = 0, nunit = 0;
       for (int item = __ldg(p.coff + cta), it_end = __ldg(p.coff + cta + 1); item < it_end; ++item) {
         const int TH = __ldg(p.itab + item).z;   // rows of this item (1 .. H)
         const int nrows = TH + 2 * pad;
         const int unit = p.rs_unit;
-        for (int j0 = 0; j0 < nrows; j0 += unit) {
+        for (int j0 = 0; j0 < nrows; j0 += unit, ++nunit) {
           const int ju = (nrows - j0 < unit) ? nrows - j0 : unit;
           uint4 plan = make_uint4(0u, 0u, 0u, 0u);
           {
@@ -629,7 +627,7 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
                      ((uint32_t)n1 << 12) | ((uint32_t)tf << 15) | ((uint32_t)sl << 20) | ((uint32_t)tf1 << 25);
           }
           plan.w = (uint32_t)ju | ((item + 1 == it_end && j0 + unit >= nrows) ? 256u : 0u);   // rows of the unit | the CTA's last unit
-          if (lane == 0) mbar_wait(smem_u32(&sb->plan_empty[pp]), pph ^ 1u, 6);
+          if (nunit >= 2) tc_named_sync(5 + pp, ISS2 ? 96 : 64);   // the unit that used this plan buffer has been issued
           // lane u waits on the ring row of unit row u, lane 16+u on the accumulator slot that row opens
           if (lane < ju) {
             int sl = slot + lane; uint32_t ph = rph;
@@ -642,9 +640,9 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
           __syncwarp();
           if (lane < ju) sb->plan[pp][lane] = plan;
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&sb->plan_full[pp]));
+          tc_named_arrive(3 + pp, 64);
+          if (ISS2) tc_named_arrive(7 + pp, 64);
           pp ^= 1;
-          if (pp == 0) pph ^= 1u;
           slot += ju;
           if (slot >= R) { slot -= R; rph ^= 1u; }
         }

@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(l0f_threads(N), 1) refine_l0f_kernel(const __g
       const int pos = tile_pos0(t, nt, th) + quad * 32 + lane;
       const int r = (int)__umulhi((uint32_t)pos, p.magicP), c = pos - r * P;
       valid = r < th && c < wv && (t == 0 || pos >= t * 128);
-      oy = y0 + r; ox = xoff + c;
+      if (valid) { oy = y0 + r; ox = xoff + c; }     // (discarded positions read table row 0)
     };
     auto advance = [&]() { if (++t >= nt) { item += gridDim.x; load_item(); } };
     load_item();
