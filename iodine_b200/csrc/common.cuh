@@ -143,6 +143,8 @@ struct Plan {
   void* r16[2];                   // refine conv ping-pong, 16-bit chunk-planar (16-bit modes)
   float* z = nullptr;             // [BK,L]
   float* u = nullptr;             // [BK,n_class,C]
+  float* eu = nullptr;            // [BK,n_class,C] exp(u) (tensor-core modes: tc_layer1_kernel multiplies instead of evaluating)
+  int* ubig = nullptr;            // [BK] 1 where a slot's |u| exceeds the range in which exp(u) * exp(p) is safe
   float* G = nullptr;             // [BK,n_class,C] class-wise pixel sums of dJ/d(pre-act 1)
   float* dz = nullptr;            // [BK,L]
   double* stats = nullptr;        // [BK,4,2] (sum, sumsq) for grad_means/grad_mask/lik/loo
@@ -169,6 +171,9 @@ struct Plan {
   float* log_mask = nullptr;      // [K,H,W]
   float* log_mean = nullptr;      // [K,3,H,W]
 };
+
+// collapsed first decoder layer, tensor-core modes: |u|, |p| up to which exp(u + p) is formed as exp(u) * exp(p)
+#define IOD_L1_EXP_RANGE 40.f
 
 // split-K factor of the LSTM gate GEMM (head.cu); the gates buffer holds that many partial sums
 constexpr int LSTM_KSPLIT = 8;

@@ -1011,6 +1011,8 @@ struct TcState {
   uint16_t* w_out = nullptr;             // decoder.conv forward, N = 16 (4 real rows)
   uint16_t* w_in4 = nullptr;             // decoder.conv data-gradient, tap pairs
   float* ptab_c = nullptr;                    // chunk-planar fp32 copy of ptab
+  float* eptab_c = nullptr;                   // exp() of it (clamped to +-IOD_L1_EXP_RANGE), same layout
+  int* pbig = nullptr;                        // 1 if any |ptab| exceeds that range (then tc_layer1_kernel evaluates exp)
   int n_ent_cc = 0, n_ent_in4 = 0;
   TcGeom g_cc, g_out, g_in4;
   // row-streaming variant (W == 128): weight images with the KS tap rows stacked along N, own geometry
@@ -1210,6 +1212,8 @@ int tc_alloc(Plan* p) {
   IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_out, st->g_out.w_bytes));
   IOD_CHECK_CUDA(cudaMalloc((void**)&st->w_in4, (size_t)st->g_in4.w_bytes * st->nsplit_in4));
   IOD_CHECK_CUDA(cudaMalloc((void**)&st->ptab_c, (size_t)p->HW * C * sizeof(float)));
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->eptab_c, (size_t)p->HW * C * sizeof(float)));
+  IOD_CHECK_CUDA(cudaMalloc((void**)&st->pbig, sizeof(int)));
   return 0;
 }
 
@@ -1222,7 +1226,7 @@ void tc_free(Plan* p) {
   cudaFree(st->w_out_rs);
   cudaFree(st->zero_row);
   for (int i = 0; i < 2; ++i) { cudaFree(st->itab[i]); cudaFree(st->coff[i]); }
-  cudaFree(st->w_out); cudaFree(st->w_in4); cudaFree(st->ptab_c);
+  cudaFree(st->w_out); cudaFree(st->w_in4); cudaFree(st->ptab_c); cudaFree(st->eptab_c); cudaFree(st->pbig);
   delete st;
   p->tc = nullptr;
 }
@@ -1314,6 +1318,17 @@ __global__ void tc_pack_in4_kernel(const float* __restrict__ w, void* __restrict
     else reinterpret_cast<uint16_t*>(img)[j] = to_h(v, f16);
   }
 }
+// eptab_c = exp(clamp(ptab_c)); *pbig = 1 if the clamp was ever active
+__global__ void tc_ptab_exp_kernel(const float* __restrict__ ptab_c, float* __restrict__ eptab_c, int* __restrict__ pbig, int n) {
+  int big = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float v = ptab_c[i];
+    eptab_c[i] = expf(fminf(fmaxf(v, -IOD_L1_EXP_RANGE), IOD_L1_EXP_RANGE));
+    big |= !(fabsf(v) <= IOD_L1_EXP_RANGE);
+  }
+  if (__syncthreads_or(big) && threadIdx.x == 0) atomicOr(pbig, 1);
+}
+
 __global__ void tc_ptab_planar_kernel(const float* __restrict__ ptab, float* __restrict__ ptab_c, int HW, int C, int PW) {
   const int total = HW * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -1344,6 +1359,9 @@ int tc_setup_weights(Plan* p, const IodineWeights* w, cudaStream_t st_) {
     IOD_LAUNCH_CHECK(p);
   }
   tc_ptab_planar_kernel<<<256, 256, 0, st_>>>(p->ptab, st->ptab_c, p->HW, C, st->pw);   // after pack_ptab (same stream)
+  IOD_LAUNCH_CHECK(p);
+  IOD_CHECK_CUDA(cudaMemsetAsync(st->pbig, 0, sizeof(int), st_));
+  tc_ptab_exp_kernel<<<256, 256, 0, st_>>>(st->ptab_c, st->eptab_c, st->pbig, p->HW * C);
   IOD_LAUNCH_CHECK(p);
   return 0;
 }
@@ -1636,45 +1654,78 @@ int tc_rs_worklist(const Plan* p, int which, const int4** itab, const int32_t** 
 // act0[n][k][y][x][8] = ELU(u[n][class(y,x)][co] + ptab_c[k][y][x][8])   (first decoder layer, collapsed)
 // A thread owns one (pixel, 8-channel plane) and walks TC_L1_NB slot-images with the coordinate-table
 // values in registers (the table is read once per group of images, not once per image).
-constexpr int TC_L1_NB = 8;
+constexpr int TC_L1_NB = 32;             // slots per thread: the pixel's table entries (64 B from L2) are read once per TC_L1_NB stores of 16 B
 // mode: 0 = bf16 planes of 8, 1 = fp16 planes of 8, 2 = tf32 planes of 4 (two planes per thread, same 8 channels)
-__global__ void __launch_bounds__(256)
-tc_layer1_kernel(const float* __restrict__ u, const float* __restrict__ ptab_c, uint4* __restrict__ act0,
-                 int H, int W, int C, int KS, int BK, int mode) {
+// ELU needs exp(u + p) for the non-positive pre-activations.  u depends on (slot, border class, channel), p on (pixel,
+// channel): exp(u) (sample_u_kernel) and exp(p) (tc_ptab_exp_kernel, once per weight load) are tables, and the kernel
+// multiplies -- 4 instructions per value instead of 7 and no MUFU (235 M exponentials per launch at 16 per clock and SM
+// were 52 us of the kernel's 138).  Slots / weights whose |u| / |p| leave +-IOD_L1_EXP_RANGE take the evaluated form.
+template <int mode>
+__global__ void __launch_bounds__(256, 4)
+tc_layer1_kernel(const float* __restrict__ u, const float* __restrict__ eu, const int* __restrict__ ubig,
+                 const float* __restrict__ ptab_c, const float* __restrict__ eptab_c, const int* __restrict__ pbig,
+                 uint4* __restrict__ act0, int H, int W, int C, int KS, int BK) {
   const int k = blockIdx.y;                            // group of 8 channels
   const int P = KS / 2, HW = H * W;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= HW) return;
   const int y = pix / W, x = pix - y * W;
   const int cls = border_class(y, H, P) * KS + border_class(x, W, P);
-  float4 p0, p1;
+  float4 p0, p1, e0, e1;
   if (mode == 2) {                                     // ptab_c is [C/4][HW][4]
-    p0 = __ldg(reinterpret_cast<const float4*>(ptab_c + ((size_t)(2 * k) * HW + pix) * 4));
-    p1 = __ldg(reinterpret_cast<const float4*>(ptab_c + ((size_t)(2 * k + 1) * HW + pix) * 4));
+    const size_t i0 = ((size_t)(2 * k) * HW + pix) * 4, i1 = ((size_t)(2 * k + 1) * HW + pix) * 4;
+    p0 = __ldg(reinterpret_cast<const float4*>(ptab_c + i0));
+    p1 = __ldg(reinterpret_cast<const float4*>(ptab_c + i1));
+    e0 = __ldg(reinterpret_cast<const float4*>(eptab_c + i0));
+    e1 = __ldg(reinterpret_cast<const float4*>(eptab_c + i1));
   } else {                                             // [C/8][HW][8]
-    const float4* pv = reinterpret_cast<const float4*>(ptab_c + ((size_t)k * HW + pix) * 8);
+    const size_t i0 = ((size_t)k * HW + pix) * 8;
+    const float4* pv = reinterpret_cast<const float4*>(ptab_c + i0);
+    const float4* ev = reinterpret_cast<const float4*>(eptab_c + i0);
     p0 = __ldg(pv); p1 = __ldg(pv + 1);
+    e0 = __ldg(ev); e1 = __ldg(ev + 1);
   }
   const int n0 = blockIdx.z * TC_L1_NB;
   const int n1 = (n0 + TC_L1_NB < BK) ? n0 + TC_L1_NB : BK;
-#pragma unroll 4
-  for (int n = n0; n < n1; ++n) {
-    const float4* uv = reinterpret_cast<const float4*>(u + ((size_t)n * KS * KS + cls) * C + k * 8);
-    const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
-    // hardware exponential: |error| ~1e-7 absolute, far below the operand rounding that follows (the
-    // libm expm1f made this bandwidth-bound kernel compute-bound)
-    const float v0 = elu_fast(u0.x + p0.x), v1 = elu_fast(u0.y + p0.y), v2 = elu_fast(u0.z + p0.z), v3 = elu_fast(u0.w + p0.w),
-                v4 = elu_fast(u1.x + p1.x), v5 = elu_fast(u1.y + p1.y), v6 = elu_fast(u1.z + p1.z), v7 = elu_fast(u1.w + p1.w);
+  // one decision for the block's slots, taken before the loop (a per-slot test would put a dependent load and a branch
+  // in front of every iteration's loads)
+  bool big = __ldg(pbig) != 0;
+  for (int n = n0; n < n1; ++n) big |= __ldg(ubig + n) != 0;
+  // pointers stepped per slot (the index arithmetic of the straightforward form was half of the kernel's instructions)
+  const size_t u_step = (size_t)KS * KS * C / 4;                       // float4 per slot
+  const float4* up = reinterpret_cast<const float4*>(u + ((size_t)n0 * KS * KS + cls) * C + k * 8);
+  const float4* xp = reinterpret_cast<const float4*>(eu + ((size_t)n0 * KS * KS + cls) * C + k * 8);
+  const size_t o_step = (size_t)(mode == 2 ? C / 4 : C / 8) * HW;      // uint4 per slot
+  uint4* op = act0 + ((size_t)n0 * (mode == 2 ? C / 4 : C / 8) + (mode == 2 ? 2 * k : k)) * HW + pix;
+  auto store = [&](float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
     if (mode == 2) {
-      const uint4 a = make_uint4(__float_as_uint(to_tf32(v0)), __float_as_uint(to_tf32(v1)), __float_as_uint(to_tf32(v2)), __float_as_uint(to_tf32(v3)));
-      const uint4 b = make_uint4(__float_as_uint(to_tf32(v4)), __float_as_uint(to_tf32(v5)), __float_as_uint(to_tf32(v6)), __float_as_uint(to_tf32(v7)));
-      act0[((size_t)n * (C / 4) + 2 * k) * HW + pix] = a;
-      act0[((size_t)n * (C / 4) + 2 * k + 1) * HW + pix] = b;
+      op[0] = make_uint4(__float_as_uint(to_tf32(v0)), __float_as_uint(to_tf32(v1)), __float_as_uint(to_tf32(v2)), __float_as_uint(to_tf32(v3)));
+      op[HW] = make_uint4(__float_as_uint(to_tf32(v4)), __float_as_uint(to_tf32(v5)), __float_as_uint(to_tf32(v6)), __float_as_uint(to_tf32(v7)));
     } else {
       uint4 o;
       o.x = pack_h2(v0, v1, mode); o.y = pack_h2(v2, v3, mode); o.z = pack_h2(v4, v5, mode); o.w = pack_h2(v6, v7, mode);
-      act0[((size_t)n * (C / 8) + k) * HW + pix] = o;
+      op[0] = o;
     }
+    op += o_step;
+  };
+  if (big) {
+#pragma unroll 4
+    for (int n = n0; n < n1; ++n) {
+      const float4 u0 = __ldg(up), u1 = __ldg(up + 1);
+      up += u_step;
+      // hardware exponential: |error| ~1e-7 absolute, far below the operand rounding that follows
+      store(elu_fast(u0.x + p0.x), elu_fast(u0.y + p0.y), elu_fast(u0.z + p0.z), elu_fast(u0.w + p0.w),
+            elu_fast(u1.x + p1.x), elu_fast(u1.y + p1.y), elu_fast(u1.z + p1.z), elu_fast(u1.w + p1.w));
+    }
+    return;
+  }
+  auto elu2 = [](float uu, float pp, float eu_, float ep_) { const float pre = uu + pp; return pre > 0.f ? pre : fmaf(eu_, ep_, -1.f); };
+#pragma unroll 4
+  for (int n = n0; n < n1; ++n) {
+    const float4 u0 = __ldg(up), u1 = __ldg(up + 1), x0 = __ldg(xp), x1 = __ldg(xp + 1);
+    up += u_step; xp += u_step;
+    store(elu2(u0.x, p0.x, x0.x, e0.x), elu2(u0.y, p0.y, x0.y, e0.y), elu2(u0.z, p0.z, x0.z, e0.z), elu2(u0.w, p0.w, x0.w, e0.w),
+          elu2(u1.x, p1.x, x1.x, e1.x), elu2(u1.y, p1.y, x1.y, e1.y), elu2(u1.z, p1.z, x1.z, e1.z), elu2(u1.w, p1.w, x1.w, e1.w));
   }
 }
 
@@ -1683,8 +1734,11 @@ static int plane_mode(const Plan* p) { return tf_mode(p) ? 2 : (p->s.precision =
 int tc_launch_layer1(Plan* p, void* act0, cudaStream_t st_) {
   TcState* st = tc_state(p);
   dim3 grid((p->HW + 255) / 256, p->C / 8, (p->BK + TC_L1_NB - 1) / TC_L1_NB);
-  tc_layer1_kernel<<<grid, 256, 0, st_>>>(p->u, st->ptab_c, reinterpret_cast<uint4*>(act0), p->s.H, p->s.W, p->C,
-                                          p->s.dec_k, p->BK, plane_mode(p));
+#define IOD_L1(m) tc_layer1_kernel<m><<<grid, 256, 0, st_>>>(p->u, p->eu, p->ubig, st->ptab_c, st->eptab_c, st->pbig, \
+                                                      reinterpret_cast<uint4*>(act0), p->s.H, p->s.W, p->C, p->s.dec_k, p->BK)
+  const int pm = plane_mode(p);
+  if (pm == 2) IOD_L1(2); else if (pm == 1) IOD_L1(1); else IOD_L1(0);
+#undef IOD_L1
   IOD_LAUNCH_CHECK(p);
   return 0;
 }

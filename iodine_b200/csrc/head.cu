@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256)
 sample_u_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
                 const float* __restrict__ eps, const float* __restrict__ z_in,
                 const float* __restrict__ wsumT, float* __restrict__ z_out, float* __restrict__ u,
-                int L, int C, int NCC /* n_class*C */) {
+                int L, int C, int NCC /* n_class*C */, float* __restrict__ eu, int* __restrict__ ubig) {
   extern __shared__ float sz[];
   const int n = blockIdx.x;
   for (int i = threadIdx.x; i < L; i += blockDim.x) {
@@ -177,6 +177,7 @@ sample_u_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
     z_out[(size_t)n * L + i] = z;
   }
   __syncthreads();
+  int big = 0;
   for (int o = threadIdx.x; o < NCC; o += blockDim.x) {
     const int cls = o / C, co = o - cls * C;
     const float* wr = wsumT + (size_t)cls * L * C + co;
@@ -187,7 +188,18 @@ sample_u_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
       s1 = fmaf(__ldg(wr + (size_t)(i + 1) * C), sz[i + 1], s1);
     }
     if (i < L) s0 = fmaf(__ldg(wr + (size_t)i * C), sz[i], s0);
-    u[(size_t)n * NCC + o] = s0 + s1;
+    const float uv = s0 + s1;
+    u[(size_t)n * NCC + o] = uv;
+    // tc_layer1_kernel forms exp(u + p) as exp(u) * exp(p) (conv_tc.cu): safe while both factors stay far from the ends
+    // of the fp32 range -- outside |u| <= IOD_L1_EXP_RANGE the slot is flagged and takes the evaluated exponential
+    if (eu) {
+      eu[(size_t)n * NCC + o] = expf(fminf(fmaxf(uv, -IOD_L1_EXP_RANGE), IOD_L1_EXP_RANGE));
+      big |= !(fabsf(uv) <= IOD_L1_EXP_RANGE);
+    }
+  }
+  if (ubig) {
+    big = __syncthreads_or(big);
+    if (threadIdx.x == 0) ubig[n] = big;
   }
 }
 
@@ -226,7 +238,8 @@ int launch_sample_l1(Plan* p, const float* mu, const float* logvar, const float*
   const IodineShape& s = p->s;
   const int ncc = p->n_class * p->C;
   sample_u_kernel<<<p->BK, 256, s.L * sizeof(float), st>>>(mu, logvar, eps, z_in, p->wsumT, p->z, p->u,
-                                                           s.L, p->C, ncc);
+                                                           s.L, p->C, ncc, tc_mode(p) ? p->eu : nullptr,
+                                                           tc_mode(p) ? p->ubig : nullptr);
   IOD_LAUNCH_CHECK(p);
   const int per = p->HW * (p->C / 4);
   dim3 grid((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256, p->BK);

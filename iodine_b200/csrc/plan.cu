@@ -56,6 +56,8 @@ static size_t carve(Plan* p, char* base) {
   p->r16[1] = take(rtc ? BK * r1 * 2 : 1024);
   p->z = (float*)take(BK * L * sizeof(float));
   p->u = (float*)take(BK * p->n_class * C * sizeof(float));
+  p->eu = (float*)take(BK * p->n_class * C * sizeof(float));
+  p->ubig = (int*)take(BK * sizeof(int));
   p->G = (float*)take(BK * p->n_class * C * sizeof(float));
   p->dz = (float*)take(BK * L * sizeof(float));
   p->stats = (double*)take(BK * 8 * sizeof(double));

@@ -118,3 +118,35 @@ def test_16bit_full_size_matches_fp32_path_clevr6_b4(prec, bar):
     errs = {'pred': rel_err(p16, p32), 'mask': rel_err(k16, k32), 'elbo': rel_err(e16, e32)}
     print(prec, {k: '%.2e' % v for k, v in errs.items()})
     assert max(errs.values()) < bar, errs
+
+
+@pytest.mark.parametrize('name,over,B,prec', [
+    ('clevr6', dict(iters=2, slots=3), 2, 'fp16'),                          # the fused kernel's flagship shape
+    ('dsprites', dict(iters=2), 2, 'tf32'),                                  # 64x64: Wo = 32, one narrow segment
+    ('tiny', dict(img_size=256, dec_chan=16, dec_layers=2, slots=9, iters=1, ref_chan=32), 1, 'fp16'),   # two segments, K > 8
+    ('tiny', dict(iters=2), 3, 'bf16'),                                      # 16x16: tiny items (TR = 1)
+])
+def test_fused_aux_path_matches_separate_assembly(name, over, B, prec, monkeypatch):
+    """mixture_fast_kernel<FUSED> + refine_l0f_kernel (no assembled refinement input in HBM) against the same library with
+    IODINE_NO_AUX_FUSE=1 (raw fp32 aux channels -> assemble16_kernel -> 16-byte gather kernel): the same reconstruction
+    up to the 16-bit rounding of the refinement encoder's first layer (the x-coordinate plane is a rounded operand
+    channel in the fused kernel and an fp32 table entry in the other)."""
+    arch = A.arch_by_name(name, **over)
+    K, L, H = arch.SLOTS, arch.DIM_LATENT, arch.IMG_SIZE
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(B, 3, H, H, generator=g).to(DEV)
+    eps = torch.randn(arch.ITERS + 1, B, K, L, generator=g).to(DEV)
+    res = []
+    for nofuse in (False, True):
+        if nofuse:
+            monkeypatch.setenv('IODINE_NO_AUX_FUSE', '1')
+        else:
+            monkeypatch.delenv('IODINE_NO_AUX_FUSE', raising=False)
+        m = seeded_model(arch, 2.0, precision=prec).to(DEV)
+        pred, mask, mean = m.reconstruct(x, eps=eps)
+        torch.cuda.synchronize()
+        res.append((pred.clone(), mask.clone(), m.elbo_per_step(B).clone()))
+    tol = 6e-3 if prec == 'bf16' else 1e-3
+    assert rel_err(res[0][0], res[1][0]) < tol
+    assert rel_err(res[0][1], res[1][1]) < tol
+    assert rel_err(res[0][2], res[1][2]) < tol
