@@ -1386,10 +1386,16 @@ static void fill_common(const Plan* p, const TcGeom& g, int nch_in, int N, int n
   q->Ps = g.Ps; q->R = g.R; q->m = g.m; q->segs = g.segs; q->TH = g.TH;
   q->strips = (s.H + g.TH - 1) / g.TH;
   q->rs_segs = 0;
-  q->rs_unit = g.R >= 7 ? TC_RS_UNIT : (g.R / 2 > 0 ? g.R / 2 : 1);
-  if (getenv("IODINE_TC_RS_UNIT")) {                       // experiment: rows per issue unit (must stay below the ring depth)
+  // rows per issue unit.  Short rings (tf32: 4 rows of 34.8 KB) hand rows over one at a time now that the scout warp
+  // takes the waits: a ring row is requested again as soon as its own MMAs have completed (52.7k against 50.8k steps/s
+  // with units of two rows, profiles/r2_issuer_experiments.md)
+  q->rs_unit = g.R >= 7 ? TC_RS_UNIT : 1;
+  if (getenv("IODINE_TC_RS_UNIT")) {                       // experiment: rows per issue unit
     const int u = atoi(getenv("IODINE_TC_RS_UNIT"));
-    if (u >= 1 && u < g.R && u <= 16) q->rs_unit = u;
+    // below the ring depth, and a unit's fresh accumulators + the KS-1 still open ones must fit the slot ring (the scout
+    // waits for all of a unit's slots before releasing it: a larger unit would wait for rows it has not released yet)
+    const int acc = N <= 32 ? TC_RS_SLOTS_MAX : TC_RS_SLOTS;
+    if (u >= 1 && u < g.R && u <= 16 && u + s.dec_k - 1 <= acc - 1) q->rs_unit = u;
   }
   q->rev = 0;
   q->itab = nullptr;
