@@ -22,16 +22,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// suspend-time hint of try_wait (ns): the thread sleeps in hardware until the phase completes or the hint expires, instead
+// of coming back every few hundred cycles to spin -- waiting warps then stop taking issue slots from the working ones
+#ifndef IOD_TRYWAIT_HINT_NS
+#define IOD_TRYWAIT_HINT_NS 20000u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(IOD_TRYWAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
