@@ -609,7 +609,9 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
             // output rows of this strip fed by input row j: q in [j-(KS-1), j] clipped to the strip
             const int qa = (j - (KS - 1) > 0) ? j - (KS - 1) : 0;
             const int qb = (j < TH - 1) ? j : TH - 1;
-            const int has_new = j <= TH - 1;                   // row q = j: overwrite on its first step
+            // row q = j opens a fresh accumulator: the epilogue left the slot zeroed when it drained its previous row, so only
+            // a slot's FIRST row of the kernel (TMEM is not initialised) overwrites on its first step
+            const int has_new = (j <= TH - 1) && (qg + j < ACC);
             const int cnt = qb - qa + 1;                       // accumulator blocks written by this row
             const int sa = (qg + qa) & (ACC - 1);              // slot of the first one
             const int c0 = (cnt < ACC - sa) ? cnt : ACC - sa;  // blocks before the slot ring wraps
@@ -867,6 +869,16 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
         for (int q = 0; q < NC / 16; ++q) IOD_TMEM_LD16((acc + q * 16), taddr + q * 16);
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if constexpr (RS) {
+        // row-streaming: leave the slot ZEROED for its next output row, so that the row's first MMA accumulates like
+        // every other one (an overwriting first step would have to be a separate N = Cout instruction next to the
+        // accumulating N = 2 Cout one: one more pass over the A operand per row)
+        if (!(p.dbg & 1)) {
+#pragma unroll
+          for (int q = 0; q < NC / 16; ++q) tmem_zero16(taddr + q * 16);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[stage]));   // accumulator stage is free again

@@ -134,6 +134,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, u
         "=r"(r[14]), "=r"(r[15])                                                                \
       : "r"(addr))
 
+// zero 16 accumulator columns of this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+
 // ELU with the hardware exponential: |error| <= ~2e-7 absolute, far below bf16 rounding.
 // Branch-free form with the flush-to-zero ex2 (the non-ftz __expf carries extra scaling instructions for
 // subnormals, and the ELU-heavy kernels are instruction-issue bound): max(v,0) + (2^(min(v,0) log2 e) - 1).
