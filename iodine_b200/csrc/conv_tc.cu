@@ -197,9 +197,7 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, const uint32_t (&
 // WRAP: the accumulator blocks straddle the end of the slot ring (second run from slot 0) -- a compile-time
 // flag so that the common case carries no predicated-off instructions; id0/id1/id1n/idn are the instruction
 // descriptors (N = blocks * Cout) loaded once per row, not once per MMA.
-// HALF: -1 = the whole row; 0 / 1 = the first / second half of its (dx, K-step) sequence (experiment: the next row's
-// bookkeeping between the halves was slower, profiles/r2_issuer_experiments.md)
-template <int N, int KS, int NKS, int PST16, bool WRAP, bool TF, int HALF>
+template <int N, int KS, int NKS, int PST16, bool WRAP, bool TF>
 __device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, uint32_t rb, const uint32_t (&a_off)[40],
                                              uint32_t w_base16, int c0, int c1, int boff, bool has_new, int n0, int n1,
                                              uint32_t id_c0, uint32_t id_c1, uint32_t id_n0, uint32_t id_n1, uint32_t id_1) {
@@ -215,7 +213,6 @@ __device__ __forceinline__ void tc_issue_row(uint32_t tmem_base, uint32_t d0, ui
 #pragma unroll
     for (int ks = 0; ks < NKS; ++ks) {
       const int e = dx * NKS + ks;
-      if ((HALF == 0 && e >= (KS * NKS) / 2) || (HALF == 1 && e < (KS * NKS) / 2)) continue;
       const uint32_t off = PST16 ? (uint32_t)(dx + 2 * ks * PST16) : a_off[dx * NKS + ks];
       const uint64_t ad = DESC_HI | (rb + off);
       const uint32_t eo = (uint32_t)e * 2u * NB;
@@ -565,10 +562,10 @@ __global__ void __launch_bounds__(tc_threads(N, RS, tc_iss2(EPI, RS, TF)), 1) co
               if (ISS2 && g > 0) tc_named_sync(w == 0 ? 2 : 1, 64);   // the previous row's burst has been issued
               if (leader) {
                 if (c1 > 0)
-                  tc_issue_row<N, KS, NKS, PST16, true, TF, -1>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
+                  tc_issue_row<N, KS, NKS, PST16, true, TF>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
                                                               id_c1, id_n0, id_n1, id_1);
                 else
-                  tc_issue_row<N, KS, NKS, PST16, false, TF, -1>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
+                  tc_issue_row<N, KS, NKS, PST16, false, TF>(tmem_base, d0, rb, p.a_off, wb_t, c0, c1, boff, has_new, n0, n1, id_c0,
                                                                id_c1, id_n0, id_n1, id_1);
                 if (tf != 31u) tc_commit(smem_u32(&sb->tfull[tf]));              // this row was the accumulator's last input row
                 if (ISS2 && tf1 != 31u) tc_commit(smem_u32(&sb->tfull[tf1]));    // ... its last but one
