@@ -125,6 +125,8 @@ def test_16bit_full_size_matches_fp32_path_clevr6_b4(prec, bar):
     ('dsprites', dict(iters=2), 2, 'tf32'),                                  # 64x64: Wo = 32, one narrow segment
     ('tiny', dict(img_size=256, dec_chan=16, dec_layers=2, slots=9, iters=1, ref_chan=32), 1, 'fp16'),   # two segments, K > 8
     ('tiny', dict(iters=2), 3, 'bf16'),                                      # 16x16: tiny items (TR = 1)
+    ('tiny', dict(img_size=144, slots=2, iters=1, ref_chan=16), 1, 'fp16'),  # Wo = 72: a full and a partial column segment
+    ('tiny', dict(img_size=20, slots=2, iters=2), 2, 'tf32'),                # Ho = 10: a short last strip
 ])
 def test_fused_aux_path_matches_separate_assembly(name, over, B, prec, monkeypatch):
     """mixture_fast_kernel<FUSED> + refine_l0f_kernel (no assembled refinement input in HBM) against the same library with
