@@ -9,6 +9,11 @@
 // mask_posterior (289-292), pixel likelihood (309-312) and leave-one-out likelihood
 // (321-328), plus the sums the parameter-free layer-norm (376-395) needs.  No [B,K,C,H,W]
 // intermediate of the reference (K_log_likelihood, log(mask), r, ...) touches HBM.
+//
+// mixture_kernel: libm arithmetic (exact fp32 mode).  mixture_fast_kernel: the same pass for the tensor-core modes
+// (a third fewer instructions, MUFU exp / log).  Both write either raw fp32 aux channels (`auxs`, consumed by
+// assemble_kernel / assemble16_kernel below: fp32 mode, training tape, shapes outside the fused first layer) or, FUSED,
+// the refinement network's input in the form refine_l0f_kernel (refine_tc.cu) consumes -- then there is no assembly pass.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -19,6 +19,11 @@
 //     two coordinate channels, whose convolution does not depend on the data), apply ELU and store the
 //     16-bit chunk-planar activation of the next layer.
 // Layer 0 therefore contracts over 15 data channels padded to 16 (one K step per tap) instead of 17.
+//
+// Two kernels: refine_tc_kernel (the gather formulation above: layers >= 1, and layer 0 of shapes the fused kernel does
+// not cover) and refine_l0f_kernel (layer 0 of stride-2 3x3 encoders on even image sizes: reads the pixel-mixture
+// kernel's output directly, applies the layer-norms and packs the aux stack while staging its operand, stride-2 taps as
+// unit-stride UMMA operands over phase-split planes -- see the comment above it).
 #include <stdlib.h>
 
 #include "common.cuh"
